@@ -1,0 +1,115 @@
+"""Seeded synthetic inputs for the reconstruction hot path.
+
+Everything here is deterministic from integer seeds through ``numpy.random.default_rng``
+(PCG64 - stable across numpy versions and machines), so the CPU oracle, the golden
+fixtures made in the authoring container and the CUDA path on the GPU box all see
+identical tensors.  Nothing here touches the oracle or the CUDA extension.
+
+Init rule restated from the reference (`net_util.py:13-25`): Conv weights N(0, 0.02),
+biases 0.  ``bias_std`` > 0 is used by the parity tests so the bias path is exercised.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SEED_WEIGHTS = 0
+SEED_FEAT_COARSE = 1
+SEED_FEAT_FINE = 2
+SEED_POINTS = 3
+SEED_PILOT = 7
+
+
+def mlp_state(filter_channels, res_layers, seed, bias_std=0.0, std=0.02):
+    """state_dict of a reference ``MLP`` (`MLP.py:19-30`): keys ``filters.{i}.weight|bias``."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for i in range(len(filter_channels) - 1):
+        cin = filter_channels[i] + (filter_channels[0] if i in res_layers else 0)
+        cout = filter_channels[i + 1]
+        w = rng.standard_normal((cout, cin, 1)).astype(np.float32) * np.float32(std)
+        b = (rng.standard_normal((cout,)).astype(np.float32) * np.float32(bias_std))
+        sd["filters.%d.weight" % i] = torch.from_numpy(w)
+        sd["filters.%d.bias" % i] = torch.from_numpy(b)
+    return sd
+
+
+def band_limited_features(channels, height, width, seed, base=8, scale=1.0):
+    """Smooth feature map: base x base Gaussian noise, bicubic upsampling."""
+    rng = np.random.default_rng(seed)
+    z = torch.from_numpy(rng.standard_normal((1, channels, base, base)).astype(np.float32))
+    f = F.interpolate(z, size=(height, width), mode="bicubic", align_corners=False)
+    return (f * scale).contiguous()
+
+
+def default_calib():
+    """`readData.py:88-94`: diag(1, -1, 1, 1), shape [1, 4, 4] float32."""
+    c = torch.eye(4, dtype=torch.float32)
+    c[1, 1] = -1.0
+    return c[None].contiguous()
+
+
+def scaled_calib(scale=1.25, shift=(0.03125, -0.0625, 0.015625)):
+    """A scale+shift orthographic calibration (exactly representable entries)."""
+    c = torch.eye(4, dtype=torch.float32)
+    c[0, 0], c[1, 1], c[2, 2] = scale, -scale, scale
+    c[0, 3], c[1, 3], c[2, 3] = shift
+    return c[None].contiguous()
+
+
+def random_points(n, seed=SEED_POINTS, lo=-1.1, hi=1.1):
+    """[1, 3, n] float32 points, slightly overshooting [-1, 1] so the masks are exercised."""
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(lo, hi, size=(1, 3, n)).astype(np.float32)
+    return torch.from_numpy(p)
+
+
+def boost_depth_column(coarse_sd, z_index=256, gain=100.0):
+    """random-init gives almost no depth dependence; scale the z column
+    of coarse L0 (`PIFuNetwNML.py:128-129`: z is input channel 256)."""
+    w = coarse_sd["filters.0.weight"].clone()
+    w[:, z_index, :] *= gain
+    coarse_sd["filters.0.weight"] = w
+    return coarse_sd
+
+
+def calibrate_last_layer(fine_sd, last_index, pilot_preds, target_sigma=6.0, occupied=0.05):
+    """Rescale only the last fine conv so that ~``occupied`` of the field exceeds 0.5 and
+    logits saturate.  ``pilot_preds`` are sigmoid outputs of the
+    un-calibrated net on pilot points; the same tensors then go to every implementation."""
+    p = np.clip(np.asarray(pilot_preds, dtype=np.float64).ravel(), 1e-12, 1 - 1e-12)
+    logit = np.log(p) - np.log1p(-p)
+    g = target_sigma / max(float(logit.std()), 1e-12)
+    q = float(np.quantile(logit, 1.0 - occupied))
+    w = fine_sd["filters.%d.weight" % last_index]
+    b = fine_sd["filters.%d.bias" % last_index]
+    fine_sd["filters.%d.weight" % last_index] = (w.double() * g).float()
+    fine_sd["filters.%d.bias" % last_index] = ((b.double() - q) * g).float()
+    return fine_sd
+
+
+def synthetic_rgbd(size, seed):
+    """RGB + depth(x3) image in [-1, 1], [1, 6, size, size] (recipe of SURVEY §8(d))."""
+    rng = np.random.default_rng(seed)
+    lin = np.linspace(-1.0, 1.0, size, dtype=np.float64)
+    y, x = np.meshgrid(lin, lin, indexing="ij")
+    e = 1.0 - (x / 0.35) ** 2 - (y / 0.8) ** 2
+    m = 1.0 / (1.0 + np.exp(-20.0 * e))
+    pattern = np.stack([np.cos(9 * x) * np.cos(7 * y), np.cos(5 * x + 1), np.cos(11 * y + 2)], 0)
+    rgb = np.clip(m * pattern + (m - 1.0) + 0.05 * rng.standard_normal((3, size, size)), -1, 1)
+    d = np.clip(m * (2.0 * np.sqrt(np.maximum(0.0, e)) - 1.0) + (m - 1.0), -1, 1)
+    img = np.concatenate([rgb, np.repeat(d[None], 3, 0)], 0).astype(np.float32)
+    return torch.from_numpy(img[None])
+
+
+def make_problem(seed=SEED_WEIGHTS, bias_std=0.0, depth_gain=100.0, feat_scale=1.0,
+                 coarse_dims=(257, 1024, 512, 256, 128, 1), coarse_res=(2, 3, 4),
+                 fine_dims=(272, 512, 256, 128, 1), fine_res=(1, 2)):
+    """Weights + feature maps of the two-level net, un-calibrated."""
+    coarse = mlp_state(list(coarse_dims), list(coarse_res), seed, bias_std)
+    fine = mlp_state(list(fine_dims), list(fine_res), seed + 1000, bias_std)
+    if depth_gain != 1.0:
+        boost_depth_column(coarse, coarse_dims[0] - 1, depth_gain)
+    feat_c = band_limited_features(coarse_dims[0] - 1, 128, 128, SEED_FEAT_COARSE, scale=feat_scale)
+    feat_f = band_limited_features(fine_dims[0] - coarse_dims[3], 512, 512, SEED_FEAT_FINE,
+                                   scale=feat_scale)
+    return dict(coarse=coarse, fine=fine, feat_coarse=feat_c, feat_fine=feat_f)
