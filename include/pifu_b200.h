@@ -1,0 +1,100 @@
+/* pifu_b200.h - C ABI of libpifu_b200.so: the B200-native reconstruction hot path of
+ * RGB-D-PIFuHD (occupancy query on explicit points / dense lattice / octree, marching cubes).
+ *
+ * The reference has no FFI or operator registry (it is pure Python); its boundary for this
+ * path is the Python object API.  Each entry point below names the reference interface it
+ * replaces (file:line under the reference tree).  The Python layer in
+ * `rgb-d-pifuhd_b200/` binds these with ctypes and keeps the reference's signatures
+ * (see INTEGRATION.md).
+ *
+ * Conventions: every function returns 0 on success and -1 on failure (never throws);
+ * `pifu_last_error()` gives the message.  "device pointer" = CUDA device memory on the
+ * context's device; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * A context owns one workspace: calls on the same context must be issued from one thread
+ * and are ordered on the stream they are given.
+ */
+#ifndef PIFU_B200_H
+#define PIFU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pifu_ctx pifu_ctx;
+
+#define PIFU_LEVEL_COARSE 0 /* PIFuNetwNML  (PIFuNetwNML.py:17-71)  */
+#define PIFU_LEVEL_FINE 1   /* PIFuMRNet    (PIFuMRNet.py:14-57)    */
+
+#define PIFU_GEMM_TCGEN05 0 /* tensor-core layer kernel (default, product path) */
+#define PIFU_GEMM_SIMT 1    /* CUDA-core cross-check of the same operands (tests only) */
+
+const char* pifu_last_error(void);
+int pifu_abi_version(void);
+
+/* One context per device. */
+int pifu_create(int device, pifu_ctx** out);
+void pifu_destroy(pifu_ctx* ctx);
+
+/* Snapshot one MLP (replaces reading `net.mlp` - MLP.py:13-40 - at query time).
+ * filter_channels[n_channels], res_layers[n_res], merge_layer as given to MLP.__init__
+ * (<= 0 means len(filter_channels)//2, MLP.py:25).  weights[i] / biases[i] are device
+ * pointers to Conv1d i's fp32 weight [Cout][Cin] and bias [Cout].  Only mlp_norm == 'none'
+ * stacks are accepted (MLP.py:66-67); hidden widths must be multiples of 128 and the last
+ * hidden width 128 or 256. */
+int pifu_set_mlp(pifu_ctx* ctx, int level, int n_channels, const int* filter_channels, int n_res,
+                 const int* res_layers, int merge_layer, const float* const* weights,
+                 const float* const* biases, void* stream);
+
+/* Snapshot a feature map (replaces reading `net.im_feat_list[-1]`, PIFuNetwNML.py:94-97 /
+ * PIFuMRNet.py:114-117): device fp32 NCHW [1][C][H][W]. */
+int pifu_set_features(pifu_ctx* ctx, int level, const float* nchw, int C, int H, int W, void* stream);
+
+/* projection: 0 orthogonal / 1 perspective (BasePIFuNet.py:79); DepthNormalizer constants
+ * z * z_mul / z_div (DepthNormalizer.py:23: loadSize // 2 and z_size). */
+int pifu_set_options(pifu_ctx* ctx, int perspective, float z_mul, float z_div);
+int pifu_set_gemm_impl(pifu_ctx* ctx, int impl);
+int pifu_set_chunk_tiles(pifu_ctx* ctx, int tiles_of_128_points);
+
+/* Occupancy of explicit points.  Replaces PIFuNetwNML.query (PIFuNetwNML.py:99-141; levels = 1)
+ * and PIFuMRNet.query (PIFuMRNet.py:119-186; levels = 2) for one view/crop.
+ * points: device fp32, reference layout [3][n] with row stride `pstride` elements.
+ * calib_local / calib_global: host, 16 floats row-major (4x4).  For levels == 1 both must be
+ * the same matrix.  Outputs are device pointers, any may be NULL:
+ *   out_pred     [n]      preds (mask * sigmoid), BasePIFuNet.get_preds (BasePIFuNet.py:136-142)
+ *   out_pred_low [n]      coarse prediction (netG.intermediate_preds_list[-1]); levels == 2 only
+ *   out_phi      [C][n]   coarse merge-layer feature `netG.phi` (row stride n) */
+#define PIFU_QUERY_NO_MASK 1 /* raw sigmoid, no in-bounds mask: calc_normal (PIFuMRNet.py:232-237) */
+int pifu_query(pifu_ctx* ctx, int levels, int flags, const float* points, long long pstride, long long n,
+               const float* calib_local, const float* calib_global, float* out_pred,
+               float* out_pred_low, float* out_phi, void* stream);
+
+/* Occupancy on a run of lattice points, never materialising coordinates.  Replaces
+ * create_grid + the calib pre-transform + eval_grid/batch_eval (mesh_util.py:12-38, 59-65,
+ * 98-120).  Lattice point id = (i*R1 + j)*R2 + k (C order of the reference's sdf volume);
+ * ids [id_begin, id_end) are evaluated into out[0 .. id_end-id_begin) (device fp32).
+ * calib: host 16 floats; calib_inv: host 16 doubles = numpy.linalg.inv(calib) as the
+ * reference computes it on the host (mesh_util.py:62). */
+int pifu_eval_grid(pifu_ctx* ctx, int levels, int R0, int R1, int R2, long long id_begin,
+                   long long id_end, const float* calib, const double* calib_inv, float* out,
+                   void* stream);
+
+/* Same, for an explicit list of lattice ids (device int64 [n]); out[p] = occupancy of ids[p]. */
+int pifu_eval_lattice_ids(pifu_ctx* ctx, int levels, int R0, int R1, int R2, const long long* ids,
+                          long long n, const float* calib, const double* calib_inv, float* out,
+                          void* stream);
+
+/* Number of kernels launched by this context since creation (bench accounting). */
+long long pifu_launch_count(pifu_ctx* ctx);
+
+/* Test hook: one layer, Y = act(W X^T + b), through the layer kernel (synchronous).  All
+ * pointers are device fp32: X [M][K] (points x channels), W [N][K], b [N]; Y is channel-major
+ * [N][M] like the reference's [C, N] activations. */
+int pifu_debug_gemm(pifu_ctx* ctx, const float* X, const float* W, const float* b, int M, int K, int N,
+                    int leaky, float* Y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIFU_B200_H */

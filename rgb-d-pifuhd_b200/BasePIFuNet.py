@@ -1,0 +1,48 @@
+"""Base class mirroring the attributes callers of the reference read (`BasePIFuNet.py:67-148`)."""
+import torch
+import torch.nn as nn
+
+
+def _not_hot_path(what):
+    raise NotImplementedError("%s is outside the reconstruction hot path this package replaces" % what)
+
+
+def orthogonal(points, calib, transform=None):
+    """`BasePIFuNet.py:25-43` - kept for callers that project by hand (`reconstruction.py:113`)."""
+    if transform is not None:
+        _not_hot_path("screen-space `transform`")
+    return torch.baddbmm(calib[:, :3, 3:4], calib[:, :3, :3], points)
+
+
+def perspective(points, calib, transform=None):
+    """`BasePIFuNet.py:45-65`."""
+    if transform is not None:
+        _not_hot_path("screen-space `transform`")
+    homo = torch.baddbmm(calib[:, :3, 3:4], calib[:, :3, :3], points)
+    return torch.cat([homo[:, :2, :] / homo[:, 2:3, :], homo[:, 2:3, :]], 1)
+
+
+class BasePIFuNet(nn.Module):
+    def __init__(self, projection_mode="orthogonal", criteria=None):
+        super().__init__()
+        self.name = "base"
+        self.criteria = criteria
+        # any string other than 'orthogonal' selects perspective (`BasePIFuNet.py:79`)
+        self.projection_mode = projection_mode
+        self.projection = orthogonal if projection_mode == "orthogonal" else perspective
+        self.preds = None
+        self.labels = None
+        self.nmls = None
+        self.labels_nml = None
+        self.preds_surface = None
+
+    @property
+    def is_perspective(self):
+        return self.projection is not orthogonal
+
+    def get_preds(self):
+        """`BasePIFuNet.py:136-142`."""
+        return self.preds
+
+    def get_error(self, gamma=None):
+        _not_hot_path("training loss")

@@ -7,3 +7,9 @@ compute goes through ``libpifu_b200.so`` (hand-written sm_100a CUDA behind a C A
 library raises.
 """
 __version__ = "0.1.0"
+
+from . import config, synthetic                      # noqa: E402,F401
+from .MLP import MLP                                 # noqa: E402,F401
+from .PIFuNetwNML import PIFuNetwNML                 # noqa: E402,F401
+from .PIFuMRNet import PIFuMRNet                     # noqa: E402,F401
+from .engine import get_engine                       # noqa: E402,F401

@@ -1,0 +1,74 @@
+"""ctypes binding of libpifu_b200.so (C ABI in include/pifu_b200.h).
+
+There is no fallback: if the library is missing it is built with nvcc when a toolchain is
+present, otherwise importing a compute entry point raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpifu_b200.so")
+_lib = None
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_ll_p = ctypes.POINTER(ctypes.c_longlong)
+VP = ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/pifu_b200.h declares
+SIGNATURES = {
+    "pifu_last_error": (ctypes.c_char_p, []),
+    "pifu_abi_version": (ctypes.c_int, []),
+    "pifu_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(VP)]),
+    "pifu_destroy": (None, [VP]),
+    "pifu_set_mlp": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p,
+                                    ctypes.c_int, ctypes.POINTER(VP), ctypes.POINTER(VP), VP]),
+    "pifu_set_features": (ctypes.c_int, [VP, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, VP]),
+    "pifu_set_options": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
+    "pifu_set_gemm_impl": (ctypes.c_int, [VP, ctypes.c_int]),
+    "pifu_set_chunk_tiles": (ctypes.c_int, [VP, ctypes.c_int]),
+    "pifu_query": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_longlong, ctypes.c_longlong,
+                                  c_float_p, c_float_p, VP, VP, VP, VP]),
+    "pifu_eval_grid": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_longlong, ctypes.c_longlong, c_float_p, c_double_p, VP, VP]),
+    "pifu_eval_lattice_ids": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             VP, ctypes.c_longlong, c_float_p, c_double_p, VP, VP]),
+    "pifu_launch_count": (ctypes.c_longlong, [VP]),
+    "pifu_debug_gemm": (ctypes.c_int, [VP, VP, VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, VP, VP]),
+}
+
+
+class PifuError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load (building first if needed) and type the library.  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise PifuError("libpifu_b200.so is missing and could not be built (%s). "
+                            "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root; "
+                            "there is no CPU fallback." % (e,))
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PifuError(load().pifu_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,575 @@
+// Context + C ABI (include/pifu_b200.h): snapshots of the two MLPs and feature maps, the
+// per-chunk workspace in HBM, and the layer schedule of one query.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pifu_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+namespace pifu {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+}  // namespace pifu
+
+using namespace pifu;
+
+// ----------------------------------------------------------------------------- context
+namespace {
+
+struct SegRef { int buf; int nkb; };          // whole activation buffer used as a K segment
+
+struct Layer {
+    int cout = 0, cin = 0;
+    int BN = 0, num_kb = 0;
+    std::vector<SegRef> segs;
+    uint8_t* w = nullptr;                      // packed fp16 blocks
+    float* bias = nullptr;
+    int out_buf = -1;
+};
+
+struct Level {
+    bool set = false;
+    std::vector<int> dims;
+    std::vector<int> res;
+    int merge = -1;                            // index of the layer whose output is the `phi` tap
+    int n_layers = 0;
+    std::vector<Layer> hidden;                 // layers 0 .. n_layers-2
+    float* head_w = nullptr;                   // last layer, packed order, fp32
+    float head_b = 0.f;
+    std::vector<SegRef> head_segs;
+    std::vector<SegRef> in_segs;               // the level's input row as K segments
+    float* feat = nullptr;                     // NHWC fp32
+    int C = 0, H = 0, W = 0;
+    bool is_res(int i) const { for (int r : res) if (r == i) return true; return false; }
+};
+
+struct Buffer { int nkb = 0; uint8_t* ptr = nullptr; };
+
+}  // namespace
+
+struct pifu_ctx {
+    int device = 0;
+    int num_sms = 148;
+    int gemm_impl = PIFU_GEMM_TCGEN05;
+    int chunk_tiles = 296;
+    int perspective = 0;
+    float z_mul = 512.f, z_div = 200.f;
+    Level lv[2];
+    std::vector<Buffer> bufs;                  // activation buffers, sized for chunk_tiles
+    int buf_F = -1, buf_FF = -1;
+    int n_coarse_bufs = 0;                     // buffers owned by the coarse plan come first
+    int alloc_tiles = 0;
+    uint8_t* mask = nullptr;
+    float* pred_chunk = nullptr;               // scratch for scattered outputs
+    long long launches = 0;
+    pifu::OctreeState* octree = nullptr;
+    pifu::McState* mc = nullptr;
+};
+
+namespace {
+
+int new_buffer(pifu_ctx* c, int nkb) {
+    Buffer b;
+    b.nkb = nkb;
+    c->bufs.push_back(b);
+    return static_cast<int>(c->bufs.size()) - 1;
+}
+
+void free_workspace(pifu_ctx* c) {
+    for (auto& b : c->bufs) if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; }
+    if (c->mask) { cudaFree(c->mask); c->mask = nullptr; }
+    if (c->pred_chunk) { cudaFree(c->pred_chunk); c->pred_chunk = nullptr; }
+    c->alloc_tiles = 0;
+}
+
+int ensure_workspace(pifu_ctx* c) {
+    if (c->alloc_tiles == c->chunk_tiles) {
+        bool ok = true;
+        for (auto& b : c->bufs) if (!b.ptr) ok = false;
+        if (ok) return 0;
+    } else {
+        free_workspace(c);
+    }
+    for (auto& b : c->bufs)
+        if (!b.ptr) PIFU_CUDA(cudaMalloc(&b.ptr, static_cast<size_t>(c->chunk_tiles) * b.nkb * ABLOCK_BYTES));
+    if (!c->mask) PIFU_CUDA(cudaMalloc(&c->mask, static_cast<size_t>(c->chunk_tiles) * TILE_M));
+    if (!c->pred_chunk) PIFU_CUDA(cudaMalloc(&c->pred_chunk, static_cast<size_t>(c->chunk_tiles) * TILE_M * sizeof(float)));
+    c->alloc_tiles = c->chunk_tiles;
+    return 0;
+}
+
+void free_level(Level& L) {
+    for (auto& l : L.hidden) { if (l.w) cudaFree(l.w); if (l.bias) cudaFree(l.bias); }
+    L.hidden.clear();
+    if (L.head_w) { cudaFree(L.head_w); L.head_w = nullptr; }
+    L.set = false;
+}
+
+int gemm_bn(int N, bool head) {
+    if (N % 256 == 0 && (!head || N == 256)) return 256;
+    if (N % 128 == 0 && (!head || N == 128)) return 128;
+    return 0;
+}
+
+ASeg make_seg(const pifu_ctx* c, const SegRef& r) {
+    ASeg s;
+    s.base = c->bufs[r.buf].ptr;
+    s.kb_stride = c->bufs[r.buf].nkb;
+    s.kb_off = 0;
+    s.nkb = r.nkb;
+    return s;
+}
+
+int run_gemm(pifu_ctx* c, const GemmArgs& g, cudaStream_t s) {
+    c->launches += 1;
+    if (c->gemm_impl == PIFU_GEMM_SIMT) { c->launches += g.head_w ? 1 : 0; return launch_gemm_simt(g, s); }
+    return launch_gemm_tc(g, c->num_sms, s);
+}
+
+// hidden layers [first, last] of a level; the fused last layer rides on layer n_layers-2
+int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_tiles, int n_valid,
+               float* head_out, int mask_bit, cudaStream_t s) {
+    // mask_bit < 0: the caller wants the raw sigmoid (calc_normal, `PIFuMRNet.py:232-237`)
+    for (int i = first; i <= last; ++i) {
+        Layer& l = L.hidden[i];
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.nseg = static_cast<int>(l.segs.size());
+        for (int k = 0; k < g.nseg; ++k) g.seg[k] = make_seg(c, l.segs[k]);
+        g.num_kb = l.num_kb;
+        g.w = l.w;
+        g.bias = l.bias;
+        g.N = l.cout;
+        g.m_tiles = m_tiles;
+        g.leaky = 1;
+        g.n_valid = n_valid;
+        const bool with_head = (i == L.n_layers - 2) && head_out != nullptr;
+        const bool tap = coarse && (i == L.merge);   // `phi` (MLP.py:70-71)
+        const bool feeds_next = (i < L.n_layers - 2);
+        if (feeds_next || tap || !with_head) {
+            g.out = c->bufs[l.out_buf].ptr;
+            g.out_kb_stride = c->bufs[l.out_buf].nkb;
+        }
+        if (with_head) {
+            g.head_w = L.head_w;
+            g.head_b = L.head_b;
+            g.head_nseg = static_cast<int>(L.head_segs.size());
+            for (int k = 0; k < g.head_nseg; ++k) g.head_seg[k] = make_seg(c, L.head_segs[k]);
+            g.head_out = head_out;
+            g.mask = mask_bit >= 0 ? c->mask : nullptr;
+            g.mask_bit = mask_bit >= 0 ? mask_bit : 0;
+        }
+        if (run_gemm(c, g, s)) return -1;
+    }
+    return 0;
+}
+
+struct QueryOut {
+    float* pred = nullptr;       // chunk-relative destination of preds
+    float* pred_low = nullptr;
+    float* phi = nullptr;        // [C][ld] destination of the coarse tap
+    long long phi_ld = 0;
+    bool no_mask = false;
+};
+
+int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const float* cl, const float* cg,
+              const QueryOut& o, cudaStream_t s) {
+    Level& LC = c->lv[0];
+    Level& LF = c->lv[1];
+    const int m_tiles = (n + TILE_M - 1) / TILE_M;
+    GatherArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.src = src;
+    ga.n = n;
+    memcpy(ga.cg, cg, 12 * sizeof(float));
+    memcpy(ga.cl, cl, 12 * sizeof(float));
+    ga.perspective = c->perspective;
+    ga.z_mul = c->z_mul;
+    ga.z_div = c->z_div;
+    ga.feat_c = LC.feat; ga.Hc = LC.H; ga.Wc = LC.W; ga.Cc = LC.C;
+    ga.F = c->bufs[c->buf_F].ptr; ga.kbF = c->bufs[c->buf_F].nkb;
+    if (levels == 2) {
+        ga.feat_f = LF.feat; ga.Hf = LF.H; ga.Wf = LF.W; ga.Cf = LF.C;
+        ga.FF = c->bufs[c->buf_FF].ptr; ga.kbFF = c->bufs[c->buf_FF].nkb;
+    }
+    ga.mask = c->mask;
+    c->launches += 1;
+    if (launch_gather(ga, s)) return -1;
+
+    if (levels == 1) {
+        if (run_layers(c, LC, true, 0, LC.n_layers - 2, m_tiles, n, o.pred, o.no_mask ? -1 : 0, s)) return -1;
+    } else {
+        const bool want_low = o.pred_low != nullptr;
+        if (run_layers(c, LC, true, 0, want_low ? LC.n_layers - 2 : LC.merge, m_tiles, n,
+                       want_low ? o.pred_low : nullptr, o.no_mask ? -1 : 0, s)) return -1;
+        if (run_layers(c, LF, false, 0, LF.n_layers - 2, m_tiles, n, o.pred, o.no_mask ? -1 : 1, s)) return -1;
+    }
+    if (o.phi != nullptr) {
+        const Layer& tap = LC.hidden[LC.merge];
+        c->launches += 1;
+        if (launch_unblock(c->bufs[tap.out_buf].ptr, c->bufs[tap.out_buf].nkb, 0, tap.cout, n, o.phi,
+                           o.phi_ld, s)) return -1;
+    }
+    return 0;
+}
+
+int check_ready(pifu_ctx* c, int levels) {
+    if (!c) { set_error("null context"); return -1; }
+    if (levels != 1 && levels != 2) { set_error("levels must be 1 or 2"); return -1; }
+    for (int l = 0; l < levels; ++l) {
+        if (!c->lv[l].set) { set_error("MLP of level %d not set (pifu_set_mlp)", l); return -1; }
+        if (!c->lv[l].feat) { set_error("feature map of level %d not set (pifu_set_features)", l); return -1; }
+    }
+    if (c->lv[0].C + 1 != c->lv[0].dims[0]) {
+        set_error("coarse feature channels %d + 1 != mlp_dim[0] %d", c->lv[0].C, c->lv[0].dims[0]); return -1;
+    }
+    if (levels == 2) {
+        const int cphi = c->lv[0].dims[c->lv[0].merge + 1];
+        if (c->lv[1].C + cphi != c->lv[1].dims[0]) {
+            set_error("fine feature channels %d + phi %d != mlp_dim[0] %d", c->lv[1].C, cphi, c->lv[1].dims[0]);
+            return -1;
+        }
+    }
+    return ensure_workspace(c);
+}
+
+void lattice_source(PointSource& src, int R0, int R1, int R2, const double* calib_inv) {
+    memset(&src, 0, sizeof(src));
+    src.mode = 1;
+    src.R0 = R0; src.R1 = R1; src.R2 = R2;
+    // mesh_util.py:27-33 with the default bounding box [-1, 1]^3 (b_min/b_max are ignored by
+    // reconstruction(), mesh_util.py:59): step = 2/res, offset = -1
+    src.step[0] = 2.0 / R0; src.step[1] = 2.0 / R1; src.step[2] = 2.0 / R2;
+    src.bmin[0] = src.bmin[1] = src.bmin[2] = -1.0;
+    memcpy(src.cinv, calib_inv, 12 * sizeof(double));
+}
+
+}  // namespace
+
+namespace pifu {
+// used by octree.cu: evaluate `n` lattice ids (device list) into out (device fp32 [n])
+int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
+             const float* calib, const double* calib_inv, float* out, cudaStream_t s) {
+    PointSource src;
+    lattice_source(src, R0, R1, R2, calib_inv);
+    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
+    for (long long b = 0; b < n; b += chunk) {
+        const int m = static_cast<int>(n - b < chunk ? n - b : chunk);
+        src.ids = ids + b;
+        QueryOut o;
+        o.pred = out + b;
+        if (run_chunk(c, levels, src, m, calib, calib, o, s)) return -1;
+    }
+    return 0;
+}
+int ctx_num_sms(pifu_ctx* c) { return c->num_sms; }
+void ctx_count_launch(pifu_ctx* c, int n) { c->launches += n; }
+OctreeState*& ctx_octree(pifu_ctx* c) { return c->octree; }
+McState*& ctx_mc(pifu_ctx* c) { return c->mc; }
+}  // namespace pifu
+
+// ----------------------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* pifu_last_error(void) { return g_error.c_str(); }
+int pifu_abi_version(void) { return 1; }
+
+int pifu_create(int device, pifu_ctx** out) {
+    if (!out) { set_error("null out pointer"); return -1; }
+    PIFU_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PIFU_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return -1;
+    }
+    pifu_ctx* c = new pifu_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->chunk_tiles = 2 * c->num_sms;
+    if (const char* e = getenv("PIFU_CHUNK_TILES")) { int v = atoi(e); if (v > 0) c->chunk_tiles = v; }
+    if (const char* e = getenv("PIFU_GEMM_IMPL")) { if (!strcmp(e, "simt")) c->gemm_impl = PIFU_GEMM_SIMT; }
+    *out = c;
+    return 0;
+}
+
+void pifu_destroy(pifu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_workspace(c);
+    for (int l = 0; l < 2; ++l) { free_level(c->lv[l]); if (c->lv[l].feat) cudaFree(c->lv[l].feat); }
+    pifu::octree_free(c->octree);
+    pifu::mc_free(c->mc);
+    delete c;
+}
+
+int pifu_set_options(pifu_ctx* c, int perspective, float z_mul, float z_div) {
+    if (!c) { set_error("null context"); return -1; }
+    c->perspective = perspective ? 1 : 0;
+    c->z_mul = z_mul;
+    c->z_div = z_div;
+    return 0;
+}
+
+int pifu_set_gemm_impl(pifu_ctx* c, int impl) {
+    if (!c || (impl != PIFU_GEMM_TCGEN05 && impl != PIFU_GEMM_SIMT)) { set_error("bad gemm impl"); return -1; }
+    c->gemm_impl = impl;
+    return 0;
+}
+
+int pifu_set_chunk_tiles(pifu_ctx* c, int tiles) {
+    if (!c || tiles <= 0) { set_error("bad chunk size"); return -1; }
+    c->chunk_tiles = tiles;
+    return 0;
+}
+
+long long pifu_launch_count(pifu_ctx* c) { return c ? c->launches : 0; }
+
+int pifu_set_features(pifu_ctx* c, int level, const float* nchw, int C, int H, int W, void* stream) {
+    if (!c || level < 0 || level > 1 || !nchw) { set_error("bad arguments to pifu_set_features"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    Level& L = c->lv[level];
+    if (L.feat && (L.C != C || L.H != H || L.W != W)) { cudaFree(L.feat); L.feat = nullptr; }
+    if (!L.feat) PIFU_CUDA(cudaMalloc(&L.feat, static_cast<size_t>(C) * H * W * sizeof(float)));
+    L.C = C; L.H = H; L.W = W;
+    c->launches += 1;
+    return launch_nchw_to_nhwc(nchw, L.feat, C, H * W, static_cast<cudaStream_t>(stream));
+}
+
+int pifu_set_mlp(pifu_ctx* c, int level, int n_channels, const int* ch, int n_res, const int* res_layers,
+                 int merge_layer, const float* const* weights, const float* const* biases, void* stream) {
+    if (!c || level < 0 || level > 1 || n_channels < 3 || !ch || !weights || !biases) {
+        set_error("bad arguments to pifu_set_mlp"); return -1;
+    }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (level == 1 && !c->lv[0].set) { set_error("set the coarse MLP before the fine one"); return -1; }
+    Level& L = c->lv[level];
+    if (level == 0 && c->lv[1].set) free_level(c->lv[1]);      // fine plan refers to coarse buffers
+    free_level(L);
+    if (level == 0) {
+        free_workspace(c);
+        c->bufs.clear();
+        c->buf_F = c->buf_FF = -1;
+        c->n_coarse_bufs = 0;
+    } else {
+        for (size_t b = c->n_coarse_bufs; b < c->bufs.size(); ++b)
+            if (c->bufs[b].ptr) cudaFree(c->bufs[b].ptr);
+        c->bufs.resize(c->n_coarse_bufs);
+        c->buf_FF = -1;
+    }
+    L.dims.assign(ch, ch + n_channels);
+    L.res.assign(res_layers, res_layers + n_res);
+    L.n_layers = n_channels - 1;
+    L.merge = merge_layer > 0 ? merge_layer : n_channels / 2;   // MLP.py:25
+    if (L.dims.back() != 1) { set_error("last MLP width must be 1, got %d", L.dims.back()); return -1; }
+    for (int i = 1; i < n_channels - 1; ++i)
+        if (L.dims[i] % 128) { set_error("hidden width %d is not a multiple of 128", L.dims[i]); return -1; }
+    const int last_hidden = L.dims[n_channels - 2];
+    if (last_hidden != 128 && last_hidden != 256) {
+        set_error("last hidden width must be 128 or 256, got %d", last_hidden); return -1;
+    }
+    if (level == 0 && (L.merge < 0 || L.merge > L.n_layers - 2)) {
+        set_error("merge_layer %d is not a hidden layer", L.merge); return -1;
+    }
+
+    // ---- the level's input row as K segments + the map packed column -> input channel
+    std::vector<std::vector<int>> seg_cols;     // per input segment: source channel per packed column
+    L.in_segs.clear();
+    if (level == 0) {
+        const int cf = L.dims[0] - 1;           // feature channels; channel cf is z (PIFuNetwNML.py:128-129)
+        if (cf % 8) { set_error("coarse feature channels %d not a multiple of 8", cf); return -1; }
+        const int nkb = (cf + 2 + KB - 1) / KB;
+        c->buf_F = new_buffer(c, nkb);
+        std::vector<int> m(nkb * KB, -1);
+        for (int k = 0; k < cf; ++k) m[k] = k;
+        m[cf] = cf;                             // z_hi
+        m[cf + 1] = cf;                         // z_lo (same weight column)
+        L.in_segs.push_back({c->buf_F, nkb});
+        seg_cols.push_back(m);
+    } else {
+        Level& G = c->lv[0];
+        const int cphi = G.dims[G.merge + 1];
+        const int cf = L.dims[0] - cphi;        // input order [fine feat ; phi] (PIFuMRNet.py:170-171)
+        if (cf <= 0 || cf % 8) { set_error("fine feature channels %d unsupported", cf); return -1; }
+        const int phi_buf = G.hidden[G.merge].out_buf;
+        std::vector<int> mp(cphi, 0);
+        for (int k = 0; k < cphi; ++k) mp[k] = cf + k;
+        L.in_segs.push_back({phi_buf, cphi / KB});
+        seg_cols.push_back(mp);
+        const int nkb = (cf + KB - 1) / KB;
+        c->buf_FF = new_buffer(c, nkb);
+        std::vector<int> mf(nkb * KB, -1);
+        for (int k = 0; k < cf; ++k) mf[k] = k;
+        L.in_segs.push_back({c->buf_FF, nkb});
+        seg_cols.push_back(mf);
+    }
+
+    // ---- hidden layers
+    L.hidden.resize(L.n_layers - 1);
+    int prev_buf = -1;
+    for (int i = 0; i < L.n_layers; ++i) {
+        const bool uses_input = (i == 0) || L.is_res(i);
+        const int ycols = i == 0 ? 0 : L.dims[i];
+        const int cin = ycols + (uses_input ? L.dims[0] : 0);
+        std::vector<int> colmap;
+        std::vector<SegRef> segs;
+        if (i > 0) {
+            segs.push_back({prev_buf, ycols / KB});
+            for (int k = 0; k < ycols; ++k) colmap.push_back(k);            // cat[y, input] (MLP.py:61-64)
+        }
+        if (uses_input) {
+            for (size_t sgi = 0; sgi < L.in_segs.size(); ++sgi) {
+                segs.push_back(L.in_segs[sgi]);
+                for (int src : seg_cols[sgi]) colmap.push_back(src < 0 ? -1 : ycols + src);
+            }
+        }
+        if (static_cast<int>(segs.size()) > MAX_SEGS) { set_error("too many K segments"); return -1; }
+        const int num_kb = static_cast<int>(colmap.size()) / KB;
+        if (i < L.n_layers - 1) {
+            Layer& l = L.hidden[i];
+            l.cout = L.dims[i + 1];
+            l.cin = cin;
+            l.segs = segs;
+            l.num_kb = num_kb;
+            l.BN = gemm_bn(l.cout, i == L.n_layers - 2);
+            if (!l.BN) { set_error("unsupported layer width %d", l.cout); return -1; }
+            int* dmap = nullptr;
+            PIFU_CUDA(cudaMalloc(&dmap, colmap.size() * sizeof(int)));
+            PIFU_CUDA(cudaMemcpyAsync(dmap, colmap.data(), colmap.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            PIFU_CUDA(cudaMalloc(&l.w, static_cast<size_t>(l.cout) * num_kb * ROW_BYTES));
+            PIFU_CUDA(cudaMalloc(&l.bias, l.cout * sizeof(float)));
+            PIFU_CUDA(cudaMemcpyAsync(l.bias, biases[i], l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            c->launches += 1;
+            if (launch_pack_weights(weights[i], cin, dmap, num_kb, l.cout, l.BN, l.w, s)) return -1;
+            PIFU_CUDA(cudaStreamSynchronize(s));
+            cudaFree(dmap);
+            l.out_buf = new_buffer(c, l.cout / KB);
+            prev_buf = l.out_buf;
+        } else {
+            // last layer: Conv1d -> 1 (+ sigmoid), kept in fp32 and fused into the previous epilogue
+            std::vector<float> w(cin), hw(colmap.size(), 0.f);
+            PIFU_CUDA(cudaMemcpyAsync(w.data(), weights[i], cin * sizeof(float), cudaMemcpyDeviceToHost, s));
+            PIFU_CUDA(cudaMemcpyAsync(&L.head_b, biases[i], sizeof(float), cudaMemcpyDeviceToHost, s));
+            PIFU_CUDA(cudaStreamSynchronize(s));
+            for (size_t k = 0; k < colmap.size(); ++k) hw[k] = colmap[k] >= 0 ? w[colmap[k]] : 0.f;
+            // z is carried as z_hi + z_lo: both columns take the z weight (already duplicated by colmap)
+            PIFU_CUDA(cudaMalloc(&L.head_w, hw.size() * sizeof(float)));
+            PIFU_CUDA(cudaMemcpyAsync(L.head_w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            PIFU_CUDA(cudaStreamSynchronize(s));
+            L.head_segs.assign(segs.begin() + 1, segs.end());
+        }
+    }
+    if (level == 0) c->n_coarse_bufs = static_cast<int>(c->bufs.size());
+    L.set = true;
+    return 0;
+}
+
+int pifu_query(pifu_ctx* c, int levels, int flags, const float* points, long long pstride, long long n,
+               const float* calib_local, const float* calib_global, float* out_pred, float* out_pred_low,
+               float* out_phi, void* stream) {
+    if (check_ready(c, levels)) return -1;
+    if (!points || !calib_local || !calib_global) { set_error("null points/calib"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PointSource src;
+    memset(&src, 0, sizeof(src));
+    src.mode = 0;
+    src.pstride = pstride;
+    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
+    for (long long b = 0; b < n; b += chunk) {
+        const int m = static_cast<int>(n - b < chunk ? n - b : chunk);
+        src.pts = points + b;
+        QueryOut o;
+        o.pred = out_pred ? out_pred + b : c->pred_chunk;
+        o.pred_low = (levels == 2 && out_pred_low) ? out_pred_low + b : nullptr;
+        o.phi = out_phi ? out_phi + b : nullptr;
+        o.phi_ld = n;
+        o.no_mask = (flags & PIFU_QUERY_NO_MASK) != 0;
+        if (run_chunk(c, levels, src, m, calib_local, calib_global, o, s)) return -1;
+    }
+    return 0;
+}
+
+int pifu_eval_grid(pifu_ctx* c, int levels, int R0, int R1, int R2, long long id_begin, long long id_end,
+                   const float* calib, const double* calib_inv, float* out, void* stream) {
+    if (check_ready(c, levels)) return -1;
+    if (!calib || !calib_inv || !out || id_begin < 0 || id_end < id_begin ||
+        id_end > static_cast<long long>(R0) * R1 * R2) { set_error("bad arguments to pifu_eval_grid"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PointSource src;
+    lattice_source(src, R0, R1, R2, calib_inv);
+    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
+    for (long long b = id_begin; b < id_end; b += chunk) {
+        const int m = static_cast<int>(id_end - b < chunk ? id_end - b : chunk);
+        src.id0 = b;
+        QueryOut o;
+        o.pred = out + (b - id_begin);
+        if (run_chunk(c, levels, src, m, calib, calib, o, s)) return -1;
+    }
+    return 0;
+}
+
+int pifu_eval_lattice_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
+                          const float* calib, const double* calib_inv, float* out, void* stream) {
+    if (check_ready(c, levels)) return -1;
+    if (!calib || !calib_inv || !out || !ids) { set_error("bad arguments to pifu_eval_lattice_ids"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    return pifu::eval_ids(c, levels, R0, R1, R2, ids, n, calib, calib_inv, out, static_cast<cudaStream_t>(stream));
+}
+
+int pifu_debug_gemm(pifu_ctx* c, const float* X, const float* W, const float* b, int M, int K, int N,
+                    int leaky, float* Y, void* stream) {
+    if (!c) { set_error("null context"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int BN = gemm_bn(N, false);
+    if (!BN) { set_error("debug gemm: N must be a multiple of 128"); return -1; }
+    const int nkb = (K + KB - 1) / KB, m_tiles = (M + TILE_M - 1) / TILE_M;
+    uint8_t *xa = nullptr, *wp = nullptr, *yo = nullptr;
+    int* dmap = nullptr;
+    float* bias = nullptr;
+    std::vector<int> colmap(nkb * KB, -1);
+    for (int k = 0; k < K; ++k) colmap[k] = k;
+    PIFU_CUDA(cudaMalloc(&xa, static_cast<size_t>(m_tiles) * nkb * ABLOCK_BYTES));
+    PIFU_CUDA(cudaMalloc(&wp, static_cast<size_t>(N) * nkb * ROW_BYTES));
+    PIFU_CUDA(cudaMalloc(&yo, static_cast<size_t>(m_tiles) * (N / KB) * ABLOCK_BYTES));
+    PIFU_CUDA(cudaMalloc(&dmap, colmap.size() * sizeof(int)));
+    PIFU_CUDA(cudaMalloc(&bias, N * sizeof(float)));
+    PIFU_CUDA(cudaMemcpyAsync(dmap, colmap.data(), colmap.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(bias, b, N * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int rc = launch_pack_weights(W, K, dmap, nkb, N, BN, wp, s);
+    // activations use the same image with 128-row blocks: pack X as "weights" of 128-row tiles
+    if (!rc) rc = launch_pack_rows(X, M, K, nkb, xa, s);
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.nseg = 1;
+    g.seg[0].base = xa; g.seg[0].kb_stride = nkb; g.seg[0].kb_off = 0; g.seg[0].nkb = nkb;
+    g.num_kb = nkb;
+    g.w = wp; g.bias = bias; g.N = N; g.m_tiles = m_tiles;
+    g.out = yo; g.out_kb_stride = N / KB; g.leaky = leaky; g.n_valid = M;
+    if (!rc) rc = run_gemm(c, g, s);
+    // Y comes back channel-major [N][M], the orientation of the reference's [C, N] tensors
+    if (!rc) rc = launch_unblock(yo, N / KB, 0, N, M, Y, M, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(xa); cudaFree(wp); cudaFree(yo); cudaFree(dmap); cudaFree(bias);
+    if (!rc && e != cudaSuccess) { set_error("debug gemm: %s", cudaGetErrorString(e)); rc = -1; }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared definitions: the HBM data layout of operand tiles, error plumbing, kernel prototypes.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace pifu {
+
+// ------------------------------------------------------------------ operand tile layout
+// Every GEMM operand (activations of 128 points, weights of BN output channels) is kept in
+// HBM as a sequence of "k-blocks": [rows] x 64 fp16, stored as the exact shared-memory image
+// the tensor core reads (K-major, 128-byte swizzle): row r occupies 128 contiguous bytes and
+// its eight 16-byte chunks are permuted by (chunk ^ (r & 7)).  A block therefore moves
+// HBM -> SMEM with one linear TMA bulk copy and needs no tensor map.
+constexpr int TILE_M = 128;                 // points per m-tile
+constexpr int KB = 64;                      // fp16 columns per k-block
+constexpr int ROW_BYTES = KB * 2;           // 128
+constexpr int ABLOCK_BYTES = TILE_M * ROW_BYTES;   // 16 KiB
+
+__host__ __device__ __forceinline__ uint32_t sw128_chunk_offset(uint32_t row, uint32_t chunk) {
+    return row * ROW_BYTES + ((chunk ^ (row & 7u)) << 4);
+}
+// byte offset of element (row, col) inside one k-block
+__host__ __device__ __forceinline__ uint32_t sw128_elem_offset(uint32_t row, uint32_t col) {
+    return sw128_chunk_offset(row, col >> 3) + ((col & 7u) << 1);
+}
+
+// One contiguous run of k-blocks of an activation buffer that feeds a GEMM.
+struct ASeg {
+    const uint8_t* base;    // buffer start
+    int kb_stride;          // k-blocks per m-tile in that buffer
+    int kb_off;             // first k-block used
+    int nkb;                // number of k-blocks used
+};
+
+constexpr int MAX_SEGS = 3;
+
+struct GemmArgs {
+    ASeg seg[MAX_SEGS];
+    int nseg;
+    int num_kb;             // sum of seg[].nkb
+    const uint8_t* w;       // packed weights: [N/BN][num_kb] blocks of BN x 64 fp16 (swizzled image)
+    const float* bias;      // [N]
+    int N;                  // output channels
+    int m_tiles;            // number of 128-point tiles
+    uint8_t* out;           // activation buffer written (may be null when only the head is wanted)
+    int out_kb_stride;      // k-blocks per m-tile in out
+    int out_kb_off;
+    int leaky;              // apply leaky_relu(0.01)
+    // fused last layer (Conv1d to 1 channel + sigmoid), only when N == BN:
+    const float* head_w;    // [N + 64 * sum(head_seg nkb)] fp32; null = no head
+    float head_b;
+    ASeg head_seg[MAX_SEGS];
+    int head_nseg;
+    float* head_out;        // [m_tiles * 128] sigmoid(logit) * mask
+    const uint8_t* mask;    // per point, bit `mask_bit` = in-bounds; null = no masking
+    int mask_bit;
+    int n_valid;            // points in this chunk (rows >= n_valid are padding)
+};
+
+// ------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+#define PIFU_CUDA(expr)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            pifu::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,            \
+                            cudaGetErrorString(_e));                                 \
+            return -1;                                                               \
+        }                                                                            \
+    } while (0)
+
+// ------------------------------------------------------------------ kernel launchers
+int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t s);     // tcgen05 / TMEM / TMA
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);                // CUDA-core cross-check
+
+struct PointSource {
+    // mode 0: explicit points, reference layout [3][n] with row stride `pstride`
+    const float* pts;
+    long long pstride;
+    // mode 1: lattice ids; id -> (i, j, k) of an R0 x R1 x R2 lattice; ids == null -> id0 + p.
+    // World coordinates follow `mesh_util.py:12-38,59-65` in float64: c = step*idx + bmin,
+    // then [c,1] . cinv^T, then the float32 cast of `mesh_util.py:70`.
+    const long long* ids;
+    long long id0;
+    int R0, R1, R2;
+    double step[3], bmin[3];
+    double cinv[12];        // rows 0..2 of inv(calib) (4 columns each)
+    int mode;
+};
+
+struct GatherArgs {
+    PointSource src;
+    int n;                  // points in the chunk
+    float cg[12];           // rows 0..2 of calib_global (rotation | translation), fp32
+    float cl[12];           // calib_local
+    int perspective;
+    float z_mul, z_div;     // DepthNormalizer: z * z_mul / z_div
+    const float* feat_c;    // coarse map NHWC fp32
+    int Hc, Wc, Cc;
+    const float* feat_f;    // fine map NHWC fp32 (null for coarse-only)
+    int Hf, Wf, Cf;
+    uint8_t* F;             // coarse input tiles  [m_tiles][kbF]  = [feat | z_hi | z_lo | 0...]
+    int kbF;
+    uint8_t* FF;            // fine input tiles    [m_tiles][kbFF] = [fine feat | 0...]
+    int kbFF;
+    uint8_t* mask;          // [m_tiles*128] bit0 coarse in-bounds (x,y,z), bit1 fine in-bounds (x,y)
+};
+int launch_gather(const GatherArgs& a, cudaStream_t s);
+
+}  // namespace pifu

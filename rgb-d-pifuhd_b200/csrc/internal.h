@@ -1,0 +1,30 @@
+// Declarations shared between the translation units of libpifu_b200.so (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+struct pifu_ctx;
+
+namespace pifu {
+
+int launch_pack_weights(const float* W, int cin, const int* colmap, int num_kb, int N, int BN,
+                        uint8_t* out, cudaStream_t s);
+int launch_pack_rows(const float* X, int M, int K, int num_kb, uint8_t* out, cudaStream_t s);
+int launch_nchw_to_nhwc(const float* in, float* out, int C, int HW, cudaStream_t s);
+int launch_unblock(const uint8_t* buf, int kb_stride, int kb_off, int C, int n, float* dst, long long ld,
+                   cudaStream_t s);
+
+// api.cu services used by the octree driver
+int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
+             const float* calib, const double* calib_inv, float* out, cudaStream_t s);
+int ctx_num_sms(pifu_ctx* c);
+void ctx_count_launch(pifu_ctx* c, int n);
+
+struct OctreeState;
+struct McState;
+OctreeState*& ctx_octree(pifu_ctx* c);
+McState*& ctx_mc(pifu_ctx* c);
+void octree_free(OctreeState* s);
+void mc_free(McState* s);
+
+}  // namespace pifu

@@ -1,0 +1,184 @@
+"""Thin Python face of one `pifu_ctx` (one per CUDA device).
+
+PyTorch is plumbing here: it owns device memory and the stream; every kernel is in
+libpifu_b200.so.  The engine snapshots MLP weights and feature maps of the live
+``nn.Module``s and re-snapshots when their tensors change (``load_state_dict``,
+a new ``filter*`` call)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_engines = {}
+
+
+def get_engine(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.PifuError("pifu_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = Engine(idx)
+    return _engines[idx]
+
+
+def _stream(device_index):
+    return ctypes.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def _calib16(calib):
+    """[4,4] (or [3,4]) tensor/array -> ctypes float[16] row-major."""
+    c = torch.as_tensor(calib).detach().to("cpu", torch.float32).reshape(-1, 4)
+    full = torch.eye(4, dtype=torch.float32)
+    full[: c.shape[0]] = c
+    return (ctypes.c_float * 16)(*full.reshape(-1).tolist()), full
+
+
+class Engine:
+    def __init__(self, device_index):
+        self.lib = _lib.load()
+        self.device_index = device_index
+        self.device = torch.device("cuda", device_index)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.pifu_create(device_index, ctypes.byref(h)))
+        self.h = h
+        self._mlp_key = [None, None]
+        self._feat_key = [None, None]
+        self._opt_key = None
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.pifu_destroy(self.h)
+                self.h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ------------------------------------------------------------------ snapshots
+    @staticmethod
+    def _tensor_key(ts):
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+    def sync_mlp(self, level, mlp, owner_id):
+        """mlp: object with .filters (Conv1d list), .res_layers, .merge_layer, .norm, .filter_channels"""
+        if mlp.norm in ("batch", "group"):
+            raise NotImplementedError(
+                "mlp_norm=%r couples the points of one query() call through its statistics "
+                "(MLP.py:38-41); the fused path supports mlp_norm='none' only" % (mlp.norm,))
+        params = []
+        for f in mlp.filters:
+            params += [f.weight, f.bias]
+        key = (owner_id, self._tensor_key(params))
+        if self._mlp_key[level] == key:
+            return
+        if level == 0:
+            self._mlp_key[1] = None
+        ws, bs = [], []
+        for f in mlp.filters:
+            w = f.weight.detach().to(self.device, torch.float32).reshape(f.weight.shape[0], -1).contiguous()
+            b = f.bias.detach().to(self.device, torch.float32).contiguous()
+            ws.append(w)
+            bs.append(b)
+        ch = list(mlp.filter_channels)
+        res = list(mlp.res_layers)
+        n = len(ws)
+        wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+        bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
+        _lib.check(self.lib.pifu_set_mlp(self.h, level, len(ch), (ctypes.c_int * len(ch))(*ch), len(res),
+                                         (ctypes.c_int * max(len(res), 1))(*(res or [0])),
+                                         int(mlp.merge_layer), wp, bp, _stream(self.device_index)))
+        torch.cuda.current_stream(self.device_index).synchronize()
+        self._mlp_key[level] = key
+
+    def sync_features(self, level, feat):
+        """feat: [1, C, H, W] tensor (any device/dtype)."""
+        key = self._tensor_key([feat])
+        if self._feat_key[level] == key:
+            return
+        if feat.dim() != 4 or feat.shape[0] != 1:
+            raise ValueError("expected one [1, C, H, W] feature map, got %s" % (tuple(feat.shape),))
+        f = feat.detach().to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.pifu_set_features(self.h, level, ctypes.c_void_p(f.data_ptr()), f.shape[1],
+                                              f.shape[2], f.shape[3], _stream(self.device_index)))
+        self._keep[("feat", level)] = f        # keep alive until the copy on the stream is done
+        self._feat_key[level] = key
+
+    def set_options(self, perspective, load_size, z_size):
+        key = (bool(perspective), int(load_size) // 2, float(z_size))
+        if key != self._opt_key:
+            _lib.check(self.lib.pifu_set_options(self.h, int(key[0]), float(key[1]), float(key[2])))
+            self._opt_key = key
+
+    def set_gemm_impl(self, impl):
+        _lib.check(self.lib.pifu_set_gemm_impl(self.h, int(impl)))
+
+    def set_chunk_tiles(self, tiles):
+        _lib.check(self.lib.pifu_set_chunk_tiles(self.h, int(tiles)))
+
+    def launch_count(self):
+        return int(self.lib.pifu_launch_count(self.h))
+
+    # ------------------------------------------------------------------ compute
+    def query(self, levels, points, calib_local, calib_global, want_low=False, want_phi=0, no_mask=False):
+        """points [3, n] fp32 on this device.  Returns (pred [n], low [n] | None, phi [C, n] | None)."""
+        assert points.dim() == 2 and points.shape[0] == 3
+        pts = points.detach().to(self.device, torch.float32)
+        if pts.stride(1) != 1:
+            pts = pts.contiguous()
+        n = pts.shape[1]
+        pred = torch.empty(n, device=self.device, dtype=torch.float32)
+        low = torch.empty(n, device=self.device, dtype=torch.float32) if want_low else None
+        phi = torch.empty(want_phi, n, device=self.device, dtype=torch.float32) if want_phi else None
+        cl, _ = _calib16(calib_local)
+        cg, _ = _calib16(calib_global)
+        _lib.check(self.lib.pifu_query(
+            self.h, levels, 1 if no_mask else 0, ctypes.c_void_p(pts.data_ptr()), pts.stride(0), n, cl, cg,
+            ctypes.c_void_p(pred.data_ptr()),
+            ctypes.c_void_p(low.data_ptr()) if low is not None else None,
+            ctypes.c_void_p(phi.data_ptr()) if phi is not None else None,
+            _stream(self.device_index)))
+        return pred, low, phi
+
+    @staticmethod
+    def calib_pair(calib):
+        """(float[16], double[16] inverse) exactly as `mesh_util.py:61-62` derives them."""
+        c16, full = _calib16(calib)
+        inv = np.linalg.inv(full.numpy())          # float32 in, like calib_tensor[0].cpu().numpy()
+        inv64 = np.ascontiguousarray(inv, dtype=np.float64)
+        return c16, (ctypes.c_double * 16)(*inv64.reshape(-1).tolist()), full, inv64
+
+    def eval_grid(self, levels, res, calib, id_begin=0, id_end=None, out=None):
+        R0, R1, R2 = (res, res, res) if np.isscalar(res) else res
+        total = R0 * R1 * R2
+        id_end = total if id_end is None else id_end
+        if out is None:
+            out = torch.empty(id_end - id_begin, device=self.device, dtype=torch.float32)
+        c16, inv16, _, _ = self.calib_pair(calib)
+        _lib.check(self.lib.pifu_eval_grid(self.h, levels, R0, R1, R2, id_begin, id_end, c16, inv16,
+                                           ctypes.c_void_p(out.data_ptr()), _stream(self.device_index)))
+        return out
+
+    def eval_lattice_ids(self, levels, res, ids, calib):
+        R0, R1, R2 = (res, res, res) if np.isscalar(res) else res
+        ids = ids.to(self.device, torch.int64).contiguous()
+        out = torch.empty(ids.numel(), device=self.device, dtype=torch.float32)
+        c16, inv16, _, _ = self.calib_pair(calib)
+        _lib.check(self.lib.pifu_eval_lattice_ids(self.h, levels, R0, R1, R2, ctypes.c_void_p(ids.data_ptr()),
+                                                  ids.numel(), c16, inv16, ctypes.c_void_p(out.data_ptr()),
+                                                  _stream(self.device_index)))
+        return out
+
+    def debug_gemm(self, X, W, b, leaky=True):
+        X = X.to(self.device, torch.float32).contiguous()
+        W = W.to(self.device, torch.float32).contiguous()
+        b = b.to(self.device, torch.float32).contiguous()
+        M, K = X.shape
+        N = W.shape[0]
+        Y = torch.empty(N, M, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.pifu_debug_gemm(self.h, ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(W.data_ptr()),
+                                            ctypes.c_void_p(b.data_ptr()), M, K, N, int(leaky),
+                                            ctypes.c_void_p(Y.data_ptr()), _stream(self.device_index)))
+        return Y
