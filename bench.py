@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the reconstruction hot path (BASELINE.json: occupancy queries/s; configs[1] =
+PIFuMRNet multi-level, dense 256^3 lattice, per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one 256^3 lattice (16 777 216 queries) per GPU:
+in-kernel lattice generation -> calib projection -> bilinear sampling of the coarse/fine feature
+maps -> coarse MLP trunk -> fine MLP -> occupancy field in HBM.  For N > 1 (torchrun, one rank
+per GPU) the lattice is (256*N) x 256 x 256, slab-sharded along axis 0, no data-path collective;
+the slabs are gathered to rank 0 with NCCL inside the timed step (weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = 256
+METRIC = "occupancy_queries_per_s"
+UNIT = "queries/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def build_problem():
+    """Seeded random-init two-level net + band-limited feature maps (pifu_b200.synthetic)."""
+    from pifu_b200 import synthetic as syn
+    prob = syn.make_problem(bias_std=0.0)
+    return prob, syn.default_calib()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_queries_per_s(prob, calib, n_points, steps=1, warmup=0):
+    """Times the CPU oracle (torch-CPU port of PIFuMRNet.query, same library kernels the
+    reference runs) on a bounded sample of the same lattice: every (RES^3 // n_points)-th point."""
+    from pifu_b200 import config
+    from oracle import pifu_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    oc, of = config.coarse_opt(), config.fine_opt()
+    coarse = orc.CoarseState(prob["coarse"], prob["feat_coarse"], oc)
+    fine = orc.FineState(prob["fine"], prob["feat_fine"], of, coarse)
+    stride = max(1, RES ** 3 // n_points)
+    ids = np.arange(0, RES ** 3, stride)[:n_points]
+    k, j, i = ids % RES, (ids // RES) % RES, ids // (RES * RES)
+    pts = np.stack([-1 + 2.0 * i / RES, -(-1 + 2.0 * j / RES), -1 + 2.0 * k / RES]).astype(np.float32)
+    pts = torch.from_numpy(pts)[None]
+    chunk = 100000                      # gen_mesh_imgColor's num_samples (reconstruction.py:108)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            for s in range(0, pts.shape[2], chunk):
+                orc.query_fine(fine, pts[:, :, s:s + chunk], calib)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return pts.shape[2] / (sum(times) / len(times)), torch.get_num_threads(), pts.shape[2], sum(times) / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path for this metric (oracle port: the
+    reference cannot travel to the GPU box and its query path is library torch ops)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prob, calib = build_problem()
+    n = 200000
+    qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, n, steps=args.steps, warmup=min(args.warmup, 1))
+    sample = "%d-point strided sub-lattice of the %d^3 lattice per step, chunks of 100000 (PIFuMRNet.query port, torch CPU fp32)" % (npts, RES)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PIFuMRNet multi-level occupancy query, dense %d^3 lattice (configs[1]); bounded sample" % RES},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--res", type=int, default=RES, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from pifu_b200 import PIFuMRNet, PIFuNetwNML, config, dist as pdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    res = args.res
+
+    torch.set_grad_enabled(False)
+    prob, calib = build_problem()
+    netG = PIFuNetwNML(config.coarse_opt(), "orthogonal")
+    netMR = PIFuMRNet(config.fine_opt(), netG, "orthogonal")
+    netG.mlp.load_state_dict(prob["coarse"])
+    netMR.mlp.load_state_dict(prob["fine"])
+    netMR.to(dev).eval()
+    # host copies of the hot path's inputs (what filter_* leaves behind), pinned for the e2e leg
+    feat_c_host = prob["feat_coarse"].pin_memory()
+    feat_f_host = prob["feat_fine"].pin_memory()
+    netG.im_feat_list = [feat_c_host.to(dev)]
+    netMR.im_feat_list = [feat_f_host.to(dev)]
+    eng = netMR._engine_for(torch.zeros(1, device=dev))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+
+    R0 = res * world
+    per_rank = res ** 3
+    id_b, id_e = rank * per_rank, (rank + 1) * per_rank
+    slab = torch.empty(per_rank, device=dev, dtype=torch.float32)
+    gathered = [torch.empty(per_rank, device=dev, dtype=torch.float32) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def step():
+        eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
+        if world > 1:
+            dist.gather(slab, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        flush.fill_(0.0)                    # L2 flush between timed iterations (256 MiB write)
+        step()
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    launches = eng.launch_count() - l0 + args.steps     # + the flush fills
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * per_rank / (ms_per_step * 1e-3)
+
+    # ---- end to end through the reference-shaped API with HOST buffers: features H2D from pinned
+    # memory + re-layout, the fused query, and the occupancy field back to pinned host memory
+    field_host = torch.empty(per_rank, dtype=torch.float32).pin_memory()
+    h2d = feat_c_host.numel() * 4 + feat_f_host.numel() * 4 + 16 * 4 + 16 * 8
+    d2h = per_rank * 4
+
+    def e2e_step():
+        netG.im_feat_list = [feat_c_host.to(dev, non_blocking=True)]
+        netMR.im_feat_list = [feat_f_host.to(dev, non_blocking=True)]
+        eng.sync_features(0, netG.im_feat_list[-1])
+        eng.sync_features(1, netMR.im_feat_list[-1])
+        eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
+        field_host.copy_(slab, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev2[1].record()
+    barrier()
+    t2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * per_rank / (float(t2.item()) / args.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 layer kernel): per-launch CUDA events
+    roofline = cpu = None
+    if rank == 0:
+        peaks = load_peaks()
+        eng.profile(True)
+        eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
+        n_l, gemm_ms, gemm_flops = eng.profile_read()
+        eng.profile(False)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 MLP layer)", "achieved": achieved,
+                    "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                    "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_l,
+                    "avg_launch_us": gemm_ms * 1e3 / max(n_l, 1), "share_of_step": gemm_ms / ms_per_step,
+                    "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
+                    "note": "coarse L3/L4 (preds_low) are not on the get_preds() path and are skipped"}
+        if not args.no_cpu_baseline:
+            qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, 400000)
+            cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d-point strided sub-lattice of the %d^3 lattice, chunks of 100000, %.1f s" % (npts, res, sec)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": "PIFuMRNet multi-level (coarse 257-1024-512-256 trunk + fine 272-512-256-128-1), dense "
+                                   "%dx%dx%d lattice, %d^3 = %d queries per GPU (BASELINE configs[1])" % (R0, res, res, res, per_rank),
+                       "parallelism": "slab%d" % world, "mlp_norm": "none",
+                       "l2": "256 MiB flush write between timed iterations; per-step activation traffic (~6 KB/query) >> 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,8 +85,45 @@ int pifu_eval_lattice_ids(pifu_ctx* ctx, int levels, int R0, int R1, int R2, con
                           long long n, const float* calib, const double* calib_inv, float* out,
                           void* stream);
 
+/* Octree (coarse-to-fine) lattice evaluation on the device.  Replaces eval_grid_octree
+ * (mesh_util.py:124-187): float64 field, last plane of each axis never evaluated (:135),
+ * stride R0 // init_resolution halving to 1 (:138-185), skip test (max - min) < threshold on
+ * the 8 cell corners and inclusive fill (:154-184).
+ * One-call form: sdf64 (device double [R0*R1*R2]) and/or sdf32 (device float, the cast
+ * scikit-image applies on entry) may be NULL; evaluated_per_level (host, max_levels entries,
+ * -1 padded) receives the number of lattice points evaluated at each level. */
+int pifu_eval_grid_octree(pifu_ctx* ctx, int levels, int R0, int R1, int R2, int init_resolution,
+                          double threshold, const float* calib, const double* calib_inv, double* sdf64,
+                          float* sdf32, long long* evaluated_per_level, int max_levels, void* stream);
+
+/* Stepwise form, so a multi-GPU driver can split each level's frontier across ranks:
+ *   begin -> { frontier (compacted lattice ids of this level, C order) -> [evaluate ids,
+ *   e.g. pifu_eval_lattice_ids on a share + all-gather] -> commit(values of the whole
+ *   frontier) } until frontier reports step == 0 -> export. */
+int pifu_octree_begin(pifu_ctx* ctx, int R0, int R1, int R2, int init_resolution, double threshold,
+                      void* stream);
+int pifu_octree_frontier(pifu_ctx* ctx, long long* n, const long long** ids_device, int* step, void* stream);
+int pifu_octree_commit(pifu_ctx* ctx, const float* values_device, void* stream);
+int pifu_octree_export(pifu_ctx* ctx, double* sdf64, float* sdf32, void* stream);
+
+/* Marching cubes on a device float32 volume [n0][n1][n2] at `level` (strict v > level is
+ * inside).  Replaces measure.marching_cubes_lewiner (call site mesh_util.py:84; third-party,
+ * see DESIGN.md "parity unpinned").  Two calls because the output size is data dependent:
+ * count (synchronises, returns sizes) then emit into caller-allocated device buffers:
+ * verts double [nverts][3] in volume-index coordinates (axis order of the volume), faces
+ * int32 [nfaces][3], optional normals float [nverts][3] and values float [nverts]. */
+int pifu_mc_count(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, double level,
+                  long long* nverts, long long* nfaces, void* stream);
+int pifu_mc_emit(pifu_ctx* ctx, double* verts, int* faces, float* normals, float* values, void* stream);
+
 /* Number of kernels launched by this context since creation (bench accounting). */
 long long pifu_launch_count(pifu_ctx* ctx);
+
+/* Per-launch CUDA-event timing of the tensor-core layer kernel (bench.py's roofline leg):
+ * enable, run the workload, read (synchronises): launches, summed device time and summed
+ * algorithmic FLOPs (2 * points * Cin * Cout per launch, un-padded Cin). */
+int pifu_profile_enable(pifu_ctx* ctx, int on);
+int pifu_profile_read(pifu_ctx* ctx, long long* launches, double* total_ms, double* total_flops);
 
 /* Test hook: one layer, Y = act(W X^T + b), through the layer kernel (synchronous).  All
  * pointers are device fp32: X [M][K] (points x channels), W [N][K], b [N]; Y is channel-major

@@ -141,7 +141,9 @@ def main():
     out["grid16_coords_sha"] = np.frombuffer(bytes.fromhex(sha(coords)), dtype=np.uint8)
     out["grid16_mat"] = mat
 
-    # octree through the reference with the real (calibrated) net, 64^3 / init 16
+    # octree through the reference with the real net on the saturated field, 64^3 / init 16
+    syn.saturate(prob["fine"], 3)
+    load_problem(netG, netMR, prob)
     res = 64
     coords, mat = mesh_util.create_grid(res, res, res)
     c = coords.reshape(3, -1).T
@@ -152,6 +154,8 @@ def main():
     out["mr_octree64_init16_sha_f64"] = np.frombuffer(bytes.fromhex(sha(f)), dtype=np.uint8)
 
     # perspective projection (PIFuMRNet's default-mode typo selects it, BasePIFuNet.py:79)
+    syn.saturate(prob["fine"], 3, 1.0 / syn.SATURATE_GAIN)
+    load_problem(netG, netMR, prob)
     netGp, _ = build_reference_nets(BaseOptions, PIFuNetwNML, PIFuMRNet, "none", "perspective")
     netGp.mlp.load_state_dict(prob["coarse"], strict=False)
     netGp.im_feat_list = [prob["feat_coarse"]]

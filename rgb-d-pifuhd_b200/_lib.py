@@ -33,7 +33,18 @@ SIGNATURES = {
                                       ctypes.c_longlong, ctypes.c_longlong, c_float_p, c_double_p, VP, VP]),
     "pifu_eval_lattice_ids": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              VP, ctypes.c_longlong, c_float_p, c_double_p, VP, VP]),
+    "pifu_eval_grid_octree": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_double, c_float_p, c_double_p, VP, VP, c_ll_p, ctypes.c_int, VP]),
+    "pifu_octree_begin": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, VP]),
+    "pifu_octree_frontier": (ctypes.c_int, [VP, c_ll_p, ctypes.POINTER(VP), c_int_p, VP]),
+    "pifu_octree_commit": (ctypes.c_int, [VP, VP, VP]),
+    "pifu_octree_export": (ctypes.c_int, [VP, VP, VP, VP]),
+    "pifu_mc_count": (ctypes.c_int, [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                     c_ll_p, c_ll_p, VP]),
+    "pifu_mc_emit": (ctypes.c_int, [VP, VP, VP, VP, VP, VP]),
     "pifu_launch_count": (ctypes.c_longlong, [VP]),
+    "pifu_profile_enable": (ctypes.c_int, [VP, ctypes.c_int]),
+    "pifu_profile_read": (ctypes.c_int, [VP, c_ll_p, c_double_p, c_double_p]),
     "pifu_debug_gemm": (ctypes.c_int, [VP, VP, VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, VP, VP]),
 }

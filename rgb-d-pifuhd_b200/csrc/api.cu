@@ -76,6 +76,11 @@ struct pifu_ctx {
     uint8_t* mask = nullptr;
     float* pred_chunk = nullptr;               // scratch for scattered outputs
     long long launches = 0;
+    // per-launch CUDA-event timing of the layer kernel (bench roofline), off by default
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Timed { int ev; double flops; };
+    std::vector<Timed> timed;
     pifu::OctreeState* octree = nullptr;
     pifu::McState* mc = nullptr;
 };
@@ -134,10 +139,21 @@ ASeg make_seg(const pifu_ctx* c, const SegRef& r) {
     return s;
 }
 
-int run_gemm(pifu_ctx* c, const GemmArgs& g, cudaStream_t s) {
+int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
     c->launches += 1;
     if (c->gemm_impl == PIFU_GEMM_SIMT) { c->launches += g.head_w ? 1 : 0; return launch_gemm_simt(g, s); }
-    return launch_gemm_tc(g, c->num_sms, s);
+    if (!c->profile) return launch_gemm_tc(g, c->num_sms, s);
+    const int e = static_cast<int>(c->timed.size()) * 2;
+    while (static_cast<int>(c->ev_pool.size()) < e + 2) {
+        cudaEvent_t ev;
+        PIFU_CUDA(cudaEventCreate(&ev));
+        c->ev_pool.push_back(ev);
+    }
+    PIFU_CUDA(cudaEventRecord(c->ev_pool[e], s));
+    const int rc = launch_gemm_tc(g, c->num_sms, s);
+    PIFU_CUDA(cudaEventRecord(c->ev_pool[e + 1], s));
+    c->timed.push_back({e, flops});
+    return rc;
 }
 
 // hidden layers [first, last] of a level; the fused last layer rides on layer n_layers-2
@@ -173,7 +189,10 @@ int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_ti
             g.mask = mask_bit >= 0 ? c->mask : nullptr;
             g.mask_bit = mask_bit >= 0 ? mask_bit : 0;
         }
-        if (run_gemm(c, g, s)) return -1;
+        // algorithmic work of this launch: 2 * points * true Cin * Cout (+ the fused Conv1d -> 1)
+        double flops = 2.0 * n_valid * static_cast<double>(l.cin) * l.cout;
+        if (with_head) flops += 2.0 * n_valid * (L.dims[L.n_layers - 1] + (L.is_res(L.n_layers - 1) ? L.dims[0] : 0));
+        if (run_gemm(c, g, flops, s)) return -1;
     }
     return 0;
 }
@@ -314,6 +333,7 @@ void pifu_destroy(pifu_ctx* c) {
     for (int l = 0; l < 2; ++l) { free_level(c->lv[l]); if (c->lv[l].feat) cudaFree(c->lv[l].feat); }
     pifu::octree_free(c->octree);
     pifu::mc_free(c->mc);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     delete c;
 }
 
@@ -338,6 +358,31 @@ int pifu_set_chunk_tiles(pifu_ctx* c, int tiles) {
 }
 
 long long pifu_launch_count(pifu_ctx* c) { return c ? c->launches : 0; }
+
+int pifu_profile_enable(pifu_ctx* c, int on) {
+    if (!c) { set_error("null context"); return -1; }
+    c->profile = on != 0;
+    c->timed.clear();
+    return 0;
+}
+
+int pifu_profile_read(pifu_ctx* c, long long* launches, double* total_ms, double* total_flops) {
+    if (!c || !launches || !total_ms || !total_flops) { set_error("null argument"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    PIFU_CUDA(cudaDeviceSynchronize());
+    double ms = 0.0, fl = 0.0;
+    for (const auto& t : c->timed) {
+        float e = 0.f;
+        PIFU_CUDA(cudaEventElapsedTime(&e, c->ev_pool[t.ev], c->ev_pool[t.ev + 1]));
+        ms += e;
+        fl += t.flops;
+    }
+    *launches = static_cast<long long>(c->timed.size());
+    *total_ms = ms;
+    *total_flops = fl;
+    c->timed.clear();
+    return 0;
+}
 
 int pifu_set_features(pifu_ctx* c, int level, const float* nchw, int C, int H, int W, void* stream) {
     if (!c || level < 0 || level > 1 || !nchw) { set_error("bad arguments to pifu_set_features"); return -1; }
@@ -563,7 +608,7 @@ int pifu_debug_gemm(pifu_ctx* c, const float* X, const float* W, const float* b,
     g.num_kb = nkb;
     g.w = wp; g.bias = bias; g.N = N; g.m_tiles = m_tiles;
     g.out = yo; g.out_kb_stride = N / KB; g.leaky = leaky; g.n_valid = M;
-    if (!rc) rc = run_gemm(c, g, s);
+    if (!rc) rc = run_gemm(c, g, 2.0 * M * static_cast<double>(K) * N, s);
     // Y comes back channel-major [N][M], the orientation of the reference's [C, N] tensors
     if (!rc) rc = launch_unblock(yo, N / KB, 0, N, M, Y, M, s);
     cudaError_t e = cudaStreamSynchronize(s);

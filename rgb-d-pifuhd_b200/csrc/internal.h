@@ -20,6 +20,13 @@ int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* i
 int ctx_num_sms(pifu_ctx* c);
 void ctx_count_launch(pifu_ctx* c, int n);
 
+int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s);
+int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s);
+const long long* octree_ids(pifu_ctx* c);
+int octree_commit(pifu_ctx* c, const float* vals, cudaStream_t s);
+int octree_export(pifu_ctx* c, double* sdf64, float* sdf32, cudaStream_t s);
+int octree_vals(pifu_ctx* c, long long n, float** out);
+
 struct OctreeState;
 struct McState;
 OctreeState*& ctx_octree(pifu_ctx* c);

@@ -118,6 +118,15 @@ class Engine:
     def set_chunk_tiles(self, tiles):
         _lib.check(self.lib.pifu_set_chunk_tiles(self.h, int(tiles)))
 
+    def profile(self, on):
+        _lib.check(self.lib.pifu_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self):
+        """-> (launches, total_ms, total_flops) of the layer-kernel launches since profile(True)."""
+        n, ms, fl = ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
+        _lib.check(self.lib.pifu_profile_read(self.h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
+        return n.value, ms.value, fl.value
+
     def launch_count(self):
         return int(self.lib.pifu_launch_count(self.h))
 
@@ -182,3 +191,81 @@ class Engine:
                                             ctypes.c_void_p(b.data_ptr()), M, K, N, int(leaky),
                                             ctypes.c_void_p(Y.data_ptr()), _stream(self.device_index)))
         return Y
+
+    # ------------------------------------------------------------------ octree
+    def eval_grid_octree(self, levels, res, calib, init_resolution=64, threshold=0.05,
+                         want64=True, want32=False):
+        """One-call device octree.  Returns (sdf64 | None, sdf32 | None, evaluated_per_level)."""
+        R0, R1, R2 = (res, res, res) if np.isscalar(res) else res
+        sdf64 = torch.empty((R0, R1, R2), device=self.device, dtype=torch.float64) if want64 else None
+        sdf32 = torch.empty((R0, R1, R2), device=self.device, dtype=torch.float32) if want32 else None
+        c16, inv16, _, _ = self.calib_pair(calib)
+        stats = (ctypes.c_longlong * 16)()
+        _lib.check(self.lib.pifu_eval_grid_octree(
+            self.h, levels, R0, R1, R2, int(init_resolution), float(threshold), c16, inv16,
+            ctypes.c_void_p(sdf64.data_ptr()) if want64 else None,
+            ctypes.c_void_p(sdf32.data_ptr()) if want32 else None, stats, 16, _stream(self.device_index)))
+        return sdf64, sdf32, [int(v) for v in stats if v >= 0]
+
+    def octree_begin(self, res, init_resolution=64, threshold=0.05):
+        R0, R1, R2 = (res, res, res) if np.isscalar(res) else res
+        self._oct_res = (R0, R1, R2)
+        _lib.check(self.lib.pifu_octree_begin(self.h, R0, R1, R2, int(init_resolution), float(threshold),
+                                              _stream(self.device_index)))
+
+    def octree_frontier(self):
+        """-> (step, ids) with ids a device int64 view of this level's lattice ids; step 0 = done."""
+        n = ctypes.c_longlong()
+        ptr = ctypes.c_void_p()
+        step = ctypes.c_int()
+        _lib.check(self.lib.pifu_octree_frontier(self.h, ctypes.byref(n), ctypes.byref(ptr), ctypes.byref(step),
+                                                 _stream(self.device_index)))
+        if step.value == 0 or n.value == 0:
+            return step.value, torch.empty(0, device=self.device, dtype=torch.int64)
+        # copy out: the library reuses its id buffer on the next level
+        ids = torch.as_tensor(_DevView(ptr.value, n.value, "<i8"), device=self.device).clone()
+        return step.value, ids
+
+    def octree_commit(self, vals):
+        vals = vals.to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.pifu_octree_commit(self.h, ctypes.c_void_p(vals.data_ptr()) if vals.numel() else None,
+                                               _stream(self.device_index)))
+
+    def octree_export(self, want64=True, want32=False):
+        R0, R1, R2 = self._oct_res
+        sdf64 = torch.empty((R0, R1, R2), device=self.device, dtype=torch.float64) if want64 else None
+        sdf32 = torch.empty((R0, R1, R2), device=self.device, dtype=torch.float32) if want32 else None
+        _lib.check(self.lib.pifu_octree_export(self.h, ctypes.c_void_p(sdf64.data_ptr()) if want64 else None,
+                                               ctypes.c_void_p(sdf32.data_ptr()) if want32 else None,
+                                               _stream(self.device_index)))
+        return sdf64, sdf32
+
+    # ------------------------------------------------------------------ marching cubes
+    def marching_cubes(self, field, level, want_normals=True):
+        """field: device float32 [n0, n1, n2].  -> (verts f64 [V,3], faces i32 [F,3], normals, values)
+        on the device.  Raises ValueError like skimage when there is no surface at `level`."""
+        f = field.to(self.device, torch.float32).contiguous()
+        if f.dim() != 3:
+            raise ValueError("Input volume should be a 3D array")
+        nv, nf = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(self.lib.pifu_mc_count(self.h, ctypes.c_void_p(f.data_ptr()), f.shape[0], f.shape[1], f.shape[2],
+                                          float(level), ctypes.byref(nv), ctypes.byref(nf), _stream(self.device_index)))
+        if nv.value == 0:
+            raise ValueError("No surface found at the given iso value (or level outside the data range)")
+        verts = torch.empty((nv.value, 3), device=self.device, dtype=torch.float64)
+        faces = torch.empty((nf.value, 3), device=self.device, dtype=torch.int32)
+        normals = torch.empty((nv.value, 3), device=self.device, dtype=torch.float32) if want_normals else None
+        values = torch.empty((nv.value,), device=self.device, dtype=torch.float32) if want_normals else None
+        _lib.check(self.lib.pifu_mc_emit(self.h, ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(faces.data_ptr()),
+                                         ctypes.c_void_p(normals.data_ptr()) if want_normals else None,
+                                         ctypes.c_void_p(values.data_ptr()) if want_normals else None,
+                                         _stream(self.device_index)))
+        self._keep["mc_field"] = f
+        return verts, faces, normals, values
+
+
+class _DevView:
+    """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, True), "version": 2}

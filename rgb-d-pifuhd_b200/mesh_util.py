@@ -1,0 +1,204 @@
+"""Reconstruction driver, drop-in for the reference's `mesh_util.py`.
+
+`reconstruction()` keeps the reference signature and return convention (`mesh_util.py:40-96`).
+When `net` is one of this package's nets the whole path runs on the device: the lattice is
+generated in-kernel (no `create_grid` arrays), occupancy comes from the fused query kernels
+(dense or device octree), the iso-surface from the CUDA marching cubes, and only the mesh
+crosses back to the host.  The callback forms (`eval_grid`, `eval_grid_octree`, `batch_eval`
+with an arbitrary `eval_func`) keep reference semantics on the host because the callable *is*
+the computation there.
+"""
+import numpy as np
+import torch
+
+from .engine import get_engine
+
+
+# ----------------------------------------------------------------------------- lattice
+def create_grid(resX, resY, resZ, b_min=np.array([-1, -1, -1]), b_max=np.array([1, 1, 1]), transform=None):
+    """`mesh_util.py:12-38`: coords [3, resX, resY, resZ] float64 and the index->world 4x4.
+    Note the spacing is length / res (the lattice spans [b_min, b_max - length/res])."""
+    mat = np.eye(4)
+    span = np.asarray(b_max, dtype=np.float64) - np.asarray(b_min, dtype=np.float64)
+    mat[0, 0], mat[1, 1], mat[2, 2] = span[0] / resX, span[1] / resY, span[2] / resZ
+    mat[0:3, 3] = b_min
+    idx = np.indices((resX, resY, resZ)).reshape(3, -1)
+    coords = mat[:3, :3] @ idx + mat[:3, 3:4]
+    if transform is not None:
+        coords = transform[:3, :3] @ coords + transform[:3, 3:4]
+        mat = transform @ mat
+    return coords.reshape(3, resX, resY, resZ), mat
+
+
+def batch_eval(points, eval_func, num_samples=512 * 512 * 512):
+    """`mesh_util.py:98-114`: in-order chunks of `num_samples` points into a float64 vector."""
+    n = points.shape[1]
+    out = np.zeros(n)
+    for start in range(0, n, num_samples):
+        out[start:start + num_samples] = eval_func(points[:, start:start + num_samples])
+    return out
+
+
+def eval_grid(coords, eval_func, num_samples=512 * 512 * 512):
+    """`mesh_util.py:116-120` (generic callable form)."""
+    shape = coords.shape[1:4]
+    return batch_eval(coords.reshape(3, -1), eval_func, num_samples=num_samples).reshape(shape)
+
+
+def _fill_from_skip_cells(sdf, todo, skip, mid, step):
+    """Vectorised form of the reference's per-cell fill loop (`mesh_util.py:181-184`): a voxel
+    takes the value of the lexicographically largest skip cell covering it (that cell wrote
+    last); cell p//step covers p, and cell p//step - 1 only when p % step == 0."""
+    found = np.zeros(sdf.shape, dtype=bool)
+    value = np.zeros(sdf.shape)
+    axes = [np.arange(r) for r in sdf.shape]
+    for o in np.ndindex(2, 2, 2):                  # (0,0,0) first: the high cell on every axis
+        cell, ok = [], []
+        for ax in range(3):
+            c = axes[ax] // step - o[ax]
+            good = (c >= 0) & (c < skip.shape[ax])
+            if o[ax]:
+                good &= axes[ax] % step == 0
+            cell.append(np.clip(c, 0, max(skip.shape[ax] - 1, 0)))
+            ok.append(good)
+        hit = skip[np.ix_(*cell)] & ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :] & ~found
+        value[hit] = mid[np.ix_(*cell)][hit]
+        found |= hit
+    sdf[found] = value[found]
+    todo[found] = False
+
+
+def eval_grid_octree(coords, eval_func, init_resolution=64, threshold=0.05, num_samples=512 * 512 * 512):
+    """`mesh_util.py:124-187` for an arbitrary `eval_func` (host bookkeeping, same field
+    bit for bit as the reference loop).  The device version used by `reconstruction()` is
+    `Engine.eval_grid_octree`."""
+    res = coords.shape[1:4]
+    sdf = np.zeros(res)
+    todo = np.zeros(res, dtype=bool)
+    todo[:-1, :-1, :-1] = True
+    on_lattice = np.zeros(res, dtype=bool)
+    step = res[0] // init_resolution
+    while step > 0:
+        on_lattice[::step, ::step, ::step] = True
+        test = on_lattice & todo
+        sdf[test] = batch_eval(coords[:, test], eval_func, num_samples=num_samples)
+        todo[test] = False
+        if step <= 1:
+            break
+        v = sdf[::step, ::step, ::step]
+        if min(v.shape) >= 2:
+            n = [s - 1 for s in v.shape]
+            corners = [v[a:a + n[0], b:b + n[1], c:c + n[2]] for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+            lo = np.minimum.reduce(corners)
+            hi = np.maximum.reduce(corners)
+            h = step // 2
+            centre = todo[h::step, h::step, h::step][:n[0], :n[1], :n[2]]
+            skip = ((hi - lo) < threshold) & centre
+            _fill_from_skip_cells(sdf, todo, skip, 0.5 * (lo + hi), step)
+        step //= 2
+    return sdf.reshape(res)
+
+
+# ----------------------------------------------------------------------------- driver
+def _is_native(net):
+    from .PIFuMRNet import PIFuMRNet
+    from .PIFuNetwNML import PIFuNetwNML
+    return isinstance(net, (PIFuMRNet, PIFuNetwNML))
+
+
+def _prepare_native(net, device):
+    """Snapshot weights/features of a native net into the device engine; returns (engine, levels)."""
+    from .PIFuMRNet import PIFuMRNet
+    probe = torch.zeros(1, device=device)
+    eng = net._engine_for(probe)
+    if isinstance(net, PIFuMRNet):
+        if len(net.im_feat_list) != 1 or len(net.netG.im_feat_list) != 1:
+            raise RuntimeError("call filter_global/filter_local (eval mode) before reconstruction")
+        eng.sync_features(0, net.netG.im_feat_list[-1][:1])
+        eng.sync_features(1, net.im_feat_list[-1][:1])
+        return eng, 2
+    if len(net.im_feat_list) != 1:
+        raise RuntimeError("call filter (eval mode) before reconstruction")
+    eng.sync_features(0, net.im_feat_list[-1][:1])
+    return eng, 1
+
+
+def eval_field_device(net, cuda, calib_tensor, resolution, use_octree, init_resolution=64, threshold=0.05,
+                      group=None, stats=None):
+    """Occupancy lattice as a device float32 tensor [R, R, R] (native nets only)."""
+    from . import dist as pdist
+    eng, levels = _prepare_native(net, cuda)
+    calib = calib_tensor[0]
+    if group is not None or pdist.world_size() > 1:
+        if use_octree:
+            return pdist.sharded_eval_grid_octree(eng, levels, resolution, calib, init_resolution, threshold,
+                                                  group=group, stats=stats)
+        return pdist.sharded_eval_grid(eng, levels, resolution, calib, group=group)
+    if use_octree:
+        _, sdf32, ev = eng.eval_grid_octree(levels, resolution, calib, init_resolution, threshold,
+                                            want64=False, want32=True)
+        if stats is not None:
+            stats.extend(ev)
+        return sdf32
+    return eng.eval_grid(levels, resolution, calib).view(resolution, resolution, resolution)
+
+
+def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5, use_octree=False,
+                   num_samples=10000, transform=None, *, group=None):
+    """`mesh_util.py:40-96`.  Returns (verts float64 [V,3], faces int32 [F,3], normals float32,
+    values float32) or -1 when no iso-surface exists.  As in the reference, `b_min`/`b_max`/
+    `transform` are accepted and ignored (`:59`), the lattice is [-1, 1)^3 pre-multiplied by
+    inv(calib), and faces are flipped when the index->world transform mirrors (`:91-92`).
+    `num_samples` only chunks host callbacks; the fused path is chunk-invariant."""
+    device = torch.device(cuda)
+    mat = np.eye(4)
+    mat[0, 0] = mat[1, 1] = mat[2, 2] = 2.0 / resolution
+    mat[0:3, 3] = -1.0
+    calib_inv = np.linalg.inv(calib_tensor[0].detach().cpu().numpy())       # float32, `:61-62`
+    if _is_native(net):
+        field = eval_field_device(net, device, calib_tensor, resolution, use_octree, group=group)
+        eng = get_engine(device)
+    else:
+        coords, _ = create_grid(resolution, resolution, resolution)
+        pts = coords.reshape(3, -1).T
+        pts = (np.concatenate([pts, np.ones((pts.shape[0], 1))], 1) @ calib_inv.T)[:, :3]
+        coords = pts.T.reshape(3, resolution, resolution, resolution)
+
+        def eval_func(points):
+            samples = torch.from_numpy(np.expand_dims(points, 0)).to(device=device).float()
+            net.query(samples, calib_tensor)
+            return net.get_preds()[0][0].detach().cpu().numpy()
+
+        sdf = (eval_grid_octree if use_octree else eval_grid)(coords, eval_func, num_samples=num_samples)
+        eng = get_engine(device)
+        field = torch.from_numpy(sdf.astype(np.float32)).to(device)
+    if field is None:                    # non-root rank of a sharded run
+        return None
+    try:
+        verts, faces, normals, values = eng.marching_cubes(field, thresh)
+        trans = np.matmul(calib_inv, mat)
+        t = torch.from_numpy(trans).to(device)
+        verts = (verts @ t[:3, :3].T + t[:3, 3]).cpu().numpy()
+        faces = faces.cpu().numpy()
+        if np.linalg.det(trans[:3, :3]) < 0.0:
+            faces = faces[:, ::-1]
+        return verts, faces, normals.cpu().numpy(), values.cpu().numpy()
+    except ValueError:
+        print('error cannot marching cubes')
+        return -1
+
+
+def save_obj_mesh_with_color(mesh_path, verts, faces, colors):
+    """`mesh_util.py:189-198`, vectorised: 'v x y z r g b' with %.4f, faces 1-based as (f0, f2, f1)."""
+    verts = np.asarray(verts)
+    colors = np.asarray(colors)
+    faces = np.asarray(faces)
+    with open(mesh_path, 'w') as f:
+        if len(verts):
+            vc = np.concatenate([verts[:, :3], colors[:len(verts), :3]], 1)
+            f.write('\n'.join('v %.4f %.4f %.4f %.4f %.4f %.4f' % tuple(r) for r in vc.tolist()))
+            f.write('\n')
+        if len(faces):
+            fp = faces.astype(np.int64) + 1
+            f.write('\n'.join('f %d %d %d' % (r[0], r[2], r[1]) for r in fp.tolist()))
+            f.write('\n')

@@ -19,7 +19,7 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
-def calibrated_problem(bias_std=0.01):
+def calibrated_problem(bias_std=0.01, saturated=False):
     """Exactly the tensors oracle/make_golden.py fed to the reference: un-calibrated
     problem, then the last fine conv rescaled from the pilot predictions (the golden file
     stores the first 4096 pilot values for a cross-check; the oracle recomputes all)."""
@@ -29,6 +29,8 @@ def calibrated_problem(bias_std=0.01):
     with torch.no_grad():
         p = orc.query_fine(fine, pilot, syn.default_calib())[0].numpy()
     syn.calibrate_last_layer(prob["fine"], 3, p)
+    if saturated:
+        syn.saturate(prob["fine"], 3)
     return prob, p
 
 

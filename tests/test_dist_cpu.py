@@ -1,0 +1,115 @@
+"""CPU, gloo, world_size 2: the host-side sharding logic of the N>1 path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT
+
+from pifu_b200 import dist as pdist
+
+
+def test_shard_bounds_cover_and_align():
+    for n, W, align in [(512 ** 3, 8, 512 * 512), (1000, 3, 1), (7, 8, 1), (64 ** 3, 2, 64 * 64), (0, 2, 1)]:
+        prev = 0
+        for r in range(W):
+            b, e = pdist.shard_bounds(n, W, r, align)
+            assert b == prev and e >= b
+            assert b % align == 0 or b == n
+            prev = e
+        assert prev == n
+
+
+class FakeEngine:
+    """Host stand-in for the device octree state: analytic field, same stepwise protocol."""
+
+    def __init__(self, res, fn):
+        self.res, self.fn, self.device = res, fn, torch.device("cpu")
+
+    def eval_grid(self, levels, res, calib, id_begin=0, id_end=None):
+        ids = torch.arange(id_begin, id_end)
+        return self.fn(ids)
+
+    def octree_begin(self, res, init_resolution, threshold):
+        from pifu_b200 import mesh_util
+        self.sdf = np.zeros((res,) * 3)
+        self.todo = np.zeros((res,) * 3, bool)
+        self.todo[:-1, :-1, :-1] = True
+        self.lat = np.zeros((res,) * 3, bool)
+        self.step, self.thr, self.mu = res // init_resolution, threshold, mesh_util
+
+    def octree_frontier(self):
+        if self.step <= 0:
+            return 0, torch.empty(0, dtype=torch.int64)
+        self.lat[::self.step, ::self.step, ::self.step] = True
+        self.test = self.lat & self.todo
+        return self.step, torch.from_numpy(np.flatnonzero(self.test))
+
+    def octree_commit(self, vals):
+        self.sdf[self.test] = vals.numpy().astype(np.float64)
+        self.todo[self.test] = False
+        s = self.step
+        if s > 1:
+            v = self.sdf[::s, ::s, ::s]
+            n = [k - 1 for k in v.shape]
+            cs = [v[a:a + n[0], b:b + n[1], c:c + n[2]] for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+            lo, hi = np.minimum.reduce(cs), np.maximum.reduce(cs)
+            centre = self.todo[s // 2::s, s // 2::s, s // 2::s][:n[0], :n[1], :n[2]]
+            self.mu._fill_from_skip_cells(self.sdf, self.todo, ((hi - lo) < self.thr) & centre, 0.5 * (lo + hi), s)
+        self.step = 0 if s <= 1 else s // 2
+
+    def octree_export(self, want64=False, want32=True):
+        return None, torch.from_numpy(self.sdf.astype(np.float32))
+
+
+def _field(res):
+    def fn(ids):
+        k = ids % res
+        j = (ids // res) % res
+        i = ids // (res * res)
+        x, y, z = (i.double() / res * 2 - 1), (j.double() / res * 2 - 1), (k.double() / res * 2 - 1)
+        r = torch.sqrt((x / 0.35) ** 2 + (y / 0.8) ** 2 + (z / 0.3) ** 2)
+        return torch.clamp(0.5 + 2.0 * (1.0 - r), 0, 1).float()
+    return fn
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = 32
+    eng = FakeEngine(res, _field(res))
+    dense = pdist.sharded_eval_grid(eng, 2, res, None)
+    stats = []
+    octo = pdist.sharded_eval_grid_octree(eng, 2, res, None, init_resolution=8, threshold=0.05, stats=stats,
+                                          evaluate=lambda ids: eng.fn(ids))
+    if rank == 0:
+        torch.save({"dense": dense, "octree": octo, "stats": stats}, out)
+    else:
+        assert dense is None and octo is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_single(tmp_path):
+    from pifu_b200 import mesh_util
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, 29571, out), nprocs=2, join=True)
+    got = torch.load(out)
+    res = 32
+    fn = _field(res)
+    ref_dense = fn(torch.arange(res ** 3)).view(res, res, res)
+    assert torch.equal(got["dense"], ref_dense)
+    coords = np.indices((res,) * 3).astype(np.float64)
+
+    def eval_func(p):
+        ids = (p[0] * res + p[1]) * res + p[2]
+        return fn(torch.from_numpy(ids.astype(np.int64))).numpy()
+    calls = []
+    ref_oct = mesh_util.eval_grid_octree(coords, lambda p: (calls.append(p.shape[1]), eval_func(p))[1],
+                                         init_resolution=8, num_samples=10 ** 9)
+    assert np.array_equal(got["octree"].numpy(), ref_oct.astype(np.float32))
+    assert got["stats"] == calls

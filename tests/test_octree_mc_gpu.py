@@ -1,0 +1,179 @@
+"""GPU parity of the device octree (bit-exact field vs the reference loop) and of the CUDA
+marching cubes (bit-exact topology and vertices vs the sequential CPU oracle)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import calibrated_problem, golden, oracle_states, orc, syn
+from test_oracle_golden import ANALYTIC
+from test_query_gpu import build_nets, sign_agreement
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def sat():
+    torch.set_grad_enabled(False)
+    prob, _ = calibrated_problem(saturated=True)
+    netG, netMR = build_nets(prob)
+    return prob, netG, netMR
+
+
+def _analytic_on_device(name, ids, res):
+    """The golden generator's analytic fields evaluated on device lattice ids in float64 with
+    IEEE-exact ops only (+,-,*,/,sqrt,clip) -> bit-identical to the numpy evaluation."""
+    k = (ids % res).double()
+    j = ((ids // res) % res).double()
+    i = (ids // (res * res)).double()
+    step = 2.0 / res
+    x, y, z = i * step + (-1.0), j * step + (-1.0), k * step + (-1.0)
+    if name == "ellipsoid":
+        r = torch.sqrt((x / 0.35) ** 2 + (y / 0.8) ** 2 + (z / 0.3) ** 2)
+        v = 0.5 + 2.0 * (1.0 - r)
+    else:
+        v = 0.5 + 0.6 * (x * y - z * z) + 0.25 * (x * x * x - y * z)
+    return torch.clamp(v, 0.0, 1.0).float()
+
+
+@pytest.mark.parametrize("name", ["ellipsoid", "ripple"])
+@pytest.mark.parametrize("res,init", [(64, 8), (64, 16), (96, 12), (128, 32), (128, 64)])
+def test_device_octree_bit_exact_vs_reference_loop(name, res, init):
+    """Frontier compaction + skip + fill on the device reproduce the reference's float64 field
+    bit for bit (sha256 recorded from mesh_util.eval_grid_octree itself) and evaluate exactly
+    the same number of lattice points."""
+    from pifu_b200 import get_engine
+    g = golden("octree_analytic.npz")
+    eng = get_engine("cuda")
+    eng.octree_begin(res, init, 0.05)
+    evaluated = 0
+    while True:
+        step, ids = eng.octree_frontier()
+        if step == 0:
+            break
+        assert bool((ids[1:] > ids[:-1]).all())          # C order of the boolean mask
+        evaluated += ids.numel()
+        eng.octree_commit(_analytic_on_device(name, ids, res))
+    sdf64, sdf32 = eng.octree_export(want64=True, want32=True)
+    key = "%s_%d_%d" % (name, res, init)
+    f = sdf64.cpu().numpy()
+    # numpy's x**2 and torch's x**2 are both exact products; cross-check a probe before the hash
+    assert np.array_equal(f[::7, ::5, ::3], g[key + "_probe"])
+    assert evaluated == int(g[key + "_evaluated"])
+    assert np.array_equal(sha(f), g[key + "_sha"])
+    assert np.array_equal(sdf32.cpu().numpy(), f.astype(np.float32))
+
+
+def test_octree_with_net(sat):
+    """Same evaluated values -> identical field: run the oracle's restatement of the reference
+    loop on the GPU's own dense field and compare with the device octree bit for bit; then
+    compare with the reference's field (golden) within the 16-bit-operand tolerance."""
+    prob, netG, netMR = sat
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    calib = syn.default_calib()
+    res = 64
+    dense = eng.eval_grid(2, res, calib).cpu().numpy().astype(np.float32)
+    coords, _, _ = orc.lattice_coords(res, calib)
+
+    def lookup(points):
+        idx = np.rint((points + 1.0) * (res / 2.0)).astype(np.int64)
+        idx[1] = np.rint((-points[1] + 1.0) * (res / 2.0)).astype(np.int64)     # calib flips y
+        return dense[(idx[0] * res + idx[1]) * res + idx[2]]
+    stats = []
+    ref = orc.eval_grid_octree(coords, lookup, init_resolution=16, num_samples=10 ** 9, stats=stats)
+    sdf64, _, ev = eng.eval_grid_octree(2, res, calib, init_resolution=16, want64=True)
+    assert ev == [n for _, n in stats]
+    assert np.array_equal(sdf64.cpu().numpy(), ref)
+    gold = golden("query_none.npz")["mr_octree64_init16"]
+    out = sdf64.cpu().numpy()
+    assert np.abs(out - gold).max() < 0.03          # filled midpoints inherit two corner errors
+    assert sign_agreement(out, gold) >= 0.9995
+    assert sum(ev) < 0.6 * res ** 3                  # the octree actually prunes on this field
+
+
+def _oracle_mc(vol, level=0.5):
+    from oracle import mc_oracle
+    return mc_oracle.marching_cubes(vol, level)
+
+
+def _sphere(n):
+    g = np.linspace(-1, 1, n)
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    return (0.6 - np.sqrt((x - 0.03) ** 2 + (y + 0.02) ** 2 + (z - 0.05) ** 2)).astype(np.float32) + 0.5
+
+
+def _noise(shape, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(0, 1, shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("vol", ["sphere33", "sphere64", "noise", "noise_ragged", "tiny"])
+def test_marching_cubes_bit_exact(vol):
+    from pifu_b200 import get_engine
+    v = {"sphere33": _sphere(33), "sphere64": _sphere(64), "noise": _noise((24, 24, 24), 1),
+         "noise_ragged": _noise((9, 17, 31), 2), "tiny": _noise((2, 2, 2), 5)}[vol]
+    if vol == "tiny":
+        v[0, 0, 0], v[1, 1, 1] = 0.9, 0.1
+    rv, rf, rn, rval, _ = _oracle_mc(v)
+    eng = get_engine("cuda")
+    verts, faces, normals, values = eng.marching_cubes(torch.from_numpy(v).cuda(), 0.5)
+    assert np.array_equal(faces.cpu().numpy(), rf)                    # topology + numbering: bit-exact
+    assert np.array_equal(verts.cpu().numpy(), rv)                    # float64 positions: bit-exact
+    assert np.abs(verts.cpu().numpy() - rv).max() <= 1e-5             # (north_star's stated tolerance)
+    assert np.array_equal(values.cpu().numpy(), rval)
+    assert np.abs(normals.cpu().numpy() - rn).max() < 1e-6
+
+
+def test_marching_cubes_no_surface():
+    from pifu_b200 import get_engine
+    eng = get_engine("cuda")
+    with pytest.raises(ValueError):
+        eng.marching_cubes(torch.full((8, 8, 8), 0.25, device="cuda"), 0.5)
+
+
+def test_reconstruction_end_to_end(sat):
+    """mesh_util.reconstruction (reference signature): device octree + device MC; the mesh must
+    equal the CPU oracle's MC of the very same field, transformed as mesh_util.py:87-92."""
+    from pifu_b200 import mesh_util
+    prob, netG, netMR = sat
+    calib = syn.default_calib().cuda()
+    res = 64
+    out = mesh_util.reconstruction(netMR, "cuda", calib, res, None, None, thresh=0.5, use_octree=True,
+                                   num_samples=5000)
+    assert out != -1
+    verts, faces, normals, values = out
+    assert verts.dtype == np.float64 and faces.dtype == np.int32 and normals.dtype == np.float32
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    _, sdf32, _ = eng.eval_grid_octree(2, res, calib[0], want64=False, want32=True)
+    rv, rf, _, _, _ = _oracle_mc(sdf32.cpu().numpy())
+    mat = np.eye(4)
+    mat[0, 0] = mat[1, 1] = mat[2, 2] = 2.0 / res
+    mat[:3, 3] = -1
+    trans = np.linalg.inv(calib[0].cpu().numpy()) @ mat
+    rv = (trans[:3, :3] @ rv.T + trans[:3, 3:4]).T
+    assert np.linalg.det(trans[:3, :3]) < 0
+    assert np.array_equal(faces, rf[:, ::-1])
+    assert np.abs(verts - rv).max() < 1e-12
+    # dense evaluation gives the same surface wherever the octree did not skip
+    dense = mesh_util.reconstruction(netMR, "cuda", calib, res, None, None, use_octree=False)
+    assert dense != -1 and abs(len(dense[0]) - len(verts)) < 0.2 * len(verts)
+    # an empty field follows the reference's error convention
+    flat = mesh_util.reconstruction(_Flat(), "cuda", calib, 16, None, None, use_octree=False)
+    assert flat == -1
+
+
+class _Flat:
+    """A foreign `net` (not this package's): generic callback path of reconstruction()."""
+
+    def query(self, samples, calib):
+        self.preds = torch.full((1, 1, samples.shape[2]), 0.25, device=samples.device)
+
+    def get_preds(self):
+        return self.preds

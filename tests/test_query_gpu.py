@@ -64,7 +64,7 @@ def test_mr_query_parity(setup, impl):
     netG, netMR = build_nets(prob)
     get_engine("cuda").set_gemm_impl(1 if impl == "simt" else 0)
     try:
-        pts = syn.random_points(20000, 5)
+        pts = syn.random_points(200000 if impl == "tcgen05" else 20000, 5)
         calib = syn.default_calib()
         ref, ref_low, ref_phi = orc.query_fine(fine, pts, calib)
         netMR.query(pts.cuda(), calib.cuda())
@@ -117,12 +117,15 @@ def test_calc_normal(setup):
     _, netMR = build_nets(prob)
     pts = syn.random_points(2048)[:, :, :256]
     calib = syn.default_calib()
-    ref, raw = orc.calc_normal_fine(fine, pts, calib, calib, delta=0.001, return_raw=True)
-    netMR.calc_normal(pts[:, None].cuda(), calib[:, None].cuda(), calib.cuda(), delta=0.001)
+    # finite differences amplify the 16-bit operand noise by 1/delta: compare where the
+    # occupancy difference is well above it
+    ref, raw = orc.calc_normal_fine(fine, pts, calib, calib, delta=0.01, return_raw=True)
+    netMR.calc_normal(pts[:, None].cuda(), calib[:, None].cuda(), calib.cuda(), delta=0.01)
     n = netMR.nmls.cpu().numpy()
-    ok = np.linalg.norm(raw.numpy(), axis=1) > 2e-3     # difference well above the 16-bit operand noise
+    assert n.shape == ref.shape
+    ok = np.linalg.norm(raw.numpy(), axis=1) > 5e-3
     assert ok.sum() > 10
-    assert ((n * ref.numpy()).sum(1)[ok] > 0.99).all()
+    assert ((n * ref.numpy()).sum(1)[ok] > 0.98).all()
 
 
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 5000])
@@ -153,6 +156,21 @@ def test_chunk_invariance(setup):
         assert torch.equal(a, netMR.get_preds())
     finally:
         eng.set_chunk_tiles(296)
+
+
+def test_saturated_field(setup):
+    """Octree / marching-cubes field (last layer x8): the logit-domain error of 16-bit operands
+    shows as up to ~6e-3 in occupancy at the surface; the sign at 0.5 must still agree."""
+    prob, _ = calibrated_problem(saturated=True)
+    _, fine = oracle_states(prob)
+    _, netMR = build_nets(prob)
+    pts = syn.random_points(200000, 9)
+    calib = syn.default_calib()
+    ref = orc.query_fine(fine, pts, calib)[0]
+    netMR.query(pts.cuda(), calib.cuda())
+    out = netMR.get_preds().cpu()
+    assert (out - ref).abs().max().item() < 8e-3
+    assert sign_agreement(out.numpy(), ref.numpy()) >= 0.9999
 
 
 def test_dense_grid_parity(setup):
