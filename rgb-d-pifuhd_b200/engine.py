@@ -268,4 +268,4 @@ class _DevView:
     """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
 
     def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
