@@ -27,8 +27,9 @@ typedef struct pifu_ctx pifu_ctx;
 #define PIFU_LEVEL_COARSE 0 /* PIFuNetwNML  (PIFuNetwNML.py:17-71)  */
 #define PIFU_LEVEL_FINE 1   /* PIFuMRNet    (PIFuMRNet.py:14-57)    */
 
-#define PIFU_GEMM_TCGEN05 0 /* tensor-core layer kernel (default, product path) */
+#define PIFU_GEMM_TCGEN05 0 /* tensor-core layer kernel, CTA pairs / cta_group::2 (default, product path) */
 #define PIFU_GEMM_SIMT 1    /* CUDA-core cross-check of the same operands (tests only) */
+#define PIFU_GEMM_TCGEN05_1CTA 2 /* tensor-core layer kernel without CTA pairs (A/B measurements) */
 
 const char* pifu_last_error(void);
 int pifu_abi_version(void);

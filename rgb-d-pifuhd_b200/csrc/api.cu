@@ -142,7 +142,8 @@ ASeg make_seg(const pifu_ctx* c, const SegRef& r) {
 int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
     c->launches += 1;
     if (c->gemm_impl == PIFU_GEMM_SIMT) { c->launches += g.head_w ? 1 : 0; return launch_gemm_simt(g, s); }
-    if (!c->profile) return launch_gemm_tc(g, c->num_sms, s);
+    const int pair = c->gemm_impl == PIFU_GEMM_TCGEN05 ? 1 : 0;
+    if (!c->profile) return launch_gemm_tc(g, c->num_sms, pair, s);
     const int e = static_cast<int>(c->timed.size()) * 2;
     while (static_cast<int>(c->ev_pool.size()) < e + 2) {
         cudaEvent_t ev;
@@ -150,7 +151,7 @@ int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
         c->ev_pool.push_back(ev);
     }
     PIFU_CUDA(cudaEventRecord(c->ev_pool[e], s));
-    const int rc = launch_gemm_tc(g, c->num_sms, s);
+    const int rc = launch_gemm_tc(g, c->num_sms, pair, s);
     PIFU_CUDA(cudaEventRecord(c->ev_pool[e + 1], s));
     c->timed.push_back({e, flops});
     return rc;
@@ -319,9 +320,12 @@ int pifu_create(int device, pifu_ctx** out) {
     pifu_ctx* c = new pifu_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    c->chunk_tiles = 2 * c->num_sms;
+    c->chunk_tiles = 16 * c->num_sms;      // 16 waves per layer launch amortise pipeline fill/drain (measured)
     if (const char* e = getenv("PIFU_CHUNK_TILES")) { int v = atoi(e); if (v > 0) c->chunk_tiles = v; }
-    if (const char* e = getenv("PIFU_GEMM_IMPL")) { if (!strcmp(e, "simt")) c->gemm_impl = PIFU_GEMM_SIMT; }
+    if (const char* e = getenv("PIFU_GEMM_IMPL")) {
+        if (!strcmp(e, "simt")) c->gemm_impl = PIFU_GEMM_SIMT;
+        if (!strcmp(e, "tc1")) c->gemm_impl = PIFU_GEMM_TCGEN05_1CTA;
+    }
     *out = c;
     return 0;
 }
@@ -346,7 +350,7 @@ int pifu_set_options(pifu_ctx* c, int perspective, float z_mul, float z_div) {
 }
 
 int pifu_set_gemm_impl(pifu_ctx* c, int impl) {
-    if (!c || (impl != PIFU_GEMM_TCGEN05 && impl != PIFU_GEMM_SIMT)) { set_error("bad gemm impl"); return -1; }
+    if (!c || impl < PIFU_GEMM_TCGEN05 || impl > PIFU_GEMM_TCGEN05_1CTA) { set_error("bad gemm impl"); return -1; }
     c->gemm_impl = impl;
     return 0;
 }

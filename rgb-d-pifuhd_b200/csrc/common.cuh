@@ -72,7 +72,7 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 // ------------------------------------------------------------------ kernel launchers
-int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t s);     // tcgen05 / TMEM / TMA
+int launch_gemm_tc(const GemmArgs& a, int num_sms, int pair, cudaStream_t s);   // tcgen05 / TMEM / TMA
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);                // CUDA-core cross-check
 
 struct PointSource {

@@ -34,14 +34,18 @@ def sign_agreement(a, b, level=0.5):
     return float(((a > level) == (b > level)).mean())
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
-@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 272, 512), (1000, 832, 256), (4096, 1024, 512)])
+IMPL = {"tcgen05": 0, "simt": 1, "tc1": 2}     # CTA-pair tcgen05 (product), CUDA-core check, 1-CTA tcgen05
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc1", "tcgen05"])
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 272, 512), (1000, 832, 256), (4096, 1024, 512),
+                                   (40000, 320, 1024)])
 def test_layer_kernel_vs_torch(impl, M, K, N):
     """One Conv1d(k=1)+leaky_relu layer; fp16 operands, fp32 accumulate -> compare with fp32 torch
     on the same fp16-rounded operands (tight) and on the fp32 operands (fp16 rounding only)."""
     from pifu_b200 import get_engine
     eng = get_engine("cuda")
-    eng.set_gemm_impl(1 if impl == "simt" else 0)
+    eng.set_gemm_impl(IMPL[impl])
     try:
         g = torch.Generator().manual_seed(M + K + N)
         X = torch.randn(M, K, generator=g)
@@ -56,15 +60,15 @@ def test_layer_kernel_vs_torch(impl, M, K, N):
         eng.set_gemm_impl(0)
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("impl", ["simt", "tc1", "tcgen05"])
 def test_mr_query_parity(setup, impl):
     from pifu_b200 import get_engine
     prob = setup
     _, fine = oracle_states(prob)
     netG, netMR = build_nets(prob)
-    get_engine("cuda").set_gemm_impl(1 if impl == "simt" else 0)
+    get_engine("cuda").set_gemm_impl(IMPL[impl])
     try:
-        pts = syn.random_points(200000 if impl == "tcgen05" else 20000, 5)
+        pts = syn.random_points(20000 if impl == "simt" else 200000, 5)
         calib = syn.default_calib()
         ref, ref_low, ref_phi = orc.query_fine(fine, pts, calib)
         netMR.query(pts.cuda(), calib.cuda())
@@ -155,7 +159,7 @@ def test_chunk_invariance(setup):
         netMR.query(pts, calib)
         assert torch.equal(a, netMR.get_preds())
     finally:
-        eng.set_chunk_tiles(296)
+        eng.set_chunk_tiles(16 * 148)
 
 
 def test_saturated_field(setup):
