@@ -126,6 +126,20 @@ long long pifu_launch_count(pifu_ctx* ctx);
 int pifu_profile_enable(pifu_ctx* ctx, int on);
 int pifu_profile_read(pifu_ctx* ctx, long long* launches, double* total_ms, double* total_flops);
 
+/* Same, restricted to one kernel kind (0 = per-layer tcgen05 kernel, 1 = lattice chain kernel);
+ * does not clear the records. */
+int pifu_profile_read_kind(pifu_ctx* ctx, int kind, long long* launches, double* total_ms, double* total_flops);
+
+/* Lattice chain kernel (whole MLP stack of a 128-point lattice-column tile in one kernel,
+ * activations resident in shared/tensor memory).  pifu_eval_grid uses it automatically when
+ * both MLPs have the reference configuration (options.py:86-87,92-93), the projection is
+ * orthogonal, R2 is a multiple of 128 and the calibration does not mix z into x/y; anything
+ * else takes the per-layer kernels.  pifu_set_chain(ctx, 0) forces the per-layer kernels (A/B
+ * measurements, parity tests between the two paths); pifu_chain_ready reports 1 when the
+ * chain operands are built and enabled. */
+int pifu_set_chain(pifu_ctx* ctx, int enabled);
+int pifu_chain_ready(pifu_ctx* ctx);
+
 /* Test hook: one layer, Y = act(W X^T + b), through the layer kernel (synchronous).  All
  * pointers are device fp32: X [M][K] (points x channels), W [N][K], b [N]; Y is channel-major
  * [N][M] like the reference's [C, N] activations. */

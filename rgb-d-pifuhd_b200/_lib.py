@@ -45,6 +45,9 @@ SIGNATURES = {
     "pifu_launch_count": (ctypes.c_longlong, [VP]),
     "pifu_profile_enable": (ctypes.c_int, [VP, ctypes.c_int]),
     "pifu_profile_read": (ctypes.c_int, [VP, c_ll_p, c_double_p, c_double_p]),
+    "pifu_profile_read_kind": (ctypes.c_int, [VP, ctypes.c_int, c_ll_p, c_double_p, c_double_p]),
+    "pifu_set_chain": (ctypes.c_int, [VP, ctypes.c_int]),
+    "pifu_chain_ready": (ctypes.c_int, [VP]),
     "pifu_debug_gemm": (ctypes.c_int, [VP, VP, VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, VP, VP]),
 }

@@ -59,6 +59,28 @@ struct Level {
 
 struct Buffer { int nkb = 0; uint8_t* ptr = nullptr; };
 
+// Operands of the lattice chain kernel (chain_tc.cu), built when the two MLPs have the
+// reference configuration (`options.py:86-87,92-93`): coarse 257-1024-512-256-..., fine
+// 272-512-256-128-1.
+struct ChainPlan {
+    bool coarse_ok = false, fine_ok = false;
+    bool enabled = true;
+    uint8_t* wstream = nullptr;      // chain::WSTREAM_BYTES, stages in consumption order
+    uint8_t* w_colA = nullptr;       // feature columns of coarse L0 and L2: N = 1280, F layout (5 k-blocks)
+    float* bias_colA = nullptr;      // [b0 ; b2]
+    uint8_t* w_colB = nullptr;       // fine-feature columns of fine L0, L1, L2: N = 896, FF layout (1 k-block)
+    float* bias_colB = nullptr;      // [bF0 ; bF1 ; bF2]
+    float* wz0 = nullptr;            // z column of coarse L0
+    float* wz2 = nullptr;            // z column of coarse L2
+    float* b1 = nullptr;
+    float* w3 = nullptr;             // fine Conv1d -> 1
+    float b3 = 0.f;
+    float* cc = nullptr;             // per-column constants of the current column chunk
+    int cc_cols = 0;
+    int* colmaps = nullptr;          // scratch for the packer
+};
+constexpr int CHAIN_COLS_PER_CHUNK = 148 * 32;
+
 }  // namespace
 
 struct pifu_ctx {
@@ -79,7 +101,8 @@ struct pifu_ctx {
     // per-launch CUDA-event timing of the layer kernel (bench roofline), off by default
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
-    struct Timed { int ev; double flops; };
+    struct Timed { int ev; double flops; int kind; };      // kind 0 layer kernel, 1 chain kernel
+    ChainPlan cplan;
     std::vector<Timed> timed;
     pifu::OctreeState* octree = nullptr;
     pifu::McState* mc = nullptr;
@@ -139,11 +162,9 @@ ASeg make_seg(const pifu_ctx* c, const SegRef& r) {
     return s;
 }
 
-int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
-    c->launches += 1;
-    if (c->gemm_impl == PIFU_GEMM_SIMT) { c->launches += g.head_w ? 1 : 0; return launch_gemm_simt(g, s); }
-    const int pair = c->gemm_impl == PIFU_GEMM_TCGEN05 ? 1 : 0;
-    if (!c->profile) return launch_gemm_tc(g, c->num_sms, pair, s);
+template <typename F>
+int run_timed(pifu_ctx* c, int kind, double flops, cudaStream_t s, F&& launch) {
+    if (!c->profile) return launch();
     const int e = static_cast<int>(c->timed.size()) * 2;
     while (static_cast<int>(c->ev_pool.size()) < e + 2) {
         cudaEvent_t ev;
@@ -151,10 +172,17 @@ int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
         c->ev_pool.push_back(ev);
     }
     PIFU_CUDA(cudaEventRecord(c->ev_pool[e], s));
-    const int rc = launch_gemm_tc(g, c->num_sms, pair, s);
+    const int rc = launch();
     PIFU_CUDA(cudaEventRecord(c->ev_pool[e + 1], s));
-    c->timed.push_back({e, flops});
+    c->timed.push_back({e, flops, kind});
     return rc;
+}
+
+int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
+    c->launches += 1;
+    if (c->gemm_impl == PIFU_GEMM_SIMT) { c->launches += g.head_w ? 1 : 0; return launch_gemm_simt(g, s); }
+    const int pair = c->gemm_impl == PIFU_GEMM_TCGEN05 ? 1 : 0;
+    return run_timed(c, 0, flops, s, [&]() { return launch_gemm_tc(g, c->num_sms, pair, s); });
 }
 
 // hidden layers [first, last] of a level; the fused last layer rides on layer n_layers-2
@@ -247,6 +275,213 @@ int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const floa
     return 0;
 }
 
+
+// ----------------------------------------------------------------------------- chain plan
+void free_chain(ChainPlan& P, bool coarse_too) {
+    auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+    if (coarse_too) {
+        fr(P.wstream); fr(P.w_colA); fr(P.bias_colA); fr(P.wz0); fr(P.wz2); fr(P.b1); fr(P.colmaps);
+        P.coarse_ok = false;
+    }
+    fr(P.w_colB); fr(P.bias_colB); fr(P.w3);
+    P.fine_ok = false;
+}
+
+size_t chain_stage_offset(int s) {
+    return s < chain::STAGES_256 ? static_cast<size_t>(s) * 256 * ROW_BYTES
+                                 : static_cast<size_t>(chain::STAGES_256) * 256 * ROW_BYTES +
+                                   static_cast<size_t>(s - chain::STAGES_256) * 128 * ROW_BYTES;
+}
+
+// pack `nst` consecutive weight stages: stage i = rows [row0, row0 + N) of W, source columns
+// col0 + 64 i .. + 63, as two N/2-row halves (one per CTA of a pair)
+int chain_pack_stages(ChainPlan& P, int first_stage, int nst, const float* W, int cin, int row0, int col0,
+                      int N, cudaStream_t s) {
+    std::vector<int> m(static_cast<size_t>(nst) * KB);
+    for (int i = 0; i < nst; ++i)
+        for (int k = 0; k < KB; ++k) m[static_cast<size_t>(i) * KB + k] = col0 + i * KB + k;
+    int* dm = P.colmaps + static_cast<size_t>(first_stage) * KB;
+    PIFU_CUDA(cudaMemcpyAsync(dm, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    PIFU_CUDA(cudaStreamSynchronize(s));            // m is a stack-lifetime host buffer
+    for (int i = 0; i < nst; ++i)
+        if (launch_pack_weights(W + static_cast<size_t>(row0) * cin, cin, dm + i * KB, 1, N, N / 2,
+                                P.wstream + chain_stage_offset(first_stage + i), s)) return -1;
+    return 0;
+}
+
+// feature-column weights of one layer appended to a "column constants" GEMM operand:
+// packed column k < nfeat reads source column col0 + k, all other packed columns are zero
+int chain_pack_colw(ChainPlan& P, const float* W, int cin, int col0, int nfeat, int num_kb, int N, int BN,
+                    uint8_t* dst, cudaStream_t s) {
+    std::vector<int> m(static_cast<size_t>(num_kb) * KB, -1);
+    for (int k = 0; k < nfeat; ++k) m[k] = col0 + k;
+    int* dm = P.colmaps + static_cast<size_t>(chain::STAGES) * KB;     // scratch behind the stage maps
+    PIFU_CUDA(cudaMemcpyAsync(dm, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    PIFU_CUDA(cudaStreamSynchronize(s));
+    if (launch_pack_weights(W, cin, dm, num_kb, N, BN, dst, s)) return -1;
+    PIFU_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int build_chain_coarse(pifu_ctx* c, const float* const* weights, const float* const* biases, cudaStream_t s) {
+    using namespace chain;
+    ChainPlan& P = c->cplan;
+    free_chain(P, true);
+    const Level& L = c->lv[0];
+    if (!(L.n_layers >= 4 && L.dims[0] == 257 && L.dims[1] == C0 && L.dims[2] == C1 && L.dims[3] == C2 &&
+          !L.is_res(1) && L.is_res(2) && L.merge == 2 && c->bufs[c->buf_F].nkb == 5)) return 0;
+    PIFU_CUDA(cudaMalloc(&P.wstream, WSTREAM_BYTES));
+    PIFU_CUDA(cudaMalloc(&P.colmaps, (static_cast<size_t>(STAGES) + 8) * KB * sizeof(int)));
+    PIFU_CUDA(cudaMalloc(&P.w_colA, static_cast<size_t>(C0 + C2) * 5 * ROW_BYTES));
+    PIFU_CUDA(cudaMalloc(&P.bias_colA, (C0 + C2) * sizeof(float)));
+    PIFU_CUDA(cudaMalloc(&P.wz0, C0 * sizeof(float)));
+    PIFU_CUDA(cudaMalloc(&P.wz2, C2 * sizeof(float)));
+    PIFU_CUDA(cudaMalloc(&P.b1, C1 * sizeof(float)));
+    const int cin2 = C1 + 257;
+    // J0 / J1: coarse L1 output halves; J2: the y part of coarse L2 (cat[y, input], MLP.py:61-64)
+    if (chain_pack_stages(P, 0, 16, weights[1], C0, 0, 0, 256, s)) return -1;
+    if (chain_pack_stages(P, 16, 16, weights[1], C0, 256, 0, 256, s)) return -1;
+    if (chain_pack_stages(P, 32, 8, weights[2], cin2, 0, 0, 256, s)) return -1;
+    // per-column constants: coarse L0 feature columns [0, 256), coarse L2 feature columns [512, 768)
+    if (chain_pack_colw(P, weights[0], 257, 0, 256, 5, C0, 256, P.w_colA, s)) return -1;
+    if (chain_pack_colw(P, weights[2], cin2, C1, 256, 5, C2, 256,
+                        P.w_colA + static_cast<size_t>(C0) * 5 * ROW_BYTES, s)) return -1;
+    PIFU_CUDA(cudaMemcpyAsync(P.bias_colA, biases[0], C0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(P.bias_colA + C0, biases[2], C2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(P.b1, biases[1], C1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // z columns (`PIFuNetwNML.py:128-129`: z is the last input channel)
+    PIFU_CUDA(cudaMemcpy2DAsync(P.wz0, sizeof(float), weights[0] + 256, 257 * sizeof(float), sizeof(float), C0,
+                                cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpy2DAsync(P.wz2, sizeof(float), weights[2] + C1 + 256, cin2 * sizeof(float), sizeof(float), C2,
+                                cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaStreamSynchronize(s));
+    c->launches += 42;
+    P.coarse_ok = true;
+    return 0;
+}
+
+int build_chain_fine(pifu_ctx* c, const float* const* weights, const float* const* biases, cudaStream_t s) {
+    using namespace chain;
+    ChainPlan& P = c->cplan;
+    free_chain(P, false);
+    const Level& L = c->lv[1];
+    if (!P.coarse_ok) return 0;
+    if (!(L.n_layers == 4 && L.dims[0] == 16 + C2 && L.dims[1] == F0 && L.dims[2] == F1 && L.dims[3] == F2 &&
+          L.is_res(1) && L.is_res(2) && !L.is_res(3) && c->bufs[c->buf_FF].nkb == 1)) return 0;
+    PIFU_CUDA(cudaMalloc(&P.w_colB, static_cast<size_t>(F0 + F1 + F2) * ROW_BYTES));
+    PIFU_CUDA(cudaMalloc(&P.bias_colB, (F0 + F1 + F2) * sizeof(float)));
+    PIFU_CUDA(cudaMalloc(&P.w3, F2 * sizeof(float)));
+    const int cin0 = 16 + C2, cin1 = F0 + cin0, cin2 = F1 + cin0;
+    // input order [fine feat ; phi] (`PIFuMRNet.py:170-171`), skip concat [y ; input] (`MLP.py:61-64`)
+    if (chain_pack_stages(P, 40, 4, weights[0], cin0, 0, 16, 256, s)) return -1;            // J3: phi part
+    if (chain_pack_stages(P, 44, 4, weights[0], cin0, 256, 16, 256, s)) return -1;          // J4
+    if (chain_pack_stages(P, 48, 4, weights[1], cin1, 0, F0 + 16, 256, s)) return -1;       // J5: phi part
+    if (chain_pack_stages(P, 52, 8, weights[1], cin1, 0, 0, 256, s)) return -1;             //     y part
+    if (chain_pack_stages(P, 60, 4, weights[2], cin2, 0, F1 + 16, 128, s)) return -1;       // J6: phi part
+    if (chain_pack_stages(P, 64, 4, weights[2], cin2, 0, 0, 128, s)) return -1;             //     y part
+    if (chain_pack_colw(P, weights[0], cin0, 0, 16, 1, F0, 128, P.w_colB, s)) return -1;
+    if (chain_pack_colw(P, weights[1], cin1, F0, 16, 1, F1, 128, P.w_colB + static_cast<size_t>(F0) * ROW_BYTES, s)) return -1;
+    if (chain_pack_colw(P, weights[2], cin2, F1, 16, 1, F2, 128,
+                        P.w_colB + static_cast<size_t>(F0 + F1) * ROW_BYTES, s)) return -1;
+    PIFU_CUDA(cudaMemcpyAsync(P.bias_colB, biases[0], F0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(P.bias_colB + F0, biases[1], F1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(P.bias_colB + F0 + F1, biases[2], F2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(P.w3, weights[3], F2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaStreamSynchronize(s));
+    P.b3 = L.head_b;
+    c->launches += 31;
+    P.fine_ok = true;
+    return 0;
+}
+
+bool chain_eligible(const pifu_ctx* c, int levels, int R2, const float* calib, const double* calib_inv) {
+    const ChainPlan& P = c->cplan;
+    // x and y of the projected point must not depend on the lattice index along axis 2
+    return levels == 2 && P.enabled && P.coarse_ok && P.fine_ok && c->gemm_impl == PIFU_GEMM_TCGEN05 &&
+           !c->perspective && R2 % TILE_M == 0 && calib[2] == 0.f && calib[6] == 0.f &&
+           calib_inv[2] == 0.0 && calib_inv[6] == 0.0;
+}
+
+void lattice_source(PointSource& src, int R0, int R1, int R2, const double* calib_inv);
+
+// lattice ids [id_a, id_b), both multiples of 128, through the chain kernel
+int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_b, const float* calib,
+              const double* calib_inv, float* out, cudaStream_t s) {
+    using namespace chain;
+    ChainPlan& P = c->cplan;
+    const long long tpc = R2 / TILE_M;
+    const long long ta = id_a / TILE_M, tb = id_b / TILE_M;
+    const long long col_a = ta / tpc, col_b = (tb + tpc - 1) / tpc;
+    long long per_chunk = CHAIN_COLS_PER_CHUNK;
+    const long long ws_cols = static_cast<long long>(c->chunk_tiles) * TILE_M;
+    if (per_chunk > ws_cols) per_chunk = ws_cols;
+    if (P.cc_cols < per_chunk) {
+        if (P.cc) { cudaFree(P.cc); P.cc = nullptr; }
+        PIFU_CUDA(cudaMalloc(&P.cc, static_cast<size_t>(per_chunk) * CC_FLOATS * sizeof(float)));
+        P.cc_cols = static_cast<int>(per_chunk);
+    }
+    Level& LC = c->lv[0];
+    Level& LF = c->lv[1];
+    for (long long cb = col_a; cb < col_b; cb += per_chunk) {
+        const long long ce = cb + per_chunk < col_b ? cb + per_chunk : col_b;
+        const int ncol = static_cast<int>(ce - cb);
+        const int m_tiles = (ncol + TILE_M - 1) / TILE_M;
+        // ---- one sample per column (k = 0): feature rows + in-bounds masks of the column
+        GatherArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        lattice_source(ga.src, R0, R1, R2, calib_inv);
+        ga.src.id0 = cb * R2;
+        ga.src.id_stride = R2;
+        ga.n = ncol;
+        memcpy(ga.cg, calib, 12 * sizeof(float));
+        memcpy(ga.cl, calib, 12 * sizeof(float));
+        ga.z_mul = c->z_mul; ga.z_div = c->z_div;
+        ga.feat_c = LC.feat; ga.Hc = LC.H; ga.Wc = LC.W; ga.Cc = LC.C;
+        ga.F = c->bufs[c->buf_F].ptr; ga.kbF = c->bufs[c->buf_F].nkb;
+        ga.feat_f = LF.feat; ga.Hf = LF.H; ga.Wf = LF.W; ga.Cf = LF.C;
+        ga.FF = c->bufs[c->buf_FF].ptr; ga.kbFF = c->bufs[c->buf_FF].nkb;
+        ga.mask = c->mask;
+        c->launches += 1;
+        if (launch_gather(ga, s)) return -1;
+        // ---- per-column constants cc = [W0f feat + b0 | W2f feat + b2 | WF0f ff + bF0 | WF1f ff + bF1 | WF2f ff + bF2]
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.nseg = 1;
+        g.seg[0].base = ga.F; g.seg[0].kb_stride = ga.kbF; g.seg[0].kb_off = 0; g.seg[0].nkb = ga.kbF;
+        g.num_kb = ga.kbF;
+        g.w = P.w_colA; g.bias = P.bias_colA; g.N = C0 + C2; g.m_tiles = m_tiles; g.n_valid = ncol;
+        g.out_f32 = P.cc; g.f32_ld = CC_FLOATS; g.f32_col0 = 0;
+        if (run_gemm(c, g, 2.0 * ncol * 256.0 * (C0 + C2), s)) return -1;
+        g.seg[0].base = ga.FF; g.seg[0].kb_stride = ga.kbFF; g.seg[0].nkb = ga.kbFF;
+        g.num_kb = ga.kbFF;
+        g.w = P.w_colB; g.bias = P.bias_colB; g.N = F0 + F1 + F2;
+        g.f32_col0 = C0 + C2;
+        if (run_gemm(c, g, 2.0 * ncol * 16.0 * (F0 + F1 + F2), s)) return -1;
+        // ---- the tiles of these columns
+        const long long t0 = ta > cb * tpc ? ta : cb * tpc;
+        const long long t1 = tb < ce * tpc ? tb : ce * tpc;
+        if (t1 <= t0) continue;
+        ChainArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.wstream = P.wstream; ca.cc = P.cc; ca.colmask = c->mask;
+        ca.wz0 = P.wz0; ca.wz2 = P.wz2; ca.b1 = P.b1; ca.w3 = P.w3; ca.b3 = P.b3;
+        ca.tile0 = t0; ca.n_tiles = static_cast<int>(t1 - t0); ca.col0 = cb;
+        ca.R0 = R0; ca.R1 = R1; ca.R2 = R2;
+        memcpy(ca.step, ga.src.step, sizeof(ca.step));
+        memcpy(ca.bmin, ga.src.bmin, sizeof(ca.bmin));
+        memcpy(ca.cinv, ga.src.cinv, sizeof(ca.cinv));
+        memcpy(ca.cg, calib, 12 * sizeof(float));
+        ca.z_mul = c->z_mul; ca.z_div = c->z_div;
+        ca.out = out + (t0 * TILE_M - id_a);
+        c->launches += 1;
+        // algorithmic work: the get_preds() layer stack of every point (coarse L0-L2, fine L0-L3)
+        const double flops = static_cast<double>(ca.n_tiles) * TILE_M * 2.0 *
+                             (257.0 * C0 + 1.0 * C0 * C1 + 769.0 * C2 + 272.0 * F0 + 784.0 * F1 + 528.0 * F2 + F2);
+        if (run_timed(c, 1, flops, s, [&]() { return launch_chain(ca, c->num_sms, s); })) return -1;
+    }
+    return 0;
+}
+
 int check_ready(pifu_ctx* c, int levels) {
     if (!c) { set_error("null context"); return -1; }
     if (levels != 1 && levels != 2) { set_error("levels must be 1 or 2"); return -1; }
@@ -322,6 +557,7 @@ int pifu_create(int device, pifu_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->chunk_tiles = 16 * c->num_sms;      // 16 waves per layer launch amortise pipeline fill/drain (measured)
     if (const char* e = getenv("PIFU_CHUNK_TILES")) { int v = atoi(e); if (v > 0) c->chunk_tiles = v; }
+    if (const char* e = getenv("PIFU_CHAIN")) c->cplan.enabled = atoi(e) != 0;
     if (const char* e = getenv("PIFU_GEMM_IMPL")) {
         if (!strcmp(e, "simt")) c->gemm_impl = PIFU_GEMM_SIMT;
         if (!strcmp(e, "tc1")) c->gemm_impl = PIFU_GEMM_TCGEN05_1CTA;
@@ -335,6 +571,8 @@ void pifu_destroy(pifu_ctx* c) {
     cudaSetDevice(c->device);
     free_workspace(c);
     for (int l = 0; l < 2; ++l) { free_level(c->lv[l]); if (c->lv[l].feat) cudaFree(c->lv[l].feat); }
+    free_chain(c->cplan, true);
+    if (c->cplan.cc) cudaFree(c->cplan.cc);
     pifu::octree_free(c->octree);
     pifu::mc_free(c->mc);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -388,6 +626,34 @@ int pifu_profile_read(pifu_ctx* c, long long* launches, double* total_ms, double
     return 0;
 }
 
+int pifu_profile_read_kind(pifu_ctx* c, int kind, long long* launches, double* total_ms, double* total_flops) {
+    if (!c || !launches || !total_ms || !total_flops) { set_error("null argument"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    PIFU_CUDA(cudaDeviceSynchronize());
+    double ms = 0.0, fl = 0.0;
+    long long n = 0;
+    for (const auto& t : c->timed) {
+        if (t.kind != kind) continue;
+        float e = 0.f;
+        PIFU_CUDA(cudaEventElapsedTime(&e, c->ev_pool[t.ev], c->ev_pool[t.ev + 1]));
+        ms += e;
+        fl += t.flops;
+        n += 1;
+    }
+    *launches = n;
+    *total_ms = ms;
+    *total_flops = fl;
+    return 0;
+}
+
+int pifu_set_chain(pifu_ctx* c, int enabled) {
+    if (!c) { set_error("null context"); return -1; }
+    c->cplan.enabled = enabled != 0;
+    return 0;
+}
+
+int pifu_chain_ready(pifu_ctx* c) { return c && c->cplan.coarse_ok && c->cplan.fine_ok && c->cplan.enabled ? 1 : 0; }
+
 int pifu_set_features(pifu_ctx* c, int level, const float* nchw, int C, int H, int W, void* stream) {
     if (!c || level < 0 || level > 1 || !nchw) { set_error("bad arguments to pifu_set_features"); return -1; }
     PIFU_CUDA(cudaSetDevice(c->device));
@@ -409,6 +675,7 @@ int pifu_set_mlp(pifu_ctx* c, int level, int n_channels, const int* ch, int n_re
     if (level == 1 && !c->lv[0].set) { set_error("set the coarse MLP before the fine one"); return -1; }
     Level& L = c->lv[level];
     if (level == 0 && c->lv[1].set) free_level(c->lv[1]);      // fine plan refers to coarse buffers
+    free_chain(c->cplan, level == 0);
     free_level(L);
     if (level == 0) {
         free_workspace(c);
@@ -525,6 +792,8 @@ int pifu_set_mlp(pifu_ctx* c, int level, int n_channels, const int* ch, int n_re
     }
     if (level == 0) c->n_coarse_bufs = static_cast<int>(c->bufs.size());
     L.set = true;
+    if (level == 0) { if (build_chain_coarse(c, weights, biases, s)) return -1; }
+    else if (build_chain_fine(c, weights, biases, s)) return -1;
     return 0;
 }
 
@@ -561,16 +830,28 @@ int pifu_eval_grid(pifu_ctx* c, int levels, int R0, int R1, int R2, long long id
         id_end > static_cast<long long>(R0) * R1 * R2) { set_error("bad arguments to pifu_eval_grid"); return -1; }
     PIFU_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // whole 128-point tiles of lattice columns go through the chain kernel; ragged ends (and
+    // every configuration chain_eligible() rejects) through the per-layer kernels
+    long long ca = id_begin, cb = id_begin;
+    if (chain_eligible(c, levels, R2, calib, calib_inv)) {
+        ca = (id_begin + TILE_M - 1) / TILE_M * TILE_M;
+        cb = id_end / TILE_M * TILE_M;
+        if (cb <= ca) ca = cb = id_begin;
+    }
     PointSource src;
     lattice_source(src, R0, R1, R2, calib_inv);
     const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
-    for (long long b = id_begin; b < id_end; b += chunk) {
-        const int m = static_cast<int>(id_end - b < chunk ? id_end - b : chunk);
-        src.id0 = b;
-        QueryOut o;
-        o.pred = out + (b - id_begin);
-        if (run_chunk(c, levels, src, m, calib, calib, o, s)) return -1;
+    const long long lo[2] = {id_begin, cb}, hi[2] = {ca, id_end};
+    for (int part = 0; part < 2; ++part) {
+        for (long long b = lo[part]; b < hi[part]; b += chunk) {
+            const int m = static_cast<int>(hi[part] - b < chunk ? hi[part] - b : chunk);
+            src.id0 = b;
+            QueryOut o;
+            o.pred = out + (b - id_begin);
+            if (run_chunk(c, levels, src, m, calib, calib, o, s)) return -1;
+        }
     }
+    if (cb > ca && run_chain(c, R0, R1, R2, ca, cb, calib, calib_inv, out + (ca - id_begin), s)) return -1;
     return 0;
 }
 

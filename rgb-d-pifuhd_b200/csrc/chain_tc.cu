@@ -1,0 +1,504 @@
+// Lattice chain kernel: the whole per-point MLP of one 128-point tile in ONE kernel, with
+// every activation kept on the SM (north_star (b): "weights fed by TMA, activations never
+// leaving the SM").
+//
+// Scope: dense lattice evaluation (`mesh_util.py:59-80`, eval_grid) of the two-level net
+// (`PIFuMRNet.py:119-186`) when the 128 points of a tile share one lattice column (i, j) and the
+// calibration does not mix z into x/y, i.e. the projected (x, y) - hence every bilinear
+// feature sample - is constant along the tile and only z varies.  Then
+//   * the feature part of every layer that concatenates the level input (`MLP.py:61-64`) is a
+//     per-column constant vector, computed once per column by the layer kernel (gemm_tc.cu)
+//     and handed over as `cc` (bias folded in);
+//   * coarse L0 degenerates to y0[n] = leaky(c0[n] + wz0[n] * z): no GEMM, the CUDA cores
+//     write it straight into the tensor core's shared-memory operand tiles;
+//   * what remains per point are the dense GEMMs L1 (1024->512), L2 (512->256, +c2 + wz2*z),
+//     fine L0 (256->512), L1 (512+256->256), L2 (256+256->128) and the Conv1d->1 head:
+//     1 048 576 MACs instead of 1 392 000.
+//
+// One CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256) works on two tiles; every weight
+// k-block is fetched once per pair (each CTA stages half of its rows).  Per CTA:
+//   warp 0      TMA producer: streams the 68 weight stages of a tile (2 MiB, consumption order)
+//               through a 5-deep ring of 16 KiB slots
+//   warp 1      MMA issuer (leader CTA) / "stage landed" forwarder (peer CTA)
+//   warp 2      TMEM allocator (512 columns = two 256-column fp32 accumulators Ha / Hb)
+//   warps 4-11  CUDA-core warps: generate y0 k-blocks, drain accumulators (TMEM -> bias ->
+//               leaky_relu -> fp16 -> swizzled operand k-block in smem), fused head
+// Job order per tile (accumulator, output width, A source), halves swapped every tile:
+//   J0 L1[:256]->Ha  J1 L1[256:]->Hb  J2 L2->Ha  J3 F0[:256]->Hb  J4 F0[256:]->Ha
+//   J5 F1->Hb  J6 F2->Ha[0:128]
+// Shared memory: P = 4 k-block slots (y0 ring during J0/J1, then phi, which stays resident for
+// J3-J6), D = 4 k-block slots (ring for y1 / fine activations), W = weight ring.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pifu {
+
+namespace {
+
+using namespace chain;
+
+constexpr int SLOT = ABLOCK_BYTES;
+constexpr int NP = 4, ND = 4, NW = 5;
+constexpr int G2_FLOATS = C2 + F0 + F1 + F2;
+constexpr int OFF_P = 0;
+constexpr int OFF_D = OFF_P + NP * SLOT;
+constexpr int OFF_W = OFF_D + ND * SLOT;
+constexpr int OFF_C0 = OFF_W + NW * SLOT;           // per-column c0 [C0] fp32 (TMA)
+constexpr int OFF_G2 = OFF_C0 + C0 * 4;             // per-column c2 | cF0 | cF1 | cF2 (TMA)
+constexpr int OFF_WZ0 = OFF_G2 + G2_FLOATS * 4;     // wz0 [C0]
+constexpr int OFF_WZ2 = OFF_WZ0 + C0 * 4;           // wz2 [C2]
+constexpr int OFF_B1 = OFF_WZ2 + C2 * 4;            // b1 [C1]
+constexpr int OFF_W3 = OFF_B1 + C1 * 4;             // w3 [F2]
+constexpr int OFF_Z = OFF_W3 + F2 * 4;              // z feature of the rows, [2][128]
+constexpr int OFF_PART = OFF_Z + 2 * TILE_M * 4;    // head partial sums [128]
+constexpr int OFF_BAR = OFF_PART + TILE_M * 4;
+constexpr int NBAR = 3 * NW + 2 * NP + 2 * ND + 4 + 2;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB of shared memory a CTA may use");
+static_assert(OFF_C0 % 16 == 0 && OFF_G2 % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+
+constexpr int NUM_THREADS = 384;
+constexpr int ALU_WARP0 = 4;
+constexpr int ALU_THREADS = 256;
+constexpr int ALU_WARPS = 8;
+
+__device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }
+__device__ __forceinline__ void alu_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// DepthNormalizer feature of lattice point `id` (`mesh_util.py:12-38,59-65,70`,
+// `BasePIFuNet.py:35-38`, `DepthNormalizer.py:23`), identical arithmetic to gather.cu
+__device__ __forceinline__ float lattice_z(const ChainArgs& a, long long id) {
+    const int k = static_cast<int>(id % a.R2);
+    const long long ij = id / a.R2;
+    const int j = static_cast<int>(ij % a.R1);
+    const int i = static_cast<int>(ij / a.R1);
+    const double c0 = __dadd_rn(__dmul_rn(a.step[0], static_cast<double>(i)), a.bmin[0]);
+    const double c1 = __dadd_rn(__dmul_rn(a.step[1], static_cast<double>(j)), a.bmin[1]);
+    const double c2 = __dadd_rn(__dmul_rn(a.step[2], static_cast<double>(k)), a.bmin[2]);
+    const double* m = a.cinv;
+    const float px = static_cast<float>(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c0, m[0]), __dmul_rn(c1, m[1])), __dmul_rn(c2, m[2])), m[3]));
+    const float py = static_cast<float>(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c0, m[4]), __dmul_rn(c1, m[5])), __dmul_rn(c2, m[6])), m[7]));
+    const float pz = static_cast<float>(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c0, m[8]), __dmul_rn(c1, m[9])), __dmul_rn(c2, m[10])), m[11]));
+    const float* c = a.cg;
+    const float zg = c[11] + fmaf(c[10], pz, fmaf(c[9], py, c[8] * px));
+    return __fdiv_rn(__fmul_rn(zg, a.z_mul), a.z_div);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = w_full + NW;
+    uint64_t* w_pfull = w_empty + NW;
+    uint64_t* p_full = w_pfull + NW;
+    uint64_t* p_empty = p_full + NP;
+    uint64_t* d_full = p_empty + NP;
+    uint64_t* d_empty = d_full + ND;
+    uint64_t* acc_full = d_empty + ND;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* g_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+    float* s_z = reinterpret_cast<float*>(smem + OFF_Z);
+    float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NW; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); ptx::mbar_init(&w_pfull[s], 1); }
+        for (int s = 0; s < NP; ++s) { ptx::mbar_init(&p_full[s], 2 * ALU_WARPS); ptx::mbar_init(&p_empty[s], 1); }
+        for (int s = 0; s < ND; ++s) { ptx::mbar_init(&d_full[s], 2 * ALU_WARPS); ptx::mbar_init(&d_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&acc_full[s], 1); ptx::mbar_init(&acc_empty[s], 2 * ALU_WARPS); }
+        ptx::mbar_init(&g_full[0], 1);
+        ptx::mbar_init(&g_full[1], 1);
+        ptx::fence_barrier_init();
+    } else if (warp == 2) {
+        ptx::tmem_alloc<2>(tmem_slot, 512);
+    }
+    if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+    {
+        float* d0 = reinterpret_cast<float*>(smem + OFF_WZ0);
+        float* d2 = reinterpret_cast<float*>(smem + OFF_WZ2);
+        float* db = reinterpret_cast<float*>(smem + OFF_B1);
+        float* d3 = reinterpret_cast<float*>(smem + OFF_W3);
+        for (int i = threadIdx.x; i < C0; i += NUM_THREADS) d0[i] = __ldg(a.wz0 + i);
+        for (int i = threadIdx.x; i < C2; i += NUM_THREADS) d2[i] = __ldg(a.wz2 + i);
+        for (int i = threadIdx.x; i < C1; i += NUM_THREADS) db[i] = __ldg(a.b1 + i);
+        for (int i = threadIdx.x; i < F2; i += NUM_THREADS) d3[i] = __ldg(a.w3 + i);
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_pairs = (a.n_tiles + 1) / 2;
+    const int first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+    const uint32_t sP = ptx::smem_u32(smem + OFF_P), sD = ptx::smem_u32(smem + OFF_D), sW = ptx::smem_u32(smem + OFF_W);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer: weight stream
+            int ws = 0;
+            uint32_t ph = 0;
+            for (int pt = first; pt < n_pairs; pt += stride) {
+                const uint8_t* src = a.wstream;
+                for (int s = 0; s < STAGES; ++s) {
+                    const uint32_t total = (s < STAGES_256 ? 256u : 128u) * ROW_BYTES;
+                    const uint32_t half = total >> 1;
+                    ptx::mbar_wait(&w_empty[ws], ph ^ 1u);
+                    ptx::mbar_arrive_expect_tx(&w_full[ws], half);
+                    ptx::bulk_g2s(smem + OFF_W + ws * SLOT, src + rank * half, half, &w_full[ws]);
+                    src += total;
+                    if (++ws == NW) { ws = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && !leader) {
+            // ------------------------------------------------ peer: forward "stage landed"
+            const uint32_t remote = ptx::map_to_cta(ptx::smem_u32(w_pfull), 0);
+            int ws = 0;
+            uint32_t ph = 0;
+            for (int pt = first; pt < n_pairs; pt += stride) {
+                for (int s = 0; s < STAGES; ++s) {
+                    ptx::mbar_wait(&w_full[ws], ph);
+                    ptx::mbar_arrive_cluster(remote + ws * 8);
+                    if (++ws == NW) { ws = 0; ph ^= 1u; }
+                }
+            }
+        } else if (lane == 0) {
+            // ------------------------------------------------ MMA issuer (leader of the pair)
+            constexpr uint32_t I256 = ptx::make_idesc_f16(256, 256);
+            constexpr uint32_t I128 = ptx::make_idesc_f16(256, 128);
+            int ws = 0;
+            uint32_t wph = 0;
+            uint32_t pf = 0, df = 0, ae = 3;          // parities to wait on (bit per barrier)
+            auto wait_bit = [&](uint64_t* bar, uint32_t& bits, int i) {
+                ptx::mbar_wait(&bar[i], (bits >> i) & 1u);
+                bits ^= (1u << i);
+            };
+            auto kblock = [&](uint32_t a_addr, uint32_t d_tmem, uint32_t idesc, bool accum) {
+                ptx::mbar_wait(&w_full[ws], wph);
+                ptx::mbar_wait(&w_pfull[ws], wph);
+                ptx::tc_fence_after();
+                const uint64_t ad = ptx::make_sw128_desc(a_addr);
+                const uint64_t bd = ptx::make_sw128_desc(sW + ws * SLOT);
+#pragma unroll
+                for (int k = 0; k < KB / 16; ++k)
+                    ptx::umma_f16_ss<2>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (accum || k > 0) ? 1u : 0u);
+                ptx::umma_commit<2>(&w_empty[ws]);
+                if (++ws == NW) { ws = 0; wph ^= 1u; }
+            };
+            int it = 0;
+            for (int pt = first; pt < n_pairs; pt += stride, ++it) {
+                const int Ha = it & 1, Hb = Ha ^ 1;
+                const uint32_t tHa = tmem_base + Ha * 256, tHb = tmem_base + Hb * 256;
+                // J0 / J1: coarse L1, output halves, A = y0 ring (generated twice)
+                for (int half = 0; half < 2; ++half) {
+                    const int H = half ? Hb : Ha;
+                    wait_bit(acc_empty, ae, H);
+                    for (int kb = 0; kb < C0 / KB; ++kb) {
+                        const int s = kb & 3;
+                        wait_bit(p_full, pf, s);
+                        kblock(sP + s * SLOT, half ? tHb : tHa, I256, kb > 0);
+                        ptx::umma_commit<2>(&p_empty[s]);
+                    }
+                    ptx::umma_commit<2>(&acc_full[H]);
+                }
+                // J2: coarse L2, A = y1 through the D ring
+                wait_bit(acc_empty, ae, Ha);
+                for (int kb = 0; kb < C1 / KB; ++kb) {
+                    const int s = kb & 3;
+                    wait_bit(d_full, df, s);
+                    kblock(sD + s * SLOT, tHa, I256, kb > 0);
+                    ptx::umma_commit<2>(&d_empty[s]);
+                }
+                ptx::umma_commit<2>(&acc_full[Ha]);
+                // J3 / J4: fine L0 output halves, A = phi (resident in P)
+                wait_bit(acc_empty, ae, Hb);
+                for (int s = 0; s < 4; ++s) {
+                    wait_bit(p_full, pf, s);
+                    kblock(sP + s * SLOT, tHb, I256, s > 0);
+                }
+                ptx::umma_commit<2>(&acc_full[Hb]);
+                wait_bit(acc_empty, ae, Ha);
+                for (int s = 0; s < 4; ++s) kblock(sP + s * SLOT, tHa, I256, s > 0);
+                ptx::umma_commit<2>(&acc_full[Ha]);
+                // J5: fine L1, A = phi then yF0 through the D ring
+                wait_bit(acc_empty, ae, Hb);
+                for (int s = 0; s < 4; ++s) kblock(sP + s * SLOT, tHb, I256, s > 0);
+                for (int kb = 0; kb < F0 / KB; ++kb) {
+                    const int s = kb & 3;
+                    wait_bit(d_full, df, s);
+                    kblock(sD + s * SLOT, tHb, I256, true);
+                    ptx::umma_commit<2>(&d_empty[s]);
+                }
+                ptx::umma_commit<2>(&acc_full[Hb]);
+                // J6: fine L2 (128 wide), A = phi (last use: release P) then yF1
+                wait_bit(acc_empty, ae, Ha);
+                for (int s = 0; s < 4; ++s) {
+                    kblock(sP + s * SLOT, tHa, I128, s > 0);
+                    ptx::umma_commit<2>(&p_empty[s]);
+                }
+                for (int s = 0; s < 4; ++s) {
+                    wait_bit(d_full, df, s);
+                    kblock(sD + s * SLOT, tHa, I128, true);
+                    ptx::umma_commit<2>(&d_empty[s]);
+                }
+                ptx::umma_commit<2>(&acc_full[Ha]);
+            }
+        }
+    } else if (warp >= ALU_WARP0) {
+        // ---------------------------------------------------- CUDA-core warps
+        const int w = warp - ALU_WARP0;              // 0..7
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int hh = w >> 2;                       // column half it drains
+        const int row = q * 32 + lane;               // drain: one TMEM lane = one point
+        const int atid = threadIdx.x - ALU_WARP0 * 32;
+        const int gchunk = lane & 7;                 // y0 generation: 8 channels x 4 rows per thread
+        const int grow0 = 16 * w + (lane >> 3);
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t pf_addr = ptx::map_to_cta(ptx::smem_u32(p_full), 0);
+        const uint32_t df_addr = ptx::map_to_cta(ptx::smem_u32(d_full), 0);
+        const uint32_t ae_addr = ptx::map_to_cta(ptx::smem_u32(acc_empty), 0);
+        const uint32_t c0_a = ptx::smem_u32(smem + OFF_C0), g2_a = ptx::smem_u32(smem + OFF_G2);
+        const uint32_t wz0_a = ptx::smem_u32(smem + OFF_WZ0), wz2_a = ptx::smem_u32(smem + OFF_WZ2);
+        const uint32_t b1_a = ptx::smem_u32(smem + OFF_B1), w3_a = ptx::smem_u32(smem + OFF_W3);
+        uint32_t pe = 0xFu, de = 0xFu, af = 0u, gph = 0u;
+        float zr[4] = {0.f, 0.f, 0.f, 0.f};
+
+        auto wait_bit = [&](uint64_t* bar, uint32_t& bits, int i) {
+            ptx::mbar_wait(&bar[i], (bits >> i) & 1u);
+            bits ^= (1u << i);
+        };
+        auto signal = [&](uint32_t cluster_bar) {       // slot written: publish to the MMA issuer
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(cluster_bar);
+        };
+        auto release_acc = [&](int H) {                 // accumulator half read completely
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ae_addr + H * 8);
+        };
+        auto tile_of = [&](int pt) {                    // tile this CTA owns in pair-tile pt (clamped)
+            int t = 2 * pt + static_cast<int>(rank);
+            return t < a.n_tiles ? t : a.n_tiles - 1;
+        };
+        auto col_of = [&](int t) { return ((a.tile0 + t) * TILE_M) / a.R2 - a.col0; };
+        auto load_g1 = [&](int t) {
+            ptx::mbar_arrive_expect_tx(&g_full[0], C0 * 4);
+            ptx::bulk_g2s(smem + OFF_C0, a.cc + col_of(t) * CC_FLOATS, C0 * 4, &g_full[0]);
+        };
+        auto load_g2 = [&](int t) {
+            ptx::mbar_arrive_expect_tx(&g_full[1], G2_FLOATS * 4);
+            ptx::bulk_g2s(smem + OFF_G2, a.cc + col_of(t) * CC_FLOATS + C0, G2_FLOATS * 4, &g_full[1]);
+        };
+        // y0 k-block kb = leaky(c0 + wz0 * z) for channels [64 kb, 64 kb + 64) -> P slot kb & 3
+        auto gen = [&](int kb) {
+            const int s = kb & 3;
+            wait_bit(p_empty, pe, s);
+            const uint32_t slot = sP + s * SLOT;
+            const uint32_t n0 = static_cast<uint32_t>(kb * KB + gchunk * 8) * 4u;
+            const float4 ca = lds128(c0_a + n0), cb = lds128(c0_a + n0 + 16);
+            const float4 wa = lds128(wz0_a + n0), wb = lds128(wz0_a + n0 + 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float z = zr[i];
+                uint4 pk;
+                pk.x = pack2(leaky(fmaf(wa.x, z, ca.x)), leaky(fmaf(wa.y, z, ca.y)));
+                pk.y = pack2(leaky(fmaf(wa.z, z, ca.z)), leaky(fmaf(wa.w, z, ca.w)));
+                pk.z = pack2(leaky(fmaf(wb.x, z, cb.x)), leaky(fmaf(wb.y, z, cb.y)));
+                pk.w = pack2(leaky(fmaf(wb.z, z, cb.z)), leaky(fmaf(wb.w, z, cb.w)));
+                sts128(slot + sw128_chunk_offset(grow0 + 4 * i, gchunk), pk);
+            }
+            signal(pf_addr + s * 8);
+        };
+        // accumulator half H, columns [64 j + 32 hh, +32) of this thread's row ->
+        // leaky(acc + bias (+ wz * z)) -> fp16 -> chunks 4 hh .. 4 hh + 3 of the row in `slot`
+        auto drain = [&](int H, int j, uint32_t slot, uint32_t bias_a, uint32_t wz_a, float z) {
+            const int c0 = 64 * j + 32 * hh;
+            uint32_t v[32];
+            ptx::tmem_ld32(tq + H * 256 + c0, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float x[8];
+                const float4 ba = lds128(bias_a + (c0 + 8 * g) * 4), bb = lds128(bias_a + (c0 + 8 * g + 4) * 4);
+                x[0] = __uint_as_float(v[8 * g + 0]) + ba.x; x[1] = __uint_as_float(v[8 * g + 1]) + ba.y;
+                x[2] = __uint_as_float(v[8 * g + 2]) + ba.z; x[3] = __uint_as_float(v[8 * g + 3]) + ba.w;
+                x[4] = __uint_as_float(v[8 * g + 4]) + bb.x; x[5] = __uint_as_float(v[8 * g + 5]) + bb.y;
+                x[6] = __uint_as_float(v[8 * g + 6]) + bb.z; x[7] = __uint_as_float(v[8 * g + 7]) + bb.w;
+                if (wz_a != 0u) {
+                    const float4 wa = lds128(wz_a + (c0 + 8 * g) * 4), wb = lds128(wz_a + (c0 + 8 * g + 4) * 4);
+                    x[0] = fmaf(wa.x, z, x[0]); x[1] = fmaf(wa.y, z, x[1]); x[2] = fmaf(wa.z, z, x[2]); x[3] = fmaf(wa.w, z, x[3]);
+                    x[4] = fmaf(wb.x, z, x[4]); x[5] = fmaf(wb.y, z, x[5]); x[6] = fmaf(wb.z, z, x[6]); x[7] = fmaf(wb.w, z, x[7]);
+                }
+                uint4 pk;
+                pk.x = pack2(leaky(x[0]), leaky(x[1])); pk.y = pack2(leaky(x[2]), leaky(x[3]));
+                pk.z = pack2(leaky(x[4]), leaky(x[5])); pk.w = pack2(leaky(x[6]), leaky(x[7]));
+                sts128(slot + sw128_chunk_offset(row, 4 * hh + g), pk);
+            }
+        };
+        // drain a 256-column half into the four D slots (y1 / yF0 / yF1 k-blocks)
+        auto drain_to_d = [&](int H, uint32_t bias_a) {
+            wait_bit(acc_full, af, H);
+            ptx::tc_fence_after();
+            for (int j = 0; j < 4; ++j) {
+                wait_bit(d_empty, de, j);
+                drain(H, j, sD + j * SLOT, bias_a, 0u, 0.f);
+                signal(df_addr + j * 8);
+            }
+            release_acc(H);
+        };
+
+        int it = 0;
+        if (first < n_pairs) {
+            const int t0 = tile_of(first);
+            if (atid == 0) { load_g1(t0); load_g2(t0); }
+            if (atid < TILE_M) s_z[atid] = lattice_z(a, (a.tile0 + t0) * TILE_M + atid);
+            alu_bar();
+            wait_bit(g_full, gph, 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zr[i] = s_z[grow0 + 4 * i];
+            for (int kb = 0; kb < 4; ++kb) gen(kb);
+        }
+        for (int pt = first; pt < n_pairs; pt += stride, ++it) {
+            const int Ha = it & 1, Hb = Ha ^ 1;
+            const bool has_next = pt + stride < n_pairs;
+            const int t = 2 * pt + static_cast<int>(rank);
+            const bool live = t < a.n_tiles;
+            const int tn = has_next ? tile_of(pt + stride) : 0;
+            float* zcur = s_z + (it & 1) * TILE_M;
+            float* znext = s_z + ((it + 1) & 1) * TILE_M;
+            if (has_next && atid < TILE_M) znext[atid] = lattice_z(a, (a.tile0 + tn) * TILE_M + atid);
+
+            // feed J0 (k-blocks 0..3 were generated ahead), then J1 with the drain of Ha -> y1[:256]
+            for (int kb = 4; kb < C0 / KB; ++kb) gen(kb);
+            for (int kb = 0; kb < C0 / KB; ++kb) {
+                gen(kb);
+                if ((kb & 3) == 3) {
+                    const int j = kb >> 2;
+                    if (j == 0) { wait_bit(acc_full, af, Ha); ptx::tc_fence_after(); }
+                    wait_bit(d_empty, de, j);
+                    drain(Ha, j, sD + j * SLOT, b1_a, 0u, 0.f);
+                    signal(df_addr + j * 8);
+                    if (j == 3) release_acc(Ha);
+                }
+            }
+            alu_bar();                                   // c0 / z of this tile no longer read
+            if (has_next && atid == 0) load_g1(tn);
+            // J1 done -> y1[256:]
+            drain_to_d(Hb, b1_a + 256 * 4);
+            // J2 done -> phi = leaky(acc + c2 + wz2 * z) into the P slots (resident until J6)
+            {
+                wait_bit(g_full, gph, 1);
+                wait_bit(acc_full, af, Ha);
+                ptx::tc_fence_after();
+                const float z = zcur[row];
+                for (int j = 0; j < 4; ++j) {
+                    wait_bit(p_empty, pe, j);
+                    drain(Ha, j, sP + j * SLOT, g2_a, wz2_a, z);
+                    signal(pf_addr + j * 8);
+                }
+                release_acc(Ha);
+            }
+            drain_to_d(Hb, g2_a + C2 * 4);                       // J3 -> yF0[:256]
+            drain_to_d(Ha, g2_a + (C2 + 256) * 4);               // J4 -> yF0[256:]
+            drain_to_d(Hb, g2_a + (C2 + F0) * 4);                // J5 -> yF1
+            if (has_next) {                                      // next tile's first y0 k-blocks
+                wait_bit(g_full, gph, 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) zr[i] = znext[grow0 + 4 * i];
+                for (int kb = 0; kb < 4; ++kb) gen(kb);
+            }
+            // J6 done -> fused Conv1d -> 1 + sigmoid + in-bounds mask (`MLP.py:72-73`, `PIFuMRNet.py:173-174`)
+            {
+                wait_bit(acc_full, af, Ha);
+                ptx::tc_fence_after();
+                uint32_t v[2][32];
+                ptx::tmem_ld32(tq + Ha * 256 + 64 * hh, v[0]);
+                ptx::tmem_ld32(tq + Ha * 256 + 64 * hh + 32, v[1]);
+                ptx::tmem_ld_wait();
+                release_acc(Ha);
+                const uint32_t cf2 = g2_a + (C2 + F0 + F1) * 4;
+                float hacc = 0.f;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int c = 64 * hh + 32 * u + 4 * g;
+                        const float4 b = lds128(cf2 + c * 4), wv = lds128(w3_a + c * 4);
+                        hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 0]) + b.x), wv.x, hacc);
+                        hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 1]) + b.y), wv.y, hacc);
+                        hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 2]) + b.z), wv.z, hacc);
+                        hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 3]) + b.w), wv.w, hacc);
+                    }
+                }
+                if (hh == 1) s_part[row] = hacc;
+                alu_bar();
+                if (hh == 0 && live) {
+                    const float logit = hacc + s_part[row] + a.b3;
+                    const float p = 1.f / (1.f + expf(-logit));
+                    const bool inb = (__ldg(a.colmask + col_of(t)) >> 1) & 1;
+                    a.out[static_cast<size_t>(t) * TILE_M + row] = inb ? p : 0.f;
+                }
+            }
+            alu_bar();                                   // G2 constants / s_part of this tile consumed
+            if (has_next && atid == 0) load_g2(tn);
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();                                 // no CTA leaves while its peer can still signal it
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<2>(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s) {
+    if (a.n_tiles <= 0) return 0;
+    if (a.R2 % TILE_M != 0) { set_error("chain: lattice depth %d is not a multiple of 128", a.R2); return -1; }
+    static bool configured[32] = {};
+    int dev = 0;
+    PIFU_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 31]) {
+        PIFU_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured[dev & 31] = true;
+    }
+    const int pairs = (a.n_tiles + 1) / 2;
+    const int max_pairs = num_sms / 2;
+    const int grid = (pairs < max_pairs ? pairs : max_pairs) * 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PIFU_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, a));
+    return 0;
+}
+
+}  // namespace pifu

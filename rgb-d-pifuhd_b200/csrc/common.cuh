@@ -57,6 +57,12 @@ struct GemmArgs {
     const uint8_t* mask;    // per point, bit `mask_bit` = in-bounds; null = no masking
     int mask_bit;
     int n_valid;            // points in this chunk (rows >= n_valid are padding)
+    // optional fp32 row-major copy of the epilogue result (bias/activation applied, before the
+    // fp16 rounding): out_f32[(mt*128 + row) * f32_ld + f32_col0 + n]; used for the per-column
+    // constants of the lattice chain kernel
+    float* out_f32;
+    long long f32_ld;
+    int f32_col0;
 };
 
 // ------------------------------------------------------------------ errors
@@ -84,6 +90,7 @@ struct PointSource {
     // then [c,1] . cinv^T, then the float32 cast of `mesh_util.py:70`.
     const long long* ids;
     long long id0;
+    long long id_stride;    // ids == null: id = id0 + p * id_stride (0 is read as 1)
     int R0, R1, R2;
     double step[3], bmin[3];
     double cinv[12];        // rows 0..2 of inv(calib) (4 columns each)
@@ -108,5 +115,40 @@ struct GatherArgs {
     uint8_t* mask;          // [m_tiles*128] bit0 coarse in-bounds (x,y,z), bit1 fine in-bounds (x,y)
 };
 int launch_gather(const GatherArgs& a, cudaStream_t s);
+
+// ------------------------------------------------------------------ lattice chain kernel
+// (chain_tc.cu) One launch evaluates whole 128-point tiles of lattice columns through
+// coarse L1-L2 and the fine MLP with every activation kept in shared/tensor memory.
+namespace chain {
+constexpr int C0 = 1024, C1 = 512, C2 = 256;           // coarse hidden widths (L0, L1, L2 = phi)
+constexpr int F0 = 512, F1 = 256, F2 = 128;            // fine hidden widths
+constexpr int CC_FLOATS = C0 + C2 + F0 + F1 + F2;      // per-column constants, fp32
+constexpr int CC_OFF_C2 = C0, CC_OFF_F0 = C0 + C2, CC_OFF_F1 = C0 + C2 + F0, CC_OFF_F2 = C0 + C2 + F0 + F1;
+constexpr int STAGES_256 = 16 + 16 + 8 + 4 + 4 + 12;   // weight k-block stages with 256 output rows
+constexpr int STAGES_128 = 8;                          // ... with 128 output rows (fine L2)
+constexpr int STAGES = STAGES_256 + STAGES_128;
+constexpr size_t WSTREAM_BYTES = static_cast<size_t>(STAGES_256) * 256 * ROW_BYTES +
+                                 static_cast<size_t>(STAGES_128) * 128 * ROW_BYTES;
+}  // namespace chain
+
+struct ChainArgs {
+    const uint8_t* wstream;   // chain::STAGES packed weight stages in consumption order
+    const float* cc;          // [ncols][chain::CC_FLOATS] per-column constants (bias folded in)
+    const uint8_t* colmask;   // [ncols] gather mask of the column (bit1 = fine in-bounds)
+    const float* wz0;         // [C0] z column of coarse L0 (fp32)
+    const float* wz2;         // [C2] z column of coarse L2 (fp32)
+    const float* b1;          // [C1] bias of coarse L1
+    const float* w3;          // [F2] fine last layer (Conv1d -> 1)
+    float b3;
+    long long tile0;          // global index (lattice id / 128) of the first tile
+    int n_tiles;
+    long long col0;           // lattice column (id / R2) that cc row 0 / colmask[0] describe
+    int R0, R1, R2;
+    double step[3], bmin[3], cinv[12];
+    float cg[12];
+    float z_mul, z_div;
+    float* out;               // out[t * 128 + row], t relative to tile0
+};
+int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s);
 
 }  // namespace pifu

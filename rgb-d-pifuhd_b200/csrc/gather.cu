@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
             py = __ldg(S.pts + S.pstride + p);
             pz = __ldg(S.pts + 2 * S.pstride + p);
         } else {
-            const long long id = S.ids ? __ldg(S.ids + p) : S.id0 + p;
+            const long long id = S.ids ? __ldg(S.ids + p) : S.id0 + p * (S.id_stride > 0 ? S.id_stride : 1);
             const int k = static_cast<int>(id % S.R2);
             const long long ij = id / S.R2;
             const int j = static_cast<int>(ij % S.R1);

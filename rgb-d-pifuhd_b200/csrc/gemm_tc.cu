@@ -234,6 +234,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = leaky(x[j]);
                     }
+                    if (a.out_f32 != nullptr && live && mt * TILE_M + row < a.n_valid) {
+                        float* dst = a.out_f32 + static_cast<size_t>(mt * TILE_M + row) * a.f32_ld + a.f32_col0 + nt * BN + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    }
                     if (a.head_w != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {

@@ -127,6 +127,19 @@ class Engine:
         _lib.check(self.lib.pifu_profile_read(self.h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
         return n.value, ms.value, fl.value
 
+    def profile_read_kind(self, kind):
+        """-> (launches, total_ms, total_flops) of one kernel kind (0 layer kernel, 1 chain kernel)."""
+        n, ms, fl = ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
+        _lib.check(self.lib.pifu_profile_read_kind(self.h, int(kind), ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
+        return n.value, ms.value, fl.value
+
+    def set_chain(self, enabled):
+        """Enable / disable the lattice chain kernel (eval_grid falls back to the per-layer kernels)."""
+        _lib.check(self.lib.pifu_set_chain(self.h, int(bool(enabled))))
+
+    def chain_ready(self):
+        return bool(self.lib.pifu_chain_ready(self.h))
+
     def launch_count(self):
         return int(self.lib.pifu_launch_count(self.h))
 

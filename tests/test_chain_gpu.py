@@ -1,0 +1,105 @@
+"""GPU parity of the lattice chain kernel (whole MLP stack of a lattice-column tile in one
+kernel) against the CPU oracle and against the per-layer kernels, through the C ABI
+(`pifu_eval_grid`).  Tolerances are north_star's: occupancy within 1e-3 absolute, >= 99.99 %
+sign agreement at the 0.5 iso-level."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import calibrated_problem, oracle_states, orc, syn
+from test_query_gpu import OCC_TOL, build_nets, sign_agreement
+
+pytestmark = pytest.mark.gpu
+
+
+def lattice_points(R, calib, ids):
+    """float64 lattice + calib pre-transform + float32 cast (`mesh_util.py:12-38,59-65,70`)."""
+    R0, R1, R2 = R
+    k, j, i = ids % R2, (ids // R2) % R1, ids // (R1 * R2)
+    c = np.stack([(2.0 / R0) * i + (-1.0), (2.0 / R1) * j + (-1.0), (2.0 / R2) * k + (-1.0),
+                  np.ones(len(ids))], 1)
+    inv = np.linalg.inv(calib[0].numpy()).astype(np.float64)
+    p = (c @ inv.T)[:, :3].T
+    return torch.from_numpy(np.ascontiguousarray(p.astype(np.float32)))[None]
+
+
+@pytest.fixture(scope="module")
+def setup():
+    torch.set_grad_enabled(False)
+    prob, _ = calibrated_problem()
+    _, fine = oracle_states(prob)
+    netG, netMR = build_nets(prob)
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    pts = syn.random_points(256)
+    netMR.query(pts.cuda(), syn.default_calib().cuda())        # snapshots both MLPs
+    assert eng.chain_ready()
+    return prob, fine, netMR, eng
+
+
+CASES = [
+    # lattice, id range, calib            what it exercises
+    ((2, 1, 128), None, "default"),     # one CTA pair, one tile each
+    ((3, 1, 128), None, "default"),     # odd tile count: the peer CTA of the last pair idles
+    ((4, 8, 256), None, "default"),     # two tiles per column
+    ((6, 5, 256), (100, 7000), "default"),   # ragged ends go through the per-layer kernels
+    ((4, 8, 128), None, "scaled"),      # scale + shift calibration (some columns out of bounds)
+    ((24, 32, 128), None, "default"),   # 768 tiles: several tiles per CTA, accumulator halves swap
+]
+
+
+@pytest.mark.parametrize("R,rng,calib_name", CASES, ids=["2x1x128", "3x1x128", "4x8x256", "6x5x256-ragged", "4x8x128-scaled", "24x32x128"])
+def test_chain_vs_oracle(setup, R, rng, calib_name):
+    prob, fine, netMR, eng = setup
+    calib = syn.default_calib() if calib_name == "default" else syn.scaled_calib()
+    total = R[0] * R[1] * R[2]
+    a, b = rng if rng else (0, total)
+    ids = np.arange(a, b)
+    ref = orc.query_fine(fine, lattice_points(R, calib, ids), calib)[0].numpy().ravel()
+    eng.set_chain(True)
+    l0 = eng.launch_count()
+    out = eng.eval_grid(2, R, calib[0], id_begin=a, id_end=b).cpu().numpy()
+    assert eng.launch_count() - l0 <= 4 + 14, "chain path not taken"
+    assert np.abs(out - ref).max() < OCC_TOL
+    assert np.array_equal(out == 0, ref == 0)              # identical in-bounds masks
+    if len(ids) >= 50000:
+        assert sign_agreement(out, ref) >= 0.9999
+    eng.set_chain(False)
+    try:
+        layer = eng.eval_grid(2, R, calib[0], id_begin=a, id_end=b).cpu().numpy()
+    finally:
+        eng.set_chain(True)
+    assert np.abs(out - layer).max() < OCC_TOL
+
+
+def test_chain_not_taken_when_z_mixes_into_xy(setup):
+    """A calibration that rotates z into x makes the samples vary along the column: the dense
+    path must fall back to the per-layer kernels and still match the oracle."""
+    prob, fine, netMR, eng = setup
+    c = syn.default_calib().clone()
+    c[0, 0, 0], c[0, 0, 2], c[0, 2, 0], c[0, 2, 2] = 0.8, 0.6, -0.6, 0.8
+    R = (4, 4, 128)
+    ids = np.arange(R[0] * R[1] * R[2])
+    ref = orc.query_fine(fine, lattice_points(R, c, ids), c)[0].numpy().ravel()
+    out = eng.eval_grid(2, R, c[0]).cpu().numpy()
+    assert np.abs(out - ref).max() < OCC_TOL
+
+
+def test_chain_saturated_field():
+    """Octree / marching-cubes field (last layer x8), 128^2 columns x 128: sign agreement."""
+    torch.set_grad_enabled(False)
+    prob, _ = calibrated_problem(saturated=True)
+    _, fine = oracle_states(prob)
+    netG, netMR = build_nets(prob)
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    calib = syn.default_calib()
+    netMR.query(syn.random_points(256).cuda(), calib.cuda())
+    R = (40, 40, 128)
+    ids = np.arange(R[0] * R[1] * R[2])
+    ref = orc.query_fine(fine, lattice_points(R, calib, ids), calib)[0].numpy().ravel()
+    out = eng.eval_grid(2, R, calib[0]).cpu().numpy()
+    assert np.abs(out - ref).max() < 8e-3
+    assert sign_agreement(out, ref) >= 0.9999
