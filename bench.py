@@ -12,6 +12,7 @@ the slabs are gathered to rank 0 with NCCL inside the timed step (weak scaling).
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -46,19 +47,21 @@ def build_problem():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms from before the warm-up; only the
+    samples whose nvidia-smi timestamp falls inside the timed region are reported."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -69,30 +72,42 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        self.t.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 and self.t1 and not (self.t0 <= ts <= self.t1):
+                    continue
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
+            for n, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_port_queries_per_s(prob, calib, n_points, steps=1, warmup=0):
@@ -145,7 +160,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -202,21 +217,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(warmup):
+        step()
+    barrier()
     l0 = eng.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
+    sampler.mark_begin()
     ev[0].record()
     for _ in range(args.steps):
         flush.fill_(0.0)                    # L2 flush between timed iterations (256 MiB write)
         step()
     ev[1].record()
     barrier()
+    sampler.mark_end()
     ms = ev[0].elapsed_time(ev[1])
     launches = eng.launch_count() - l0 + args.steps     # + the flush fills
     clocks = sampler.stop() if rank == 0 else None
@@ -260,15 +277,33 @@ def main():
         peaks = load_peaks()
         eng.profile(True)
         eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
-        n_l, gemm_ms, gemm_flops = eng.profile_read()
+        n_c, chain_ms, chain_flops = eng.profile_read_kind(1)
+        n_l, gemm_ms, gemm_flops = eng.profile_read_kind(0)
         eng.profile(False)
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 MLP layer)", "achieved": achieved,
-                    "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                    "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_l,
-                    "avg_launch_us": gemm_ms * 1e3 / max(n_l, 1), "share_of_step": gemm_ms / ms_per_step,
-                    "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
-                    "note": "coarse L3/L4 (preds_low) are not on the get_preds() path and are skipped"}
+        if n_c > 0:
+            # dominant kernel = the lattice chain kernel (one launch per column chunk); the per-layer
+            # kernel only computes the per-column constants
+            achieved = chain_flops / (chain_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "chain_kernel (tcgen05 CTA-pair MLP chain, activations on-chip)",
+                        "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                        "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_c,
+                        "avg_launch_us": chain_ms * 1e3 / n_c, "share_of_step": chain_ms / ms_per_step,
+                        "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
+                        "executed_flop_per_query": 2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128),
+                        "executed_tflops": achieved * (2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128)) /
+                                           (config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385)),
+                        "column_constants": {"kernel": "gemm_tc_kernel", "launches_per_step": n_l, "ms_per_step": gemm_ms},
+                        "note": "algorithmic = the reference's get_preds() layer stack per query (coarse L0-L2, fine L0-L3; "
+                                "coarse L3/L4 only feed preds_low); executed = what the tensor cores run after the "
+                                "per-column constant folding (SURVEY 7.3-4)"}
+        else:
+            achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+            roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 MLP layer)", "achieved": achieved,
+                        "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                        "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_l,
+                        "avg_launch_us": gemm_ms * 1e3 / max(n_l, 1), "share_of_step": gemm_ms / ms_per_step,
+                        "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
+                        "note": "coarse L3/L4 (preds_low) are not on the get_preds() path and are skipped"}
         if not args.no_cpu_baseline:
             qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, 400000)
             cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -282,7 +317,8 @@ def main():
             "config": {"workload": "PIFuMRNet multi-level (coarse 257-1024-512-256 trunk + fine 272-512-256-128-1), dense "
                                    "%dx%dx%d lattice, %d^3 = %d queries per GPU (BASELINE configs[1])" % (R0, res, res, res, per_rank),
                        "parallelism": "slab%d" % world, "mlp_norm": "none",
-                       "l2": "256 MiB flush write between timed iterations; per-step activation traffic (~6 KB/query) >> 126 MB L2"},
+                       "l2": "256 MiB flush write between timed iterations",
+                       "path": "chain" if eng.chain_ready() else "per-layer"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }))

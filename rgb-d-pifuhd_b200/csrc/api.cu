@@ -296,16 +296,16 @@ size_t chain_stage_offset(int s) {
 // pack `nst` consecutive weight stages: stage i = rows [row0, row0 + N) of W, source columns
 // col0 + 64 i .. + 63, as two N/2-row halves (one per CTA of a pair)
 int chain_pack_stages(ChainPlan& P, int first_stage, int nst, const float* W, int cin, int row0, int col0,
-                      int N, cudaStream_t s) {
+                      int N, cudaStream_t s, int stage_stride = 1) {
     std::vector<int> m(static_cast<size_t>(nst) * KB);
     for (int i = 0; i < nst; ++i)
         for (int k = 0; k < KB; ++k) m[static_cast<size_t>(i) * KB + k] = col0 + i * KB + k;
-    int* dm = P.colmaps + static_cast<size_t>(first_stage) * KB;
+    int* dm = P.colmaps + static_cast<size_t>(chain::STAGES + 8) * KB;      // scratch behind the column maps
     PIFU_CUDA(cudaMemcpyAsync(dm, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    PIFU_CUDA(cudaStreamSynchronize(s));            // m is a stack-lifetime host buffer
     for (int i = 0; i < nst; ++i)
         if (launch_pack_weights(W + static_cast<size_t>(row0) * cin, cin, dm + i * KB, 1, N, N / 2,
-                                P.wstream + chain_stage_offset(first_stage + i), s)) return -1;
+                                P.wstream + chain_stage_offset(first_stage + i * stage_stride), s)) return -1;
+    PIFU_CUDA(cudaStreamSynchronize(s));            // m is a stack-lifetime host buffer, dm is reused
     return 0;
 }
 
@@ -331,16 +331,16 @@ int build_chain_coarse(pifu_ctx* c, const float* const* weights, const float* co
     if (!(L.n_layers >= 4 && L.dims[0] == 257 && L.dims[1] == C0 && L.dims[2] == C1 && L.dims[3] == C2 &&
           !L.is_res(1) && L.is_res(2) && L.merge == 2 && c->bufs[c->buf_F].nkb == 5)) return 0;
     PIFU_CUDA(cudaMalloc(&P.wstream, WSTREAM_BYTES));
-    PIFU_CUDA(cudaMalloc(&P.colmaps, (static_cast<size_t>(STAGES) + 8) * KB * sizeof(int)));
+    PIFU_CUDA(cudaMalloc(&P.colmaps, (static_cast<size_t>(STAGES) + 8 + 16) * KB * sizeof(int)));
     PIFU_CUDA(cudaMalloc(&P.w_colA, static_cast<size_t>(C0 + C2) * 5 * ROW_BYTES));
     PIFU_CUDA(cudaMalloc(&P.bias_colA, (C0 + C2) * sizeof(float)));
     PIFU_CUDA(cudaMalloc(&P.wz0, C0 * sizeof(float)));
     PIFU_CUDA(cudaMalloc(&P.wz2, C2 * sizeof(float)));
     PIFU_CUDA(cudaMalloc(&P.b1, C1 * sizeof(float)));
     const int cin2 = C1 + 257;
-    // J0 / J1: coarse L1 output halves; J2: the y part of coarse L2 (cat[y, input], MLP.py:61-64)
-    if (chain_pack_stages(P, 0, 16, weights[1], C0, 0, 0, 256, s)) return -1;
-    if (chain_pack_stages(P, 16, 16, weights[1], C0, 256, 0, 256, s)) return -1;
+    // J01: coarse L1, per k-block the two output halves; J2: the y part of coarse L2 (cat[y, input], MLP.py:61-64)
+    if (chain_pack_stages(P, 0, 16, weights[1], C0, 0, 0, 256, s, 2)) return -1;
+    if (chain_pack_stages(P, 1, 16, weights[1], C0, 256, 0, 256, s, 2)) return -1;
     if (chain_pack_stages(P, 32, 8, weights[2], cin2, 0, 0, 256, s)) return -1;
     // per-column constants: coarse L0 feature columns [0, 256), coarse L2 feature columns [512, 768)
     if (chain_pack_colw(P, weights[0], 257, 0, 256, 5, C0, 256, P.w_colA, s)) return -1;

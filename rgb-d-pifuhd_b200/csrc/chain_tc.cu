@@ -23,9 +23,9 @@
 //   warp 2      TMEM allocator (512 columns = two 256-column fp32 accumulators Ha / Hb)
 //   warps 4-11  CUDA-core warps: generate y0 k-blocks, drain accumulators (TMEM -> bias ->
 //               leaky_relu -> fp16 -> swizzled operand k-block in smem), fused head
-// Job order per tile (accumulator, output width, A source), halves swapped every tile:
-//   J0 L1[:256]->Ha  J1 L1[256:]->Hb  J2 L2->Ha  J3 F0[:256]->Hb  J4 F0[256:]->Ha
-//   J5 F1->Hb  J6 F2->Ha[0:128]
+// Job order per tile (accumulator half, A source):
+//   J01 L1 -> Ha|Hb (two N=256 MMAs per k-step, y0 generated once)   J2 L2 -> Ha
+//   J3 F0[:256] -> Hb   J4 F0[256:] -> Ha   J5 F1 -> Hb   J6 F2 -> Ha[0:128]
 // Shared memory: P = 4 k-block slots (y0 ring during J0/J1, then phi, which stays resident for
 // J3-J6), D = 4 k-block slots (ring for y1 / fine activations), W = weight ring.
 #include "common.cuh"
@@ -73,9 +73,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+// two fp32 values -> fp16x2 -> leaky_relu(0.01) as max(h, 0.01 h) on the packed pair
+// (F2FP + HMUL2 + HMNMX2 for two elements; the slope is fp16(0.01), relative 2e-4 off on
+// the already 100x attenuated negative branch)
+__device__ __forceinline__ uint32_t pack2_leaky(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const __half2 r = __hmax2(h, __hmul2(h, __floats2half2_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
 }
 
 // DepthNormalizer feature of lattice point `id` (`mesh_util.py:12-38,59-65,70`,
@@ -203,43 +207,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 ptx::umma_commit<2>(&w_empty[ws]);
                 if (++ws == NW) { ws = 0; wph ^= 1u; }
             };
-            int it = 0;
-            for (int pt = first; pt < n_pairs; pt += stride, ++it) {
-                const int Ha = it & 1, Hb = Ha ^ 1;
-                const uint32_t tHa = tmem_base + Ha * 256, tHb = tmem_base + Hb * 256;
-                // J0 / J1: coarse L1, output halves, A = y0 ring (generated twice)
-                for (int half = 0; half < 2; ++half) {
-                    const int H = half ? Hb : Ha;
-                    wait_bit(acc_empty, ae, H);
-                    for (int kb = 0; kb < C0 / KB; ++kb) {
-                        const int s = kb & 3;
-                        wait_bit(p_full, pf, s);
-                        kblock(sP + s * SLOT, half ? tHb : tHa, I256, kb > 0);
-                        ptx::umma_commit<2>(&p_empty[s]);
-                    }
-                    ptx::umma_commit<2>(&acc_full[H]);
+            const uint32_t tHa = tmem_base, tHb = tmem_base + 256;
+            for (int pt = first; pt < n_pairs; pt += stride) {
+                // J01: coarse L1, both output halves per y0 k-block (y0 is generated once)
+                wait_bit(acc_empty, ae, 0);
+                wait_bit(acc_empty, ae, 1);
+                for (int kb = 0; kb < C0 / KB; ++kb) {
+                    const int s = kb & 3;
+                    wait_bit(p_full, pf, s);
+                    kblock(sP + s * SLOT, tHa, I256, kb > 0);
+                    kblock(sP + s * SLOT, tHb, I256, kb > 0);
+                    ptx::umma_commit<2>(&p_empty[s]);
                 }
+                ptx::umma_commit<2>(&acc_full[0]);
+                ptx::umma_commit<2>(&acc_full[1]);
                 // J2: coarse L2, A = y1 through the D ring
-                wait_bit(acc_empty, ae, Ha);
+                wait_bit(acc_empty, ae, 0);
                 for (int kb = 0; kb < C1 / KB; ++kb) {
                     const int s = kb & 3;
                     wait_bit(d_full, df, s);
                     kblock(sD + s * SLOT, tHa, I256, kb > 0);
                     ptx::umma_commit<2>(&d_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[Ha]);
+                ptx::umma_commit<2>(&acc_full[0]);
                 // J3 / J4: fine L0 output halves, A = phi (resident in P)
-                wait_bit(acc_empty, ae, Hb);
+                wait_bit(acc_empty, ae, 1);
                 for (int s = 0; s < 4; ++s) {
                     wait_bit(p_full, pf, s);
                     kblock(sP + s * SLOT, tHb, I256, s > 0);
                 }
-                ptx::umma_commit<2>(&acc_full[Hb]);
-                wait_bit(acc_empty, ae, Ha);
+                ptx::umma_commit<2>(&acc_full[1]);
+                wait_bit(acc_empty, ae, 0);
                 for (int s = 0; s < 4; ++s) kblock(sP + s * SLOT, tHa, I256, s > 0);
-                ptx::umma_commit<2>(&acc_full[Ha]);
+                ptx::umma_commit<2>(&acc_full[0]);
                 // J5: fine L1, A = phi then yF0 through the D ring
-                wait_bit(acc_empty, ae, Hb);
+                wait_bit(acc_empty, ae, 1);
                 for (int s = 0; s < 4; ++s) kblock(sP + s * SLOT, tHb, I256, s > 0);
                 for (int kb = 0; kb < F0 / KB; ++kb) {
                     const int s = kb & 3;
@@ -247,9 +249,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                     kblock(sD + s * SLOT, tHb, I256, true);
                     ptx::umma_commit<2>(&d_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[Hb]);
+                ptx::umma_commit<2>(&acc_full[1]);
                 // J6: fine L2 (128 wide), A = phi (last use: release P) then yF1
-                wait_bit(acc_empty, ae, Ha);
+                wait_bit(acc_empty, ae, 0);
                 for (int s = 0; s < 4; ++s) {
                     kblock(sP + s * SLOT, tHa, I128, s > 0);
                     ptx::umma_commit<2>(&p_empty[s]);
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                     kblock(sD + s * SLOT, tHa, I128, true);
                     ptx::umma_commit<2>(&d_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[Ha]);
+                ptx::umma_commit<2>(&acc_full[0]);
             }
         }
     } else if (warp >= ALU_WARP0) {
@@ -311,30 +313,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         // y0 k-block kb = leaky(c0 + wz0 * z) for channels [64 kb, 64 kb + 64) -> P slot kb & 3
         auto gen = [&](int kb) {
             const int s = kb & 3;
-            wait_bit(p_empty, pe, s);
             const uint32_t slot = sP + s * SLOT;
             const uint32_t n0 = static_cast<uint32_t>(kb * KB + gchunk * 8) * 4u;
             const float4 ca = lds128(c0_a + n0), cb = lds128(c0_a + n0 + 16);
             const float4 wa = lds128(wz0_a + n0), wb = lds128(wz0_a + n0 + 16);
+            wait_bit(p_empty, pe, s);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float z = zr[i];
                 uint4 pk;
-                pk.x = pack2(leaky(fmaf(wa.x, z, ca.x)), leaky(fmaf(wa.y, z, ca.y)));
-                pk.y = pack2(leaky(fmaf(wa.z, z, ca.z)), leaky(fmaf(wa.w, z, ca.w)));
-                pk.z = pack2(leaky(fmaf(wb.x, z, cb.x)), leaky(fmaf(wb.y, z, cb.y)));
-                pk.w = pack2(leaky(fmaf(wb.z, z, cb.z)), leaky(fmaf(wb.w, z, cb.w)));
+                pk.x = pack2_leaky(fmaf(wa.x, z, ca.x), fmaf(wa.y, z, ca.y));
+                pk.y = pack2_leaky(fmaf(wa.z, z, ca.z), fmaf(wa.w, z, ca.w));
+                pk.z = pack2_leaky(fmaf(wb.x, z, cb.x), fmaf(wb.y, z, cb.y));
+                pk.w = pack2_leaky(fmaf(wb.z, z, cb.z), fmaf(wb.w, z, cb.w));
                 sts128(slot + sw128_chunk_offset(grow0 + 4 * i, gchunk), pk);
             }
             signal(pf_addr + s * 8);
         };
-        // accumulator half H, columns [64 j + 32 hh, +32) of this thread's row ->
+        // 32 accumulator columns of this thread's row (already in registers) ->
         // leaky(acc + bias (+ wz * z)) -> fp16 -> chunks 4 hh .. 4 hh + 3 of the row in `slot`
-        auto drain = [&](int H, int j, uint32_t slot, uint32_t bias_a, uint32_t wz_a, float z) {
-            const int c0 = 64 * j + 32 * hh;
-            uint32_t v[32];
-            ptx::tmem_ld32(tq + H * 256 + c0, v);
-            ptx::tmem_ld_wait();
+        auto emit = [&](const uint32_t (&v)[32], int c0, uint32_t slot, uint32_t bias_a, uint32_t wz_a, float z) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float x[8];
@@ -349,24 +347,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                     x[4] = fmaf(wb.x, z, x[4]); x[5] = fmaf(wb.y, z, x[5]); x[6] = fmaf(wb.z, z, x[6]); x[7] = fmaf(wb.w, z, x[7]);
                 }
                 uint4 pk;
-                pk.x = pack2(leaky(x[0]), leaky(x[1])); pk.y = pack2(leaky(x[2]), leaky(x[3]));
-                pk.z = pack2(leaky(x[4]), leaky(x[5])); pk.w = pack2(leaky(x[6]), leaky(x[7]));
+                pk.x = pack2_leaky(x[0], x[1]); pk.y = pack2_leaky(x[2], x[3]);
+                pk.z = pack2_leaky(x[4], x[5]); pk.w = pack2_leaky(x[6], x[7]);
                 sts128(slot + sw128_chunk_offset(row, 4 * hh + g), pk);
             }
         };
-        // drain a 256-column half into the four D slots (y1 / yF0 / yF1 k-blocks)
-        auto drain_to_d = [&](int H, uint32_t bias_a) {
+        // drain the 256-column accumulator half H into four k-block slots (D ring, or P for phi);
+        // the TMEM load of k-block j + 1 is in flight while k-block j is converted
+        auto drain_half = [&](int H, uint32_t slot0, uint64_t* empty_bar, uint32_t& empty_bits, uint32_t full_addr,
+                              uint32_t bias_a, uint32_t wz_a, float z) {
             wait_bit(acc_full, af, H);
             ptx::tc_fence_after();
+            uint32_t v[2][32];
+            const uint32_t t0 = tq + H * 256 + 32 * hh;
+            ptx::tmem_ld32(t0, v[0]);
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
-                wait_bit(d_empty, de, j);
-                drain(H, j, sD + j * SLOT, bias_a, 0u, 0.f);
-                signal(df_addr + j * 8);
+                ptx::tmem_ld_wait();
+                if (j < 3) ptx::tmem_ld32(t0 + 64 * (j + 1), v[(j + 1) & 1]);
+                else release_acc(H);                     // every column of the half is in registers
+                wait_bit(empty_bar, empty_bits, j);
+                emit(v[j & 1], 64 * j + 32 * hh, slot0 + j * SLOT, bias_a, wz_a, z);
+                signal(full_addr + j * 8);
             }
-            release_acc(H);
         };
 
-        int it = 0;
         if (first < n_pairs) {
             const int t0 = tile_of(first);
             if (atid == 0) { load_g1(t0); load_g2(t0); }
@@ -377,8 +382,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             for (int i = 0; i < 4; ++i) zr[i] = s_z[grow0 + 4 * i];
             for (int kb = 0; kb < 4; ++kb) gen(kb);
         }
+        int it = 0;
         for (int pt = first; pt < n_pairs; pt += stride, ++it) {
-            const int Ha = it & 1, Hb = Ha ^ 1;
             const bool has_next = pt + stride < n_pairs;
             const int t = 2 * pt + static_cast<int>(rank);
             const bool live = t < a.n_tiles;
@@ -387,39 +392,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             float* znext = s_z + ((it + 1) & 1) * TILE_M;
             if (has_next && atid < TILE_M) znext[atid] = lattice_z(a, (a.tile0 + tn) * TILE_M + atid);
 
-            // feed J0 (k-blocks 0..3 were generated ahead), then J1 with the drain of Ha -> y1[:256]
+            // feed J01 (k-blocks 0..3 were generated ahead)
             for (int kb = 4; kb < C0 / KB; ++kb) gen(kb);
-            for (int kb = 0; kb < C0 / KB; ++kb) {
-                gen(kb);
-                if ((kb & 3) == 3) {
-                    const int j = kb >> 2;
-                    if (j == 0) { wait_bit(acc_full, af, Ha); ptx::tc_fence_after(); }
-                    wait_bit(d_empty, de, j);
-                    drain(Ha, j, sD + j * SLOT, b1_a, 0u, 0.f);
-                    signal(df_addr + j * 8);
-                    if (j == 3) release_acc(Ha);
-                }
-            }
-            alu_bar();                                   // c0 / z of this tile no longer read
+            alu_bar();                                   // c0 / z registers of this tile no longer read
             if (has_next && atid == 0) load_g1(tn);
-            // J1 done -> y1[256:]
-            drain_to_d(Hb, b1_a + 256 * 4);
+            // J01 done -> y1 = leaky(acc + b1): Ha -> D slots (J2 starts), then Hb as J2 frees them
+            drain_half(0, sD, d_empty, de, df_addr, b1_a, 0u, 0.f);
+            drain_half(1, sD, d_empty, de, df_addr, b1_a + 256 * 4, 0u, 0.f);
             // J2 done -> phi = leaky(acc + c2 + wz2 * z) into the P slots (resident until J6)
-            {
-                wait_bit(g_full, gph, 1);
-                wait_bit(acc_full, af, Ha);
-                ptx::tc_fence_after();
-                const float z = zcur[row];
-                for (int j = 0; j < 4; ++j) {
-                    wait_bit(p_empty, pe, j);
-                    drain(Ha, j, sP + j * SLOT, g2_a, wz2_a, z);
-                    signal(pf_addr + j * 8);
-                }
-                release_acc(Ha);
-            }
-            drain_to_d(Hb, g2_a + C2 * 4);                       // J3 -> yF0[:256]
-            drain_to_d(Ha, g2_a + (C2 + 256) * 4);               // J4 -> yF0[256:]
-            drain_to_d(Hb, g2_a + (C2 + F0) * 4);                // J5 -> yF1
+            wait_bit(g_full, gph, 1);
+            drain_half(0, sP, p_empty, pe, pf_addr, g2_a, wz2_a, zcur[row]);
+            drain_half(1, sD, d_empty, de, df_addr, g2_a + C2 * 4, 0u, 0.f);             // J3 -> yF0[:256]
+            drain_half(0, sD, d_empty, de, df_addr, g2_a + (C2 + 256) * 4, 0u, 0.f);     // J4 -> yF0[256:]
+            drain_half(1, sD, d_empty, de, df_addr, g2_a + (C2 + F0) * 4, 0u, 0.f);      // J5 -> yF1
             if (has_next) {                                      // next tile's first y0 k-blocks
                 wait_bit(g_full, gph, 0);
 #pragma unroll
@@ -428,13 +413,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             }
             // J6 done -> fused Conv1d -> 1 + sigmoid + in-bounds mask (`MLP.py:72-73`, `PIFuMRNet.py:173-174`)
             {
-                wait_bit(acc_full, af, Ha);
+                wait_bit(acc_full, af, 0);
                 ptx::tc_fence_after();
                 uint32_t v[2][32];
-                ptx::tmem_ld32(tq + Ha * 256 + 64 * hh, v[0]);
-                ptx::tmem_ld32(tq + Ha * 256 + 64 * hh + 32, v[1]);
+                ptx::tmem_ld32(tq + 64 * hh, v[0]);
+                ptx::tmem_ld32(tq + 64 * hh + 32, v[1]);
                 ptx::tmem_ld_wait();
-                release_acc(Ha);
+                release_acc(0);
                 const uint32_t cf2 = g2_a + (C2 + F0 + F1) * 4;
                 float hacc = 0.f;
 #pragma unroll
