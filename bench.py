@@ -136,6 +136,81 @@ def cpu_port_queries_per_s(prob, calib, n_points, steps=1, warmup=0):
     return pts.shape[2] / (sum(times) / len(times)), torch.get_num_threads(), pts.shape[2], sum(times) / len(times)
 
 
+def build_mesh_problem(dev):
+    """Two-level net whose random-init field has an iso-surface: only the last
+    fine conv is rescaled, from the un-calibrated net's own predictions on seeded pilot points,
+    so ~2 % of the cube is occupied and the sigmoid saturates away from the surface."""
+    from pifu_b200 import PIFuMRNet, PIFuNetwNML, config, synthetic as syn
+    prob = syn.make_problem(bias_std=0.0)
+    calib = syn.default_calib()
+    netG = PIFuNetwNML(config.coarse_opt(), "orthogonal")
+    netMR = PIFuMRNet(config.fine_opt(), netG, "orthogonal")
+    netG.mlp.load_state_dict(prob["coarse"])
+    netMR.mlp.load_state_dict(prob["fine"])
+    netMR.to(dev).eval()
+    netG.im_feat_list = [prob["feat_coarse"].to(dev)]
+    netMR.im_feat_list = [prob["feat_fine"].to(dev)]
+    pilot = syn.random_points(20000, syn.SEED_PILOT, -1.0, 1.0)
+    netMR.query(pilot.to(dev), calib.to(dev))
+    p = netMR.get_preds().float().cpu().numpy()
+    syn.calibrate_last_layer(prob["fine"], 3, p)
+    syn.saturate(prob["fine"], 3)
+    netMR.mlp.load_state_dict(prob["fine"])
+    netMR.to(dev).eval()
+    eng = netMR._engine_for(torch.zeros(1, device=dev))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    return netG, netMR, eng, calib
+
+
+def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
+    """BASELINE.json's second figure: end-to-end latency of mesh_util.reconstruction at res^3 on
+    this GPU (features resident; field -> marching cubes -> mesh on the host), octree and dense,
+    with the phases timed by CUDA events and the marching-cubes HBM roofline."""
+    from pifu_b200 import mesh_util
+    peaks = load_peaks()
+    cal = calib.to(dev)
+    out = {"resolution": res}
+    for mode in ("octree", "dense"):
+        best = None
+        for _ in range(reps + 1):                      # first pass warms allocations
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            mesh = mesh_util.reconstruction(netMR, dev, cal, res, None, None, thresh=0.5,
+                                            use_octree=(mode == "octree"), num_samples=5000)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        stats = []
+        ev[0].record()
+        field = mesh_util.eval_field_device(netMR, dev, cal, res, mode == "octree", stats=stats)
+        ev[1].record()
+        l0 = eng.launch_count()
+        verts, faces, normals, values = eng.marching_cubes(field, 0.5)
+        ev[2].record()
+        host = [t.cpu() for t in (verts, faces, normals, values)]
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        mc_ms = ev[1].elapsed_time(ev[2])
+        nv, nf = int(verts.shape[0]), int(faces.shape[0])
+        mc_bytes = 4.0 * res ** 3 + nv * (24 + 12 + 4) + nf * 12
+        d = {"latency_ms": best, "field_ms": ev[0].elapsed_time(ev[1]), "mc_ms": mc_ms,
+             "mesh_d2h_ms": ev[2].elapsed_time(ev[3]), "verts": nv, "faces": nf,
+             "mc_launches": eng.launch_count() - l0,
+             "mc_roofline": {"bound": "hbm", "achieved": mc_bytes / (mc_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                             "unit": "GB/s", "frac": mc_bytes / (mc_ms * 1e-3) / 1e9 / peaks["hbm"],
+                             "algorithmic_bytes": mc_bytes,
+                             "note": "4 B/voxel field + 40 B/vertex (f64 position, f32 normal, value) + 12 B/face; "
+                                     "count + emit, includes the host sync that sizes the output"}}
+        if mode == "octree":
+            d["evaluated_per_level"] = stats
+            d["evaluated_fraction"] = sum(stats) / float(res ** 3)
+        out[mode] = d
+        del field, verts, faces, normals, values, host
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this metric (oracle port: the
     reference cannot travel to the GPU box and its query path is library torch ops)."""
@@ -164,6 +239,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mesh", action="store_true", help="skip the 512^3 mesh-latency leg")
     ap.add_argument("--res", type=int, default=RES, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -305,9 +381,16 @@ def main():
                         "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
                         "note": "coarse L3/L4 (preds_low) are not on the get_preds() path and are skipped"}
         if not args.no_cpu_baseline:
-            qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, 400000)
+            qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, 128 ** 3)
             cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d-point strided sub-lattice of the %d^3 lattice, chunks of 100000, %.1f s" % (npts, res, sec)}
+
+    mesh = None
+    if rank == 0 and world == 1 and not args.no_mesh:
+        del flush
+        torch.cuda.empty_cache()
+        _, netMR2, eng2, calib2 = build_mesh_problem(dev)
+        mesh = mesh_latency(netMR2, eng2, calib2, dev, 512, 3)
 
     if rank == 0:
         print(json.dumps({
@@ -321,6 +404,7 @@ def main():
                        "path": "chain" if eng.chain_ready() else "per-layer"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "mesh_512": mesh,
         }))
     if world > 1:
         dist.destroy_process_group()

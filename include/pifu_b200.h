@@ -117,6 +117,21 @@ int pifu_mc_count(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, dou
                   long long* nverts, long long* nfaces, void* stream);
 int pifu_mc_emit(pifu_ctx* ctx, double* verts, int* faces, float* normals, float* values, void* stream);
 
+/* Slab form of pifu_mc_count for a volume sharded along axis 0 (the reference is
+ * single-device, there is nothing to cite beyond mesh_util.py:84).  `field` holds planes
+ * [i_global0, i_global0 + n0) of a volume with global_n0 planes; the cell layers [0, cell_layers)
+ * of it are processed (extra planes above them only feed the normals).  Vertex positions, border
+ * handling and vertex ownership use global plane indices, so the slab's vertices and faces are
+ * exactly those a traversal of the whole volume creates in these layers.  With ghost_layers == 1
+ * the first cell layer belongs to the previous slab: it is classified and numbers its vertices
+ * (the next layer's triangles refer to them) but emits no faces; *ghost_verts returns how many
+ * leading vertices it numbered, so that for a slab whose first own vertex has global number G
+ *   global vertex id = local id - *ghost_verts + G
+ * and the caller drops the first *ghost_verts vertices.  pifu_mc_emit is unchanged. */
+int pifu_mc_count_slab(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, double level,
+                       int i_global0, int global_n0, int cell_layers, int ghost_layers,
+                       long long* nverts, long long* nfaces, long long* ghost_verts, void* stream);
+
 /* Number of kernels launched by this context since creation (bench accounting). */
 long long pifu_launch_count(pifu_ctx* ctx);
 

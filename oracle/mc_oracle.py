@@ -29,6 +29,10 @@ def _load():
         _lib = ctypes.CDLL(build())
         _lib.mc_ref_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
         _lib.mc_ref_run.restype = ctypes.c_int
+        _lib.mc_ref_run_slab.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        _lib.mc_ref_run_slab.restype = ctypes.c_int
+        _lib.mc_ref_ghost_verts.restype = ctypes.c_longlong
     return _lib
 
 
@@ -58,3 +62,22 @@ def marching_cubes(volume, level):
     if nv.value == 0:
         raise RuntimeError("No surface found at the given iso value.")
     return verts, faces, normals, values, cases.reshape(vol.shape[0] - 1, vol.shape[1] - 1, vol.shape[2] - 1)
+
+
+def marching_cubes_slab(volume, level, i_global0, global_n0, cell_layers, ghost):
+    """Slab form with the signature of Engine.marching_cubes_slab (numpy in / numpy out):
+    -> (verts, faces, normals, values, ghost_verts).  An empty slab gives zero-length arrays."""
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    lib = _load()
+    if lib.mc_ref_run_slab(vol.ctypes.data, vol.shape[0], vol.shape[1], vol.shape[2], float(level),
+                           int(i_global0), int(global_n0), int(cell_layers), 1 if ghost else 0) != 0:
+        raise MemoryError("mc_ref_run_slab")
+    nv, nf, nc = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+    lib.mc_ref_sizes(ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(nc))
+    verts = np.empty((nv.value, 3), np.float64)
+    faces = np.empty((nf.value, 3), np.int32)
+    normals = np.empty((nv.value, 3), np.float32)
+    values = np.empty((nv.value,), np.float32)
+    lib.mc_ref_copy(verts.ctypes.data_as(ctypes.c_void_p), faces.ctypes.data_as(ctypes.c_void_p),
+                    normals.ctypes.data_as(ctypes.c_void_p), values.ctypes.data_as(ctypes.c_void_p), None)
+    return verts, faces, normals, values, int(lib.mc_ref_ghost_verts())

@@ -50,15 +50,23 @@ static void push_face(int a, int b, int c) {
     ++g_nf;
 }
 
-static double grad(const float* f, const int* n, const long long* st, const int* p, int a) {
+/* n[] = global extents, off = global index of local plane 0 (slab form) */
+static double grad(const float* f, const int* n, const long long* st, const int* p, int a, int off) {
     const long long i = p[0] * st[0] + p[1] * st[1] + p[2] * st[2];
-    const int lo = p[a] > 0 ? -1 : 0, hi = p[a] < n[a] - 1 ? 1 : 0;
+    const int g = p[a] + (a == 0 ? off : 0);
+    const int lo = g > 0 ? -1 : 0, hi = g < n[a] - 1 ? 1 : 0;
     return ((double)f[i + hi * st[a]] - (double)f[i + lo * st[a]]) / (double)(hi - lo);
 }
 
-/* returns 0 on success; results are fetched with mc_ref_sizes / mc_ref_copy */
-int mc_ref_run(const float* f, int n0, int n1, int n2, double level) {
-    const int n[3] = {n0, n1, n2};
+static long long g_ghost_verts = 0;
+
+/* Slab form (mirrors pifu_mc_count_slab, include/pifu_b200.h): f holds planes [i0, i0 + n0) of a
+ * volume with g0 planes; cell layers [0, layers) are traversed; with ghost != 0 the first layer
+ * belongs to the previous slab: it creates (numbers) only the vertices a traversal of the whole
+ * volume would create in that layer - not those on its low face, which an earlier layer owns -
+ * and emits no faces.  returns 0 on success; results are fetched with mc_ref_sizes / mc_ref_copy */
+int mc_ref_run_slab(const float* f, int n0, int n1, int n2, double level, int i0, int g0, int layers, int ghost) {
+    const int n[3] = {g0, n1, n2};
     const long long st[3] = {(long long)n1 * n2, n2, 1};
     const long long nvox = (long long)n0 * n1 * n2;
     int* cache = (int*)malloc(sizeof(int) * 3 * nvox);      /* edge (voxel, axis) -> vertex id */
@@ -67,10 +75,12 @@ int mc_ref_run(const float* f, int n0, int n1, int n2, double level) {
     if (!cache) return -1;
     for (q = 0; q < 3 * nvox; ++q) cache[q] = -1;
     g_nv = g_nf = 0;
-    g_ncells = (long long)(n0 - 1) * (n1 - 1) * (n2 - 1);
+    g_ghost_verts = 0;
+    g_ncells = (long long)layers * (n1 - 1) * (n2 - 1);
     g_cases = (unsigned char*)realloc(g_cases, g_ncells > 0 ? g_ncells : 1);
     q = 0;
-    for (i = 0; i < n0 - 1; ++i)
+    for (i = 0; i < layers; ++i) {
+        if (ghost && i == 1) g_ghost_verts = g_nv;
         for (j = 0; j < n1 - 1; ++j)
             for (k = 0; k < n2 - 1; ++k, ++q) {
                 int cs = 0;
@@ -90,6 +100,7 @@ int mc_ref_run(const float* f, int n0, int n1, int n2, double level) {
                         pb[0] = i + MC_CORNER[cb][0]; pb[1] = j + MC_CORNER[cb][1]; pb[2] = k + MC_CORNER[cb][2];
                         for (a = 0; a < 3; ++a) lo[a] = pa[a] < pb[a] ? pa[a] : pb[a];
                         key = 3 * (lo[0] * st[0] + lo[1] * st[1] + lo[2]) + MC_EDGE_AXIS[e];
+                        if (ghost && i == 0 && pa[0] == 0 && pb[0] == 0) { vid[c] = -1; continue; }   /* owned by the slab before */
                         if (cache[key] < 0) {
                             const double va = (double)f[pa[0] * st[0] + pa[1] * st[1] + pa[2]];
                             const double vb = (double)f[pb[0] * st[0] + pb[1] * st[1] + pb[2]];
@@ -99,8 +110,9 @@ int mc_ref_run(const float* f, int n0, int n1, int n2, double level) {
                             double p[3], g[3], len;
                             float nr[3];
                             for (a = 0; a < 3; ++a) {
-                                const double pa_w = (double)pa[a] * fa, pb_w = (double)pb[a] * fb;
-                                const double ga_w = grad(f, n, st, pa, a) * fa, gb_w = grad(f, n, st, pb, a) * fb;
+                                const int o = a == 0 ? i0 : 0;
+                                const double pa_w = (double)(pa[a] + o) * fa, pb_w = (double)(pb[a] + o) * fb;
+                                const double ga_w = grad(f, n, st, pa, a, i0) * fa, gb_w = grad(f, n, st, pb, a, i0) * fb;
                                 p[a] = (pa_w + pb_w) / fs;
                                 g[a] = (ga_w + gb_w) / fs;
                             }
@@ -114,12 +126,20 @@ int mc_ref_run(const float* f, int n0, int n1, int n2, double level) {
                         }
                         vid[c] = cache[key];
                     }
-                    push_face(vid[0], vid[1], vid[2]);
+                    if (!(ghost && i == 0)) push_face(vid[0], vid[1], vid[2]);
                 }
             }
+    }
     free(cache);
+    (void)n0;
     return 0;
 }
+
+int mc_ref_run(const float* f, int n0, int n1, int n2, double level) {
+    return mc_ref_run_slab(f, n0, n1, n2, level, 0, n0, n0 - 1, 0);
+}
+
+long long mc_ref_ghost_verts(void) { return g_ghost_verts; }
 
 void mc_ref_sizes(long long* nv, long long* nf, long long* ncells) { *nv = g_nv; *nf = g_nf; *ncells = g_ncells; }
 

@@ -41,6 +41,9 @@ SIGNATURES = {
     "pifu_octree_export": (ctypes.c_int, [VP, VP, VP, VP]),
     "pifu_mc_count": (ctypes.c_int, [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                      c_ll_p, c_ll_p, VP]),
+    "pifu_mc_count_slab": (ctypes.c_int, [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          c_ll_p, c_ll_p, c_ll_p, VP]),
     "pifu_mc_emit": (ctypes.c_int, [VP, VP, VP, VP, VP, VP]),
     "pifu_launch_count": (ctypes.c_longlong, [VP]),
     "pifu_profile_enable": (ctypes.c_int, [VP, ctypes.c_int]),

@@ -531,6 +531,7 @@ int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* i
     }
     return 0;
 }
+int ctx_check_ready(pifu_ctx* c, int levels) { return check_ready(c, levels); }
 int ctx_num_sms(pifu_ctx* c) { return c->num_sms; }
 void ctx_count_launch(pifu_ctx* c, int n) { c->launches += n; }
 OctreeState*& ctx_octree(pifu_ctx* c) { return c->octree; }

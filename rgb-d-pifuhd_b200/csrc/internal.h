@@ -17,6 +17,7 @@ int launch_unblock(const uint8_t* buf, int kb_stride, int kb_off, int C, int n, 
 // api.cu services used by the octree driver
 int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
              const float* calib, const double* calib_inv, float* out, cudaStream_t s);
+int ctx_check_ready(pifu_ctx* c, int levels);      // MLPs + feature maps set, workspace allocated
 int ctx_num_sms(pifu_ctx* c);
 void ctx_count_launch(pifu_ctx* c, int n);
 

@@ -319,6 +319,7 @@ int pifu_eval_grid_octree(pifu_ctx* c, int levels, int R0, int R1, int R2, int i
                           const float* calib, const double* calib_inv, double* sdf64, float* sdf32,
                           long long* evaluated_per_level, int max_levels, void* stream) {
     if (!c || !calib || !calib_inv) { set_error("bad arguments to pifu_eval_grid_octree"); return -1; }
+    if (ctx_check_ready(c, levels)) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (octree_begin(c, R0, R1, R2, init_resolution, threshold, s)) return -1;
     int lvl = 0;

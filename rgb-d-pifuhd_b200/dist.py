@@ -52,6 +52,79 @@ def gather_concat(local, n_total, per_rank, group=None, dst=None):
     return None
 
 
+def gather_varlen(local, counts, group=None, dst=0):
+    """Concatenate per-rank tensors whose leading sizes `counts` differ, on rank `dst` (None elsewhere)."""
+    W = world_size(group)
+    if W == 1:
+        return local
+    per = max(max(counts), 1)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    if rank(group) == dst:
+        parts = [torch.empty_like(pad) for _ in range(W)]
+        dist.gather(pad, parts, dst=dst, group=group)
+        return torch.cat([p[:n] for p, n in zip(parts, counts)], 0)
+    dist.gather(pad, None, dst=dst, group=group)
+    return None
+
+
+def exchange_halo(local, group=None):
+    """local: this rank's planes [n, R1, R2] (n >= 2).  Returns (below, above): the previous rank's
+    last plane [1, R1, R2] (None on rank 0) and the next rank's first two planes (None on the last
+    rank) - what slab marching cubes needs beyond its own planes (~1 MB at 512^2)."""
+    W, r = world_size(group), rank(group)
+    if W == 1:
+        return None, None
+    if local.shape[0] < 2:
+        raise ValueError("slab marching cubes needs at least two planes per rank")
+    edge = torch.stack([local[0], local[1], local[-1]], 0).contiguous()
+    buf = torch.empty((W * 3,) + tuple(edge.shape[1:]), dtype=edge.dtype, device=edge.device)
+    dist.all_gather_into_tensor(buf, edge, group=group)
+    buf = buf.view((W,) + tuple(edge.shape))
+    below = buf[r - 1, 2:3] if r > 0 else None
+    above = buf[r + 1, 0:2] if r < W - 1 else None
+    return below, above
+
+
+def sharded_marching_cubes(mc_slab, planes, level, R0, pb, pe, group=None, dst=0):
+    """Marching cubes of a volume sharded along axis 0; every rank extracts the cells of its own
+    planes [pb, pe) and the fragments are gathered (vertex numbers offset by the slabs before it)
+    into exactly the mesh a traversal of the whole volume produces.
+
+    planes(lo, hi) -> float32 [hi - lo, R1, R2] device tensor of global planes [lo, hi);
+    mc_slab = Engine.marching_cubes_slab (or a stand-in with the same signature).
+    Returns (verts, faces, normals, values) tensors on `dst`, None elsewhere."""
+    W = world_size(group)
+    cells_end = min(pe, R0 - 1)
+    if cells_end > pb:
+        lo, hi = max(pb - 1, 0), min(pe + 2, R0)
+        ghost = pb > 0
+        v, f, n, val, ng = mc_slab(planes(lo, hi), level, lo, R0, cells_end - lo, ghost)
+        v, n, val = v[ng:], n[ng:], val[ng:]
+    else:
+        ref = planes(pb, pb)
+        v = torch.empty((0, 3), dtype=torch.float64, device=ref.device)
+        f = torch.empty((0, 3), dtype=torch.int32, device=ref.device)
+        n = torch.empty((0, 3), dtype=torch.float32, device=ref.device)
+        val = torch.empty((0,), dtype=torch.float32, device=ref.device)
+        ng = 0
+    if W == 1:
+        if v.shape[0] == 0:
+            raise ValueError("No surface found at the given iso value (or level outside the data range)")
+        return v, f, n, val
+    cnt = torch.tensor([v.shape[0], f.shape[0]], dtype=torch.int64, device=v.device)
+    allc = torch.empty(W * 2, dtype=torch.int64, device=v.device)
+    dist.all_gather_into_tensor(allc, cnt, group=group)
+    allc = allc.view(W, 2).cpu()
+    nvs, nfs = [int(x) for x in allc[:, 0]], [int(x) for x in allc[:, 1]]
+    if sum(nvs) == 0:
+        raise ValueError("No surface found at the given iso value (or level outside the data range)")
+    first = sum(nvs[:rank(group)])                       # global number of this slab's first own vertex
+    f = f + (first - ng)
+    out = [gather_varlen(t, c, group=group, dst=dst) for t, c in ((v, nvs), (f, nfs), (n, nvs), (val, nvs))]
+    return tuple(out) if rank(group) == dst else None
+
+
 def sharded_eval_grid(eng, levels, res, calib, group=None, dst=0):
     """Dense lattice, slab-sharded along axis 0.  Returns the [R,R,R] float32 field on `dst`
     (None on the other ranks)."""
@@ -87,4 +160,37 @@ def sharded_eval_grid_octree(eng, levels, res, calib, init_resolution=64, thresh
         mine = evaluate(ids[b:e]) if e > b else torch.empty(0, device=ids.device, dtype=torch.float32)
         eng.octree_commit(gather_concat(mine, n, per, group=group, dst=None) if n else mine)
     _, sdf32 = eng.octree_export(want64=False, want32=True)
-    return sdf32 if r == dst else None
+    return sdf32 if (dst is None or r == dst) else None
+
+
+def sharded_mesh(eng, levels, res, calib, use_octree, level=0.5, init_resolution=64, threshold=0.05,
+                 group=None, dst=0, stats=None):
+    """Field + iso-surface of a res^3 lattice over all ranks (north_star: z-slab sharding, NCCL only
+    for the halo planes / frontier values and the mesh fragments).  Dense: every rank evaluates and
+    extracts its own slab, one halo exchange of three planes.  Octree: the replicated bookkeeping
+    leaves the whole field on every rank, which then extracts its own slab.  Returns the mesh
+    tensors on `dst` (None elsewhere); raises ValueError on every rank when there is no surface."""
+    W, r = world_size(group), rank(group)
+    plane = res * res
+    b, e = shard_bounds(res * plane, W, r, align=plane)
+    pb, pe = b // plane, e // plane
+    if use_octree:
+        field = sharded_eval_grid_octree(eng, levels, res, calib, init_resolution, threshold, group=group,
+                                         dst=None, stats=stats)
+
+        def planes(lo, hi):
+            return field[lo:hi]
+    else:
+        local = eng.eval_grid(levels, res, calib, id_begin=b, id_end=e).view(pe - pb, res, res) if e > b else \
+            torch.empty((0, res, res), device=eng.device, dtype=torch.float32)
+        below, above = exchange_halo(local, group=group)
+
+        def planes(lo, hi):
+            parts = []
+            if lo < pb:
+                parts.append(below[below.shape[0] - (pb - lo):])
+            parts.append(local[max(lo - pb, 0):max(min(hi, pe) - pb, 0)])
+            if hi > pe:
+                parts.append(above[:hi - pe])
+            return torch.cat(parts, 0) if len(parts) > 1 else parts[0]
+    return sharded_marching_cubes(eng.marching_cubes_slab, planes, level, res, pb, pe, group=group, dst=dst)

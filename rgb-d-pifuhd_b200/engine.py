@@ -277,6 +277,32 @@ class Engine:
         return verts, faces, normals, values
 
 
+    def marching_cubes_slab(self, field, level, i_global0, global_n0, cell_layers, ghost, want_normals=True):
+        """Slab form (multi-GPU): `field` = planes [i_global0, i_global0 + n0) of a global_n0-plane
+        volume; the first `cell_layers` cell layers are processed, the first one only as a ghost when
+        `ghost`.  -> (verts, faces, normals, values, ghost_verts): the caller drops the first
+        ghost_verts vertices and renumbers faces by (first own global vertex number - ghost_verts).
+        An empty slab returns zero-length tensors (a neighbour may still hold the surface)."""
+        f = field.to(self.device, torch.float32).contiguous()
+        nv, nf, ng = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(self.lib.pifu_mc_count_slab(
+            self.h, ctypes.c_void_p(f.data_ptr()), f.shape[0], f.shape[1], f.shape[2], float(level),
+            int(i_global0), int(global_n0), int(cell_layers), 1 if ghost else 0,
+            ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(ng), _stream(self.device_index)))
+        verts = torch.empty((nv.value, 3), device=self.device, dtype=torch.float64)
+        faces = torch.empty((nf.value, 3), device=self.device, dtype=torch.int32)
+        normals = torch.empty((nv.value, 3), device=self.device, dtype=torch.float32) if want_normals else None
+        values = torch.empty((nv.value,), device=self.device, dtype=torch.float32) if want_normals else None
+        if nv.value:
+            _lib.check(self.lib.pifu_mc_emit(self.h, ctypes.c_void_p(verts.data_ptr()),
+                                             ctypes.c_void_p(faces.data_ptr()) if nf.value else None,
+                                             ctypes.c_void_p(normals.data_ptr()) if want_normals else None,
+                                             ctypes.c_void_p(values.data_ptr()) if want_normals else None,
+                                             _stream(self.device_index)))
+        self._keep["mc_field"] = f
+        return verts, faces, normals, values, int(ng.value)
+
+
 class _DevView:
     """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
 

@@ -155,7 +155,12 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
     mat[0, 0] = mat[1, 1] = mat[2, 2] = 2.0 / resolution
     mat[0:3, 3] = -1.0
     calib_inv = np.linalg.inv(calib_tensor[0].detach().cpu().numpy())       # float32, `:61-62`
-    if _is_native(net):
+    from . import dist as pdist
+    sharded = _is_native(net) and (group is not None or pdist.world_size() > 1)
+    field = None
+    if sharded:
+        pass                             # field and iso-surface are extracted slab by slab below
+    elif _is_native(net):
         field = eval_field_device(net, device, calib_tensor, resolution, use_octree, group=group)
         eng = get_engine(device)
     else:
@@ -172,10 +177,15 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
         sdf = (eval_grid_octree if use_octree else eval_grid)(coords, eval_func, num_samples=num_samples)
         eng = get_engine(device)
         field = torch.from_numpy(sdf.astype(np.float32)).to(device)
-    if field is None:                    # non-root rank of a sharded run
-        return None
     try:
-        verts, faces, normals, values = eng.marching_cubes(field, thresh)
+        if sharded:
+            eng, levels = _prepare_native(net, device)
+            out = pdist.sharded_mesh(eng, levels, resolution, calib_tensor[0], use_octree, level=thresh, group=group)
+            if out is None:              # non-root rank: the fragments went to rank 0
+                return None
+            verts, faces, normals, values = out
+        else:
+            verts, faces, normals, values = eng.marching_cubes(field, thresh)
         trans = np.matmul(calib_inv, mat)
         t = torch.from_numpy(trans).to(device)
         verts = (verts @ t[:3, :3].T + t[:3, 3]).cpu().numpy()

@@ -113,3 +113,66 @@ def test_two_rank_sharding_matches_single(tmp_path):
                                          init_resolution=8, num_samples=10 ** 9)
     assert np.array_equal(got["octree"].numpy(), ref_oct.astype(np.float32))
     assert got["stats"] == calls
+
+
+# ----------------------------------------------------------------------------- sharded mesh
+def _oracle_slab(field, level, i0, g0, layers, ghost):
+    """Stand-in for Engine.marching_cubes_slab: the CPU oracle's slab form, torch in / torch out."""
+    from oracle import mc_oracle
+    v, f, n, val, ng = mc_oracle.marching_cubes_slab(field.numpy(), level, i0, g0, layers, ghost)
+    return torch.from_numpy(v), torch.from_numpy(f), torch.from_numpy(n), torch.from_numpy(val), ng
+
+
+class FakeMeshEngine(FakeEngine):
+    marching_cubes_slab = staticmethod(_oracle_slab)
+
+    def eval_lattice_ids(self, levels, res, ids, calib):
+        return self.fn(ids)
+
+
+def _mesh_worker(rank, world, port, out, res, flat):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fn = (lambda ids: torch.full((ids.numel(),), 0.25)) if flat else _field(res)
+    eng = FakeMeshEngine(res, fn)
+    got = {}
+    for mode in ("dense", "octree"):
+        try:
+            m = pdist.sharded_mesh(eng, 2, res, None, mode == "octree", level=0.5, init_resolution=8)
+            got[mode] = m
+            assert (m is None) == (rank != 0)
+        except ValueError:
+            got[mode] = "no surface"
+    if rank == 0:
+        torch.save(got, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,res", [(2, 32), (3, 24)])
+def test_sharded_mesh_equals_whole_volume(tmp_path, world, res):
+    """Slab-by-slab extraction + fragment gather (ghost layer, halo planes, vertex renumbering)
+    gives bit for bit the mesh of a sequential traversal of the whole volume."""
+    from oracle import mc_oracle
+    from pifu_b200 import mesh_util
+    out = str(tmp_path / "mesh.pt")
+    mp.spawn(_mesh_worker, args=(world, 29573 + world, out, res, False), nprocs=world, join=True)
+    got = torch.load(out)
+    fn = _field(res)
+    dense = fn(torch.arange(res ** 3)).view(res, res, res).numpy()
+    coords = np.indices((res,) * 3).astype(np.float64)
+    octo = mesh_util.eval_grid_octree(
+        coords, lambda p: fn(torch.from_numpy(((p[0] * res + p[1]) * res + p[2]).astype(np.int64))).numpy(),
+        init_resolution=8, num_samples=10 ** 9).astype(np.float32)
+    for mode, vol in (("dense", dense), ("octree", octo)):
+        rv, rf, rn, rval, _ = mc_oracle.marching_cubes(vol, 0.5)
+        v, f, n, val = got[mode]
+        assert np.array_equal(f.numpy(), rf) and np.array_equal(v.numpy(), rv)
+        assert np.array_equal(n.numpy(), rn) and np.array_equal(val.numpy(), rval)
+
+
+def test_sharded_mesh_without_surface_raises_everywhere(tmp_path):
+    out = str(tmp_path / "mesh.pt")
+    mp.spawn(_mesh_worker, args=(2, 29579, out, 16, True), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got == {"dense": "no surface", "octree": "no surface"}
