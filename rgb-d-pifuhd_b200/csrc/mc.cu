@@ -10,6 +10,8 @@
 // first cell has a closed form - the lexicographically smallest cell containing the edge -
 // so numbering is an exclusive scan over cells of "edges this cell owns", plus the rank of
 // the edge among the owned edges in the cell's first-use order (MC_VERTS).
+#include <cmath>
+
 #include "../../include/pifu_b200.h"
 #include "common.cuh"
 #include "internal.h"
@@ -24,13 +26,16 @@ struct McState {
     int n[3] = {0, 0, 0};
     double level = 0.5;
     const float* field = nullptr;
-    long long cells = 0;
-    uint8_t* cases = nullptr;
+    long long cells = 0;               // padded: layers * c1 * cs2
+    long long blocks = 0;
+    uint8_t* cases = nullptr;          // [layers][c1][cs2], cs2 = c2 rounded up to 4
     uint32_t* vbase = nullptr;         // per cell: number of the first vertex it creates
-    uint32_t* vsums = nullptr;         // per block -> exclusive offsets
-    uint32_t* tsums = nullptr;
-    unsigned long long* totals = nullptr;   // [2] device
-    long long cap_cells = 0, cap_blocks = 0;
+    uint32_t* vsums = nullptr;         // per block (+1): vertices created -> exclusive offsets, total at [blocks]
+    uint32_t* tsums = nullptr;         // per block (+1): triangles
+    uint32_t* partials = nullptr;      // scan spine
+    uint8_t* own = nullptr;            // [256][8] vertices a cell of case cs creates, by border mask
+    unsigned long long* totals = nullptr;   // [3] device: vertices, triangles, ghost-layer vertices
+    long long cap_cells = 0, cap_blocks = 0, cap_partials = 0;
     long long nverts = 0, nfaces = 0;
     // slab mode (multi-GPU): the volume is planes [i0, i0 + n[0]) of a g0-plane field;
     // cell layers [0, layers) are processed and the first `ghost` of them only number their vertices
@@ -40,64 +45,97 @@ struct McState {
 void mc_free(McState* s) {
     if (!s) return;
     cudaFree(s->cases); cudaFree(s->vbase); cudaFree(s->vsums); cudaFree(s->tsums); cudaFree(s->totals);
+    cudaFree(s->partials); cudaFree(s->own);
     delete s;
 }
 
 namespace {
 
-// n*: planes of the local volume; c*: cell layers processed; i0 / g0: global index of local plane
-// 0 and global plane count (slab mode); ghost: leading cell layers that emit no faces
-struct Dims { int n0, n1, n2, c0, c1, c2, i0, g0, ghost; };
+constexpr int CPT = 4;                 // cells per thread, consecutive along axis 2
 
-__device__ __forceinline__ void cell_coords(long long c, const Dims& d, int& i, int& j, int& k) {
-    k = static_cast<int>(c % d.c2);
-    j = static_cast<int>((c / d.c2) % d.c1);
-    i = static_cast<int>(c / (static_cast<long long>(d.c2) * d.c1));
-}
+// n*: planes of the local volume; c*: cell layers processed; cs2: padded cells per row, nq = cs2 / CPT;
+// i0 / g0: global index of local plane 0 and global plane count (slab mode); ghost: leading cell
+// layers that emit no faces
+struct Dims { int n0, n1, n2, c0, c1, c2, cs2, nq, i0, g0, ghost; };
 
 __device__ __forceinline__ int zero_mask(int i, int j, int k) {
     return (i == 0 ? 1 : 0) | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0);
 }
 
-// number of lattice edges first used by this cell
-__device__ __forceinline__ int owned_count(int cs, int zmask) {
+// own[cs * 8 + zmask]: number of lattice edges first used by a cell of case cs whose low faces
+// on the axes in zmask lie on the volume border (no earlier cell shares them)
+__global__ void own_table_kernel(uint8_t* __restrict__ own) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 256 * 8) return;
+    const int cs = t >> 3, zm = t & 7;
     int n = 0;
     const int nv = MC_NVERT[cs];
-    for (int q = 0; q < nv; ++q) {
-        const int e = MC_VERTS[cs][q];
-        n += ((MC_EDGE_LOWMASK[e] & ~zmask) == 0) ? 1 : 0;
-    }
-    return n;
+    for (int q = 0; q < nv; ++q) n += ((MC_EDGE_LOWMASK[MC_VERTS[cs][q]] & ~zm) == 0) ? 1 : 0;
+    own[t] = static_cast<uint8_t>(n);
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK) classify_kernel(const float* __restrict__ f, Dims d, double level,
+// thread g of the launch -> its row of cells (i, j) and first cell k0; false past the end
+__device__ __forceinline__ bool thread_cells(const Dims& d, long long g, int& i, int& j, int& k0, long long& row) {
+    const long long total = static_cast<long long>(d.c0) * d.c1 * d.nq;      // < 2^31 (checked by the host)
+    if (g >= total) return false;
+    const uint32_t g32 = static_cast<uint32_t>(g), r32 = g32 / static_cast<uint32_t>(d.nq);
+    row = r32;
+    k0 = static_cast<int>(g32 - r32 * static_cast<uint32_t>(d.nq)) * CPT;
+    i = static_cast<int>(r32 / static_cast<uint32_t>(d.c1));
+    j = static_cast<int>(r32 - static_cast<uint32_t>(i) * static_cast<uint32_t>(d.c1));
+    return true;
+}
+
+// Pass 1: case index of CPT cells per thread (the field is read once: 4 rows x 5 values per
+// thread, as 128-bit loads when the rows are 16-byte aligned), cases stored as one 32-bit word,
+// per-block totals of vertices created and triangles.
+// `lf` is the largest float <= level, so (double)v > level  <=>  v > lf exactly.
+__global__ void __launch_bounds__(SCAN_BLOCK) classify_kernel(const float* __restrict__ f, Dims d, float lf, int vec,
+                                                              const uint8_t* __restrict__ own,
                                                               uint8_t* __restrict__ cases,
                                                               uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums) {
-    const long long ncell = static_cast<long long>(d.c0) * d.c1 * d.c2;
-    const long long c = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
+    __shared__ uint32_t red[2][SCAN_BLOCK / 32];
+    const long long g = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
+    int i, j, k0;
+    long long row;
     uint32_t nv = 0, nt = 0;
-    if (c < ncell) {
-        int i, j, k;
-        cell_coords(c, d, i, j, k);
-        int cs = 0;
+    if (thread_cells(d, g, i, j, k0, row)) {
+        uint32_t in[4] = {0u, 0u, 0u, 0u};             // bit m of in[r]: value m of row r is inside
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const long long v = (static_cast<long long>(i + MC_CORNER[q][0]) * d.n1 + (j + MC_CORNER[q][1])) * d.n2 +
-                                (k + MC_CORNER[q][2]);
-            cs |= (static_cast<double>(__ldg(f + v)) > level) ? (1 << q) : 0;
+        for (int r = 0; r < 4; ++r) {
+            const float* p = f + (static_cast<long long>(i + (r >> 1)) * d.n1 + (j + (r & 1))) * d.n2 + k0;
+            float a[CPT + 1];
+            if (vec) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
+                a[4] = (k0 + CPT < d.n2) ? __ldg(p + CPT) : 0.f;
+            } else {
+#pragma unroll
+                for (int m = 0; m <= CPT; ++m) a[m] = (k0 + m < d.n2) ? __ldg(p + m) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m <= CPT; ++m) in[r] |= (a[m] > lf) ? (1u << m) : 0u;
         }
-        cases[c] = static_cast<uint8_t>(cs);
-        if (cs != 0 && cs != 255) {
-            nt = MC_NTRI[cs];
-            nv = owned_count(cs, zero_mask(i + d.i0, j, k));
-            if (i < d.ghost) nt = 0;
+        // corners: 0 (i,j,k) 1 (i,j,k+1) 2 (i,j+1,k+1) 3 (i,j+1,k) 4 (i+1,j,k) 5 (i+1,j,k+1) 6 (i+1,j+1,k+1) 7 (i+1,j+1,k)
+        uint32_t word = 0;
+        const int zij = zero_mask(i + d.i0, j, 1);
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) {
+            if (k0 + m >= d.c2) break;
+            const uint32_t cs = ((in[0] >> m) & 1u) | (((in[0] >> (m + 1)) & 1u) << 1) | (((in[1] >> (m + 1)) & 1u) << 2) |
+                                (((in[1] >> m) & 1u) << 3) | (((in[2] >> m) & 1u) << 4) | (((in[2] >> (m + 1)) & 1u) << 5) |
+                                (((in[3] >> (m + 1)) & 1u) << 6) | (((in[3] >> m) & 1u) << 7);
+            word |= cs << (8 * m);
+            if (cs != 0u && cs != 255u) {
+                nv += __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0)));
+                if (i >= d.ghost) nt += MC_NTRI[cs];
+            }
         }
+        *reinterpret_cast<uint32_t*>(cases + row * d.cs2 + k0) = word;
     }
-    uint32_t bt;
-    block_exclusive_scan(nv, &bt);
-    if (threadIdx.x == 0) vsums[blockIdx.x] = bt;
-    block_exclusive_scan(nt, &bt);
-    if (threadIdx.x == 0) tsums[blockIdx.x] = bt;
+    const uint32_t bv = block_sum(nv, red[0]);
+    const uint32_t bt = block_sum(nt, red[1]);
+    if (threadIdx.x == 0) { vsums[blockIdx.x] = bv; tsums[blockIdx.x] = bt; }
 }
 
 // weights 1 / (FLT_EPSILON + |v - level|) in float64 (== linear interpolation up to the epsilon)
@@ -140,40 +178,52 @@ __device__ __forceinline__ void edge_vertex(const float* __restrict__ f, const D
     *val = static_cast<float>(va > vb ? va : vb);
 }
 
+// Pass 2: vertices.  Blocks that create none leave at once (the surface touches ~1 % of the cells).
 __global__ void __launch_bounds__(SCAN_BLOCK) emit_vertices_kernel(const float* __restrict__ f, Dims d, double level,
+                                                                   const uint8_t* __restrict__ own,
                                                                    const uint8_t* __restrict__ cases,
                                                                    const uint32_t* __restrict__ voffs,
                                                                    uint32_t* __restrict__ vbase, double* __restrict__ verts,
                                                                    float* __restrict__ normals, float* __restrict__ values) {
-    const long long ncell = static_cast<long long>(d.c0) * d.c1 * d.c2;
-    const long long c = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
-    int cs = 0, i = 0, j = 0, k = 0, zm = 0;
-    uint32_t nv = 0;
-    if (c < ncell) {
-        cs = cases[c];
-        if (cs != 0 && cs != 255) {
-            cell_coords(c, d, i, j, k);
-            zm = zero_mask(i + d.i0, j, k);
-            nv = owned_count(cs, zm);
+    if (voffs[blockIdx.x + 1] == voffs[blockIdx.x]) return;
+    const long long g = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
+    int i = 0, j = 0, k0 = 0;
+    long long row = 0;
+    uint32_t word = 0, nv = 0;
+    uint8_t cnt[CPT] = {0, 0, 0, 0};
+    if (thread_cells(d, g, i, j, k0, row)) {
+        word = *reinterpret_cast<const uint32_t*>(cases + row * d.cs2 + k0);
+        const int zij = zero_mask(i + d.i0, j, 1);
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) {
+            const uint32_t cs = (word >> (8 * m)) & 255u;
+            if (cs != 0u && cs != 255u) { cnt[m] = __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0))); nv += cnt[m]; }
         }
     }
     uint32_t bt;
-    const uint32_t base = voffs[blockIdx.x] + block_exclusive_scan(nv, &bt);
-    if (cs == 0 || cs == 255) return;
-    vbase[c] = base;
-    uint32_t r = 0;
-    const int nvc = MC_NVERT[cs];
-    for (int q = 0; q < nvc; ++q) {
-        const int e = MC_VERTS[cs][q];
-        if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
-        double pos[3];
-        float nrm[3], val;
-        edge_vertex(f, d, level, i, j, k, e, pos, nrm, &val);
-        const size_t o = static_cast<size_t>(base + r);
-        verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
-        if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
-        if (values) values[o] = val;
-        ++r;
+    uint32_t base = voffs[blockIdx.x] + block_exclusive_scan(nv, &bt);
+    if (word == 0u || word == 0xffffffffu) return;
+    for (int m = 0; m < CPT; ++m) {
+        const int cs = static_cast<int>((word >> (8 * m)) & 255u);
+        if (cs == 0 || cs == 255) continue;
+        const int k = k0 + m;
+        const int zm = zero_mask(i + d.i0, j, k);
+        vbase[row * d.cs2 + k] = base;
+        uint32_t r = 0;
+        const int nvc = MC_NVERT[cs];
+        for (int q = 0; q < nvc; ++q) {
+            const int e = MC_VERTS[cs][q];
+            if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
+            double pos[3];
+            float nrm[3], val;
+            edge_vertex(f, d, level, i, j, k, e, pos, nrm, &val);
+            const size_t o = static_cast<size_t>(base + r);
+            verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
+            if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
+            if (values) values[o] = val;
+            ++r;
+        }
+        base += cnt[m];
     }
 }
 
@@ -184,7 +234,7 @@ __device__ __forceinline__ int vertex_id(const Dims& d, const uint8_t* __restric
     const int shift = low & ((i + d.i0 > 0 ? 1 : 0) | (j > 0 ? 2 : 0) | (k > 0 ? 4 : 0));   // axes where a previous cell shares it
     const int oi = i - (shift & 1), oj = j - ((shift >> 1) & 1), ok = k - ((shift >> 2) & 1);
     const int oe = MC_EDGE_SHIFT[e][shift];
-    const long long oc = (static_cast<long long>(oi) * d.c1 + oj) * d.c2 + ok;
+    const long long oc = (static_cast<long long>(oi) * d.c1 + oj) * d.cs2 + ok;
     const int ocs = cases[oc];
     const int zm = zero_mask(oi + d.i0, oj, ok);
     int r = 0;
@@ -197,48 +247,58 @@ __device__ __forceinline__ int vertex_id(const Dims& d, const uint8_t* __restric
     return static_cast<int>(vbase[oc]) + r;
 }
 
+// Pass 3: faces, in cell order; vertex numbers come from the owning cells' vbase.
 __global__ void __launch_bounds__(SCAN_BLOCK) emit_faces_kernel(Dims d, const uint8_t* __restrict__ cases,
                                                                 const uint32_t* __restrict__ vbase,
                                                                 const uint32_t* __restrict__ toffs, int* __restrict__ faces) {
-    const long long ncell = static_cast<long long>(d.c0) * d.c1 * d.c2;
-    const long long c = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
-    int cs = 0;
-    uint32_t nt = 0;
-    if (c < ncell) {
-        cs = cases[c];
-        if (cs != 0 && cs != 255 && c >= static_cast<long long>(d.ghost) * d.c1 * d.c2) nt = MC_NTRI[cs];
+    if (toffs[blockIdx.x + 1] == toffs[blockIdx.x]) return;
+    const long long g = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
+    int i = 0, j = 0, k0 = 0;
+    long long row = 0;
+    uint32_t word = 0, nt = 0;
+    if (thread_cells(d, g, i, j, k0, row) && i >= d.ghost) {
+        word = *reinterpret_cast<const uint32_t*>(cases + row * d.cs2 + k0);
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) nt += MC_NTRI[(word >> (8 * m)) & 255u];
     }
     uint32_t bt;
-    const uint32_t base = toffs[blockIdx.x] + block_exclusive_scan(nt, &bt);
+    uint32_t base = toffs[blockIdx.x] + block_exclusive_scan(nt, &bt);
     if (nt == 0) return;
-    int i, j, k;
-    cell_coords(c, d, i, j, k);
-    for (uint32_t t = 0; t < nt; ++t) {
-        const size_t o = static_cast<size_t>(base + t) * 3;
+    for (int m = 0; m < CPT; ++m) {
+        const int cs = static_cast<int>((word >> (8 * m)) & 255u);
+        const uint32_t n = MC_NTRI[cs];
+        for (uint32_t t = 0; t < n; ++t) {
+            const size_t o = static_cast<size_t>(base + t) * 3;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cases, vbase, i, j, k, MC_TRIS[cs][3 * t + q]);
+            for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cases, vbase, i, j, k0 + m, MC_TRIS[cs][3 * t + q]);
+        }
+        base += n;
     }
 }
 
-// number of vertices owned by the cells before the first non-ghost cell (one block)
-__global__ void __launch_bounds__(SCAN_BLOCK) ghost_prefix_kernel(Dims d, const uint8_t* __restrict__ cases,
+// number of vertices created before the first non-ghost cell (one block)
+__global__ void __launch_bounds__(SCAN_BLOCK) ghost_prefix_kernel(Dims d, const uint8_t* __restrict__ own,
+                                                                  const uint8_t* __restrict__ cases,
                                                                   const uint32_t* __restrict__ voffs,
                                                                   unsigned long long* __restrict__ out) {
-    const long long first = static_cast<long long>(d.ghost) * d.c1 * d.c2;      // first non-ghost cell
+    __shared__ uint32_t red[SCAN_BLOCK / 32];
+    const long long first = static_cast<long long>(d.ghost) * d.c1 * d.nq;      // first non-ghost thread
     const long long blk = first / SCAN_BLOCK;
-    const long long c = blk * SCAN_BLOCK + threadIdx.x;
+    const long long g = blk * SCAN_BLOCK + threadIdx.x;
     uint32_t nv = 0;
-    if (c < first) {
-        const int cs = cases[c];
-        if (cs != 0 && cs != 255) {
-            int i, j, k;
-            cell_coords(c, d, i, j, k);
-            nv = owned_count(cs, zero_mask(i + d.i0, j, k));
+    int i, j, k0;
+    long long row;
+    if (g < first && thread_cells(d, g, i, j, k0, row)) {
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(cases + row * d.cs2 + k0);
+        const int zij = zero_mask(i + d.i0, j, 1);
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) {
+            const uint32_t cs = (word >> (8 * m)) & 255u;
+            if (cs != 0u && cs != 255u) nv += __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0)));
         }
     }
-    uint32_t bt;
-    block_exclusive_scan(nv, &bt);
-    if (threadIdx.x == 0) *out = static_cast<unsigned long long>(voffs[blk]) + bt;
+    const uint32_t t = block_sum(nv, red);
+    if (threadIdx.x == 0) *out = static_cast<unsigned long long>(voffs[blk]) + t;
 }
 
 template <typename T>
@@ -249,6 +309,16 @@ int grow(T** p, long long* cap, long long need) {
     PIFU_CUDA(cudaMalloc(p, static_cast<size_t>(need) * sizeof(T)));
     *cap = need;
     return 0;
+}
+
+Dims make_dims(const McState* st) {
+    Dims d;
+    d.n0 = st->n[0]; d.n1 = st->n[1]; d.n2 = st->n[2];
+    d.c0 = st->layers; d.c1 = st->n[1] - 1; d.c2 = st->n[2] - 1;
+    d.cs2 = (d.c2 + CPT - 1) / CPT * CPT;
+    d.nq = d.cs2 / CPT;
+    d.i0 = st->i0; d.g0 = st->g0; d.ghost = st->ghost;
+    return d;
 }
 
 }  // namespace
@@ -268,13 +338,23 @@ int pifu_mc_count_slab(pifu_ctx* c, const float* field, int n0, int n1, int n2, 
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     McState*& st = ctx_mc(c);
+    int launches = 0;
     if (!st) st = new McState();
+    if (!st->own) {
+        PIFU_CUDA(cudaMalloc(&st->own, 256 * 8));
+        own_table_kernel<<<8, 256, 0, s>>>(st->own);
+        ++launches;
+    }
     st->n[0] = n0; st->n[1] = n1; st->n[2] = n2;
     st->i0 = i_global0; st->g0 = global_n0; st->layers = cell_layers; st->ghost = ghost_layers;
     st->level = level;
     st->field = field;
-    st->cells = static_cast<long long>(cell_layers) * (n1 - 1) * (n2 - 1);
-    const long long blocks = (st->cells + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const Dims d = make_dims(st);
+    st->cells = static_cast<long long>(d.c0) * d.c1 * d.cs2;
+    const long long threads = static_cast<long long>(d.c0) * d.c1 * d.nq;
+    st->blocks = (threads + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (threads > 0x7fffffffLL) { set_error("marching cubes: volume too large for one launch"); return -1; }
+    const long long blocks = st->blocks;
     long long cap = st->cap_cells;
     if (grow(&st->cases, &cap, st->cells)) return -1;
     cap = st->cap_cells;
@@ -285,15 +365,18 @@ int pifu_mc_count_slab(pifu_ctx* c, const float* field, int n0, int n1, int n2, 
     cap = st->cap_blocks;
     if (grow(&st->tsums, &cap, blocks + 1)) return -1;
     st->cap_blocks = cap;
+    if (grow(&st->partials, &st->cap_partials, scan_partials_needed(blocks))) return -1;
     if (!st->totals) PIFU_CUDA(cudaMalloc(&st->totals, 3 * sizeof(unsigned long long)));
-    Dims d{n0, n1, n2, cell_layers, n1 - 1, n2 - 1, i_global0, global_n0, ghost_layers};
-    classify_kernel<<<static_cast<unsigned>(blocks), SCAN_BLOCK, 0, s>>>(field, d, level, st->cases, st->vsums, st->tsums);
-    scan_block_totals_kernel<<<1, SCAN_BLOCK, 0, s>>>(st->vsums, static_cast<int>(blocks), st->totals);
-    scan_block_totals_kernel<<<1, SCAN_BLOCK, 0, s>>>(st->tsums, static_cast<int>(blocks), st->totals + 1);
-    int launches = 3;
+    // largest float <= level: (double)v > level  <=>  v > lf for every float v
+    float lf = static_cast<float>(level);
+    if (static_cast<double>(lf) > level) lf = nextafterf(lf, -INFINITY);
+    const int vec = (n2 % 4 == 0) && (reinterpret_cast<uintptr_t>(field) % 16 == 0) ? 1 : 0;
+    classify_kernel<<<static_cast<unsigned>(blocks), SCAN_BLOCK, 0, s>>>(field, d, lf, vec, st->own, st->cases, st->vsums, st->tsums);
+    device_exclusive_scan(st->vsums, st->tsums, blocks, st->partials, st->totals, s);
+    launches += 4;
     if (ghost_layers) {
         // vertices numbered by the ghost layer = exclusive prefix at its first non-ghost cell
-        ghost_prefix_kernel<<<1, SCAN_BLOCK, 0, s>>>(d, st->cases, st->vsums, st->totals + 2);
+        ghost_prefix_kernel<<<1, SCAN_BLOCK, 0, s>>>(d, st->own, st->cases, st->vsums, st->totals + 2);
         ++launches;
     }
     PIFU_CUDA(cudaGetLastError());
@@ -303,6 +386,7 @@ int pifu_mc_count_slab(pifu_ctx* c, const float* field, int n0, int n1, int n2, 
     PIFU_CUDA(cudaStreamSynchronize(s));
     st->nverts = static_cast<long long>(tot[0]);
     st->nfaces = static_cast<long long>(tot[1]);
+    if (st->nverts > 0x7fffffffLL || st->nfaces > 0x7fffffffLL) { set_error("marching cubes: more than 2^31 vertices"); return -1; }
     *nverts = st->nverts;
     *nfaces = st->nfaces;
     if (ghost_verts) *ghost_verts = ghost_layers ? static_cast<long long>(tot[2]) : 0;
@@ -320,11 +404,10 @@ int pifu_mc_emit(pifu_ctx* c, double* verts, int* faces, float* normals, float* 
     if (st->nverts == 0) return 0;
     if (!verts || (!faces && st->nfaces)) { set_error("null output"); return -1; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const long long blocks = (st->cells + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    Dims d{st->n[0], st->n[1], st->n[2], st->layers, st->n[1] - 1, st->n[2] - 1, st->i0, st->g0, st->ghost};
-    emit_vertices_kernel<<<static_cast<unsigned>(blocks), SCAN_BLOCK, 0, s>>>(st->field, d, st->level, st->cases, st->vsums,
-                                                                             st->vbase, verts, normals, values);
-    emit_faces_kernel<<<static_cast<unsigned>(blocks), SCAN_BLOCK, 0, s>>>(d, st->cases, st->vbase, st->tsums, faces);
+    const Dims d = make_dims(st);
+    emit_vertices_kernel<<<static_cast<unsigned>(st->blocks), SCAN_BLOCK, 0, s>>>(st->field, d, st->level, st->own, st->cases,
+                                                                                 st->vsums, st->vbase, verts, normals, values);
+    emit_faces_kernel<<<static_cast<unsigned>(st->blocks), SCAN_BLOCK, 0, s>>>(d, st->cases, st->vbase, st->tsums, faces);
     PIFU_CUDA(cudaGetLastError());
     ctx_count_launch(c, 2);
     return 0;

@@ -32,6 +32,8 @@ struct OctreeState {
     double* mid = nullptr;
     long long* ids = nullptr;        // compacted frontier
     uint32_t* block_sums = nullptr;
+    uint32_t* partials = nullptr;    // spine of the device-wide scan
+    long long cap_partials = 0;
     unsigned long long* total_dev = nullptr;
     long long frontier = 0;
     long long cap_cells = 0, cap_ids = 0, cap_blocks = 0, cap_vox = 0;
@@ -42,7 +44,7 @@ struct OctreeState {
 void octree_free(OctreeState* s) {
     if (!s) return;
     cudaFree(s->sdf); cudaFree(s->todo); cudaFree(s->skip); cudaFree(s->mid); cudaFree(s->ids);
-    cudaFree(s->block_sums); cudaFree(s->total_dev); cudaFree(s->vals);
+    cudaFree(s->block_sums); cudaFree(s->partials); cudaFree(s->total_dev); cudaFree(s->vals);
     delete s;
 }
 
@@ -68,35 +70,67 @@ __device__ __forceinline__ long long cand_voxel(long long c, int n1, int n2, int
     return (static_cast<long long>(i) * step * R1 + static_cast<long long>(j) * step) * R2 + static_cast<long long>(k) * step;
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK) frontier_count_kernel(const uint8_t* __restrict__ todo, long long ncand,
-                                                                   int n1, int n2, int step, int R1, int R2,
-                                                                   uint32_t* __restrict__ block_sums) {
-    const long long c = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
-    const bool f = c < ncand && todo[cand_voxel(c, n1, n2, step, R1, R2)];
-    const uint32_t cnt = __syncthreads_count(f);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = cnt;
+constexpr int CAND_PT = 8;        // frontier candidates per thread, consecutive along axis 2
+
+// bit m of the result: candidate c0 + m (same lattice row) is still unprocessed
+__device__ __forceinline__ uint32_t cand_flags(const uint8_t* __restrict__ todo, long long c0, long long ncand, int n1,
+                                               int n2, int step, int R1, int R2, long long* vox0) {
+    if (c0 >= ncand) return 0u;
+    const int k = static_cast<int>(c0 % n2);
+    *vox0 = cand_voxel(c0, n1, n2, step, R1, R2);
+    const uint8_t* p = todo + *vox0;
+    uint32_t bits = 0;
+    if (step == 1 && k + CAND_PT <= n2 && (reinterpret_cast<uintptr_t>(p) & 7u) == 0) {
+        const uint2 w = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            bits |= ((w.x >> (8 * m)) & 255u) ? (1u << m) : 0u;
+            bits |= ((w.y >> (8 * m)) & 255u) ? (1u << (m + 4)) : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < CAND_PT; ++m)
+            if (k + m < n2 && p[static_cast<long long>(m) * step]) bits |= 1u << m;
+    }
+    return bits;
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK) frontier_write_kernel(const uint8_t* __restrict__ todo, long long ncand,
-                                                                   int n1, int n2, int step, int R1, int R2,
-                                                                   const uint32_t* __restrict__ block_offs,
-                                                                   long long* __restrict__ ids) {
-    __shared__ uint32_t warp_base[SCAN_BLOCK / 32];
-    const long long c = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long vox = 0;
-    bool f = false;
-    if (c < ncand) { vox = cand_voxel(c, n1, n2, step, R1, R2); f = todo[vox] != 0; }
-    uint32_t wcount;
-    const uint32_t rank = warp_flag_rank(f, lane, &wcount);
-    if (lane == 0) warp_base[warp] = wcount;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int w = 0; w < SCAN_BLOCK / 32; ++w) { const uint32_t t = warp_base[w]; warp_base[w] = acc; acc += t; }
+// n2 is padded to a multiple of CAND_PT per row by the launcher (threads per row = ceil(n2 / CAND_PT)),
+// so a thread's candidates never straddle two lattice rows.
+__global__ void __launch_bounds__(SCAN_BLOCK) frontier_count_kernel(const uint8_t* __restrict__ todo, long long nthreads,
+                                                                   int tpr, long long ncand, int n1, int n2, int step,
+                                                                   int R1, int R2, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t red[SCAN_BLOCK / 32];
+    const long long t = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
+    uint32_t cnt = 0;
+    if (t < nthreads) {
+        const long long row = t / tpr;
+        const long long c0 = row * n2 + (t - row * tpr) * CAND_PT;
+        long long vox0;
+        cnt = __popc(cand_flags(todo, c0, ncand, n1, n2, step, R1, R2, &vox0));
     }
-    __syncthreads();
-    if (f) ids[static_cast<long long>(block_offs[blockIdx.x]) + warp_base[warp] + rank] = vox;
+    const uint32_t total = block_sum(cnt, red);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) frontier_write_kernel(const uint8_t* __restrict__ todo, long long nthreads,
+                                                                   int tpr, long long ncand, int n1, int n2, int step,
+                                                                   int R1, int R2, const uint32_t* __restrict__ block_offs,
+                                                                   long long* __restrict__ ids) {
+    if (block_offs[blockIdx.x + 1] == block_offs[blockIdx.x]) return;
+    const long long t = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
+    uint32_t bits = 0;
+    long long vox0 = 0;
+    if (t < nthreads) {
+        const long long row = t / tpr;
+        const long long c0 = row * n2 + (t - row * tpr) * CAND_PT;
+        bits = cand_flags(todo, c0, ncand, n1, n2, step, R1, R2, &vox0);
+    }
+    uint32_t bt;
+    long long o = static_cast<long long>(block_offs[blockIdx.x]) + block_exclusive_scan(__popc(bits), &bt);
+#pragma unroll
+    for (int m = 0; m < CAND_PT; ++m)
+        if (bits & (1u << m)) ids[o++] = vox0 + static_cast<long long>(m) * step;
 }
 
 __global__ void commit_kernel(const float* __restrict__ vals, const long long* __restrict__ ids, long long n,
@@ -131,37 +165,50 @@ __global__ void cells_kernel(const double* __restrict__ sdf, const uint8_t* __re
     mid[c] = 0.5 * (lo + hi);
 }
 
+// One thread per run of `step` voxels (i, j, ck*step .. ck*step + step - 1): they share their
+// candidate cells, except that the run's first voxel may also lie on the high face of cell ck - 1.
 __global__ void fill_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo, const uint8_t* __restrict__ skip,
                             const double* __restrict__ mid, int step, int c0, int c1, int c2,
-                            int R0, int R1, int R2) {
-    const long long n = static_cast<long long>(R0) * R1 * R2;
-    const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (v >= n) return;
-    const int p[3] = {static_cast<int>(v / (static_cast<long long>(R2) * R1)), static_cast<int>((v / R2) % R1),
-                      static_cast<int>(v % R2)};
-    const int nc[3] = {c0, c1, c2};
-    int hi[3];
-    bool two[3];
+                            int R0, int R1, int R2, int runs) {
+    const long long n = static_cast<long long>(R0) * R1 * runs;
+    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (t >= n) return;
+    const int ck = static_cast<int>(t % runs);
+    const int j = static_cast<int>((t / runs) % R1);
+    const int i = static_cast<int>(t / (static_cast<long long>(runs) * R1));
+    // the (x, y) candidates in descending lexicographic order: high cell first on each axis
+    const int hi_i = i / step, hi_j = j / step;
+    const bool two_i = (i % step) == 0, two_j = (j % step) == 0;
+    long long rowc[4];
+    bool rok[4];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { hi[a] = p[a] / step; two[a] = (p[a] % step) == 0; }
-    // descending lexicographic order over (x, y, z): the high candidate first on every axis
+    for (int m = 0; m < 4; ++m) {
+        const int oi = m >> 1, oj = m & 1;
+        const int ci = hi_i - oi, cj = hi_j - oj;
+        rok[m] = (oi == 0 || two_i) && (oj == 0 || two_j) && ci >= 0 && ci < c0 && cj >= 0 && cj < c1;
+        rowc[m] = (static_cast<long long>(ci) * c1 + cj) * c2;
+    }
+    const bool hi_ok = ck < c2, lo_ok = ck >= 1 && ck - 1 < c2;
+    // voxels 1 .. step-1 of the run: only cell ck along z
+    int hit_rest = -1;
+    if (hi_ok) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int o[3] = {(m >> 2) & 1, (m >> 1) & 1, m & 1};
-        int c[3];
-        bool ok = true;
+        for (int m = 0; m < 4; ++m)
+            if (hit_rest < 0 && rok[m] && skip[rowc[m] + ck]) hit_rest = m;
+    }
+    // voxel 0: for each (x, y) candidate, cell ck then cell ck - 1
+    long long hit0 = -1;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            c[a] = hi[a] - o[a];
-            ok = ok && (o[a] == 0 || two[a]) && c[a] >= 0 && c[a] < nc[a];
-        }
-        if (!ok) continue;
-        const long long ci = (static_cast<long long>(c[0]) * c1 + c[1]) * c2 + c[2];
-        if (skip[ci]) {
-            sdf[v] = mid[ci];
-            todo[v] = 0;
-            return;
-        }
+    for (int m = 0; m < 4; ++m) {
+        if (hit0 >= 0 || !rok[m]) continue;
+        if (hi_ok && skip[rowc[m] + ck]) hit0 = rowc[m] + ck;
+        else if (lo_ok && skip[rowc[m] + ck - 1]) hit0 = rowc[m] + ck - 1;
+    }
+    const long long v0 = (static_cast<long long>(i) * R1 + j) * R2 + static_cast<long long>(ck) * step;
+    if (hit0 >= 0) { sdf[v0] = mid[hit0]; todo[v0] = 0; }
+    if (hit_rest >= 0) {
+        const double val = mid[rowc[hit_rest] + ck];
+        for (int q = 1; q < step && ck * step + q < R2; ++q) { sdf[v0 + q] = val; todo[v0 + q] = 0; }
     }
 }
 
@@ -199,7 +246,7 @@ int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double thres
     capv = st->cap_vox;
     if (grow(&st->todo, &capv, st->voxels)) return -1;
     st->cap_vox = capv;
-    if (!st->total_dev) PIFU_CUDA(cudaMalloc(&st->total_dev, sizeof(unsigned long long)));
+    if (!st->total_dev) PIFU_CUDA(cudaMalloc(&st->total_dev, 2 * sizeof(unsigned long long)));
     init_kernel<<<4096, 256, 0, s>>>(st->sdf, st->todo, R0, R1, R2);
     PIFU_CUDA(cudaGetLastError());
     ctx_count_launch(c, 1);
@@ -215,20 +262,24 @@ int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s) {
     const int step = st->step;
     const int n0 = ceil_div(st->R[0], step), n1 = ceil_div(st->R[1], step), n2 = ceil_div(st->R[2], step);
     const long long ncand = static_cast<long long>(n0) * n1 * n2;
-    const int blocks = ceil_div(ncand, SCAN_BLOCK);
-    if (grow(&st->block_sums, &st->cap_blocks, blocks)) return -1;
-    frontier_count_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(st->todo, ncand, n1, n2, step, st->R[1], st->R[2], st->block_sums);
-    scan_block_totals_kernel<<<1, SCAN_BLOCK, 0, s>>>(st->block_sums, blocks, st->total_dev);
+    const int tpr = ceil_div(n2, CAND_PT);                       // threads per lattice row
+    const long long nthreads = static_cast<long long>(n0) * n1 * tpr;
+    const int blocks = ceil_div(nthreads, SCAN_BLOCK);
+    if (grow(&st->block_sums, &st->cap_blocks, blocks + 1)) return -1;
+    if (grow(&st->partials, &st->cap_partials, scan_partials_needed(blocks))) return -1;
+    frontier_count_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(st->todo, nthreads, tpr, ncand, n1, n2, step, st->R[1], st->R[2],
+                                                       st->block_sums);
+    device_exclusive_scan(st->block_sums, nullptr, blocks, st->partials, st->total_dev, s);
     PIFU_CUDA(cudaGetLastError());
     unsigned long long total = 0;
     PIFU_CUDA(cudaMemcpyAsync(&total, st->total_dev, sizeof(total), cudaMemcpyDeviceToHost, s));
     PIFU_CUDA(cudaStreamSynchronize(s));
     if (grow(&st->ids, &st->cap_ids, static_cast<long long>(total))) return -1;
     if (total)
-        frontier_write_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(st->todo, ncand, n1, n2, step, st->R[1], st->R[2],
+        frontier_write_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(st->todo, nthreads, tpr, ncand, n1, n2, step, st->R[1], st->R[2],
                                                            st->block_sums, st->ids);
     PIFU_CUDA(cudaGetLastError());
-    ctx_count_launch(c, 3);
+    ctx_count_launch(c, 5);
     st->frontier = static_cast<long long>(total);
     *n = st->frontier;
     return 0;
@@ -256,8 +307,9 @@ int octree_commit(pifu_ctx* c, const float* vals, cudaStream_t s) {
             st->cap_cells = cap;
             cells_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(st->sdf, st->todo, step, c0, c1, c2, st->R[1], st->R[2],
                                                           st->threshold, st->skip, st->mid);
-            fill_kernel<<<ceil_div(st->voxels, 256), 256, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, step, c0, c1, c2,
-                                                                 st->R[0], st->R[1], st->R[2]);
+            const int runs = ceil_div(st->R[2], step);
+            fill_kernel<<<ceil_div(static_cast<long long>(st->R[0]) * st->R[1] * runs, 256), 256, 0, s>>>(
+                st->sdf, st->todo, st->skip, st->mid, step, c0, c1, c2, st->R[0], st->R[1], st->R[2], runs);
             ctx_count_launch(c, 2);
         }
     }

@@ -46,24 +46,93 @@ __device__ __forceinline__ uint32_t warp_flag_rank(bool flag, int lane, uint32_t
     return __popc(m & ((1u << lane) - 1u));
 }
 
-// In-place exclusive scan of `n` uint32 block totals by ONE block (n up to a few million);
-// writes the grand total to *total.
-static __global__ void scan_block_totals_kernel(uint32_t* __restrict__ sums, int n, unsigned long long* total) {
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+// Block-wide sum (all threads receive it); smem8 = SCAN_BLOCK / 32 words, one barrier.
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* smem8) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) smem8[threadIdx.x >> 5] = v;
     __syncthreads();
-    for (int base = 0; base < n; base += SCAN_BLOCK) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < n ? sums[i] : 0u;
-        uint32_t bt;
-        const uint32_t ex = block_exclusive_scan(v, &bt);
-        const unsigned long long carry = carry_s;
-        if (i < n) sums[i] = static_cast<uint32_t>(carry + ex);
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_BLOCK / 32; ++w) t += smem8[w];
+    return t;
+}
+
+// ---- device-wide exclusive scan, in place, of one or two uint32 arrays of `n` per-block counts
+// (b may be null): reduce (SCAN_SPT * 256 entries per block) -> spine (one block) -> apply.
+// Entry [n] of each array receives the grand total, so "block i is empty" is a[i + 1] == a[i];
+// totals[0] / totals[1] (device, 64-bit) receive them too.
+constexpr int SCAN_SPT = 8;
+
+inline long long scan_partials_needed(long long n) {
+    return 2 * ((n + SCAN_BLOCK * SCAN_SPT - 1) / (SCAN_BLOCK * SCAN_SPT)) + 2;
+}
+
+static __global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(const uint32_t* __restrict__ a,
+                                                                        const uint32_t* __restrict__ b, long long n,
+                                                                        uint32_t* __restrict__ part) {
+    __shared__ uint32_t red[2][SCAN_BLOCK / 32];
+    const long long base = (blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x) * SCAN_SPT;
+    uint32_t sa = 0, sb = 0;
+#pragma unroll
+    for (int m = 0; m < SCAN_SPT; ++m)
+        if (base + m < n) { sa += a[base + m]; if (b) sb += b[base + m]; }
+    const uint32_t ta = block_sum(sa, red[0]);
+    const uint32_t tb = block_sum(sb, red[1]);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = ta; part[2 * blockIdx.x + 1] = tb; }
+}
+
+static __global__ void __launch_bounds__(SCAN_BLOCK) scan_spine_kernel(uint32_t* __restrict__ part, int nb,
+                                                                       unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long carry[2];
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += SCAN_BLOCK) {
+        const int q = base + threadIdx.x;
+        const uint32_t va = q < nb ? part[2 * q] : 0u, vb = q < nb ? part[2 * q + 1] : 0u;
+        uint32_t ta, tb;
+        const uint32_t ea = block_exclusive_scan(va, &ta);
+        const uint32_t eb = block_exclusive_scan(vb, &tb);
+        const unsigned long long ca = carry[0], cb = carry[1];
+        if (q < nb) { part[2 * q] = static_cast<uint32_t>(ca + ea); part[2 * q + 1] = static_cast<uint32_t>(cb + eb); }
         __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + bt;
+        if (threadIdx.x == 0) { carry[0] = ca + ta; carry[1] = cb + tb; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry_s;
+    if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; }
+}
+
+static __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
+                                                                       long long n, const uint32_t* __restrict__ part,
+                                                                       const unsigned long long* __restrict__ totals) {
+    const long long base = (blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x) * SCAN_SPT;
+    uint32_t va[SCAN_SPT], vb[SCAN_SPT], sa = 0, sb = 0;
+#pragma unroll
+    for (int m = 0; m < SCAN_SPT; ++m) {
+        va[m] = base + m < n ? a[base + m] : 0u;
+        vb[m] = (b && base + m < n) ? b[base + m] : 0u;
+        sa += va[m]; sb += vb[m];
+    }
+    uint32_t t;
+    uint32_t ea = part[2 * blockIdx.x] + block_exclusive_scan(sa, &t);
+    uint32_t eb = part[2 * blockIdx.x + 1] + block_exclusive_scan(sb, &t);
+#pragma unroll
+    for (int m = 0; m < SCAN_SPT; ++m)
+        if (base + m < n) { a[base + m] = ea; ea += va[m]; if (b) { b[base + m] = eb; eb += vb[m]; } }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a[n] = static_cast<uint32_t>(totals[0]);
+        if (b) b[n] = static_cast<uint32_t>(totals[1]);
+    }
+}
+
+// a, b: n + 1 entries each; part: scan_partials_needed(n) entries; totals: 2 x 64-bit.  Three launches.
+static inline void device_exclusive_scan(uint32_t* a, uint32_t* b, long long n, uint32_t* part,
+                                         unsigned long long* totals, cudaStream_t s) {
+    const long long nb = (n + SCAN_BLOCK * SCAN_SPT - 1) / (SCAN_BLOCK * SCAN_SPT);
+    const unsigned grid = static_cast<unsigned>(nb > 0 ? nb : 1);
+    scan_reduce_kernel<<<grid, SCAN_BLOCK, 0, s>>>(a, b, n, part);
+    scan_spine_kernel<<<1, SCAN_BLOCK, 0, s>>>(part, static_cast<int>(grid), totals);
+    scan_apply_kernel<<<grid, SCAN_BLOCK, 0, s>>>(a, b, n, part, totals);
 }
 
 }  // namespace pifu
