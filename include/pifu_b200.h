@@ -41,12 +41,25 @@ void pifu_destroy(pifu_ctx* ctx);
 /* Snapshot one MLP (replaces reading `net.mlp` - MLP.py:13-40 - at query time).
  * filter_channels[n_channels], res_layers[n_res], merge_layer as given to MLP.__init__
  * (<= 0 means len(filter_channels)//2, MLP.py:25).  weights[i] / biases[i] are device
- * pointers to Conv1d i's fp32 weight [Cout][Cin] and bias [Cout].  Only mlp_norm == 'none'
- * stacks are accepted (MLP.py:66-67); hidden widths must be multiples of 128 and the last
- * hidden width 128 or 256. */
+ * pointers to Conv1d i's fp32 weight [Cout][Cin] and bias [Cout].  The stack is un-normalised
+ * (mlp_norm == 'none', MLP.py:66-67) until pifu_set_mlp_norm is called; hidden widths must be
+ * multiples of 128 and the last hidden width 128 or 256. */
 int pifu_set_mlp(pifu_ctx* ctx, int level, int n_channels, const int* filter_channels, int n_res,
                  const int* res_layers, int merge_layer, const float* const* weights,
                  const float* const* biases, void* stream);
+
+/* Normalisation between each hidden Conv1d and its leaky_relu (MLP.py:36-41,66-69), to be set
+ * after pifu_set_mlp (which resets it to none).  groups = 32: GroupNorm(32, C); groups = 0: one
+ * group per channel = BatchNorm1d with batch statistics (a module left in train mode, as
+ * reconstruction.py:288-289 leaves the fine net).  gammas[i] / betas[i]: device fp32 [Cout_i] for the
+ * hidden layers i = 0 .. n_channels - 3.  The statistics run over all points of one call
+ * ([1, C, N] in the reference), so with a normalised MLP every pifu_query / pifu_eval_grid /
+ * pifu_eval_lattice_ids call is one statistics domain (at most 2^22 points, never chunked), the
+ * lattice chain kernel is not used, and pifu_eval_grid_octree (one-call form) is refused: the
+ * caller splits the work the way the reference's num_samples does.  BatchNorm1d in eval mode is a
+ * per-channel affine map and is folded into the weights by the Python layer instead. */
+int pifu_set_mlp_norm(pifu_ctx* ctx, int level, int groups, double eps, const float* const* gammas,
+                      const float* const* betas, void* stream);
 
 /* Snapshot a feature map (replaces reading `net.im_feat_list[-1]`, PIFuNetwNML.py:94-97 /
  * PIFuMRNet.py:114-117): device fp32 NCHW [1][C][H][W]. */

@@ -92,8 +92,14 @@ def mlp_forward(feature, sd, n_layers, res_layers, merge_layer, norm="none", pre
             if norm == "group":
                 y = F.group_norm(y, 32, sd[prefix + "norms.%d.weight" % i],
                                  sd[prefix + "norms.%d.bias" % i], 1e-5)
+            elif norm == "batch_train":        # BatchNorm1d left in train mode (`reconstruction.py:288-289`): batch statistics
+                y = F.batch_norm(y, None, None, sd[prefix + "norms.%d.weight" % i], sd[prefix + "norms.%d.bias" % i],
+                                 True, 0.1, 1e-5)
+            elif norm == "batch_eval":         # running statistics
+                y = F.batch_norm(y, sd[prefix + "norms.%d.running_mean" % i], sd[prefix + "norms.%d.running_var" % i],
+                                 sd[prefix + "norms.%d.weight" % i], sd[prefix + "norms.%d.bias" % i], False, 0.1, 1e-5)
             elif norm == "batch":
-                raise NotImplementedError("batch norm statistics are a training-time state")
+                raise NotImplementedError("say batch_train or batch_eval: the statistics depend on the module's mode")
             y = F.leaky_relu(y)
         if i == merge_layer:
             phi = y.clone()

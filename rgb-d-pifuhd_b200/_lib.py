@@ -27,6 +27,7 @@ SIGNATURES = {
     "pifu_set_options": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
     "pifu_set_gemm_impl": (ctypes.c_int, [VP, ctypes.c_int]),
     "pifu_set_chunk_tiles": (ctypes.c_int, [VP, ctypes.c_int]),
+    "pifu_set_mlp_norm": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_double, VP, VP, VP]),
     "pifu_query": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_longlong, ctypes.c_longlong,
                                   c_float_p, c_float_p, VP, VP, VP, VP]),
     "pifu_eval_grid": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

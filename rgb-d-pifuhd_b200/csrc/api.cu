@@ -54,6 +54,12 @@ struct Level {
     std::vector<SegRef> in_segs;               // the level's input row as K segments
     float* feat = nullptr;                     // NHWC fp32
     int C = 0, H = 0, W = 0;
+    // normalisation between Conv1d and leaky_relu (`MLP.py:36-41`): 0 = none, else the number of
+    // statistics groups per layer is channels / norm_gsize ... stored per layer as `groups`
+    int norm = 0;                              // 0 none, 1 statistics over the points of one call
+    int norm_groups = 0;                       // GroupNorm groups (32); 0 = one group per channel (BatchNorm1d, train mode)
+    double norm_eps = 1e-5;
+    std::vector<float*> gamma, beta;           // per hidden layer, device fp32 [cout]
     bool is_res(int i) const { for (int r : res) if (r == i) return true; return false; }
 };
 
@@ -97,6 +103,9 @@ struct pifu_ctx {
     int alloc_tiles = 0;
     uint8_t* mask = nullptr;
     float* pred_chunk = nullptr;               // scratch for scattered outputs
+    double* norm_stats = nullptr;              // [2 * max groups] sum / sum of squares of one normalised layer
+    float* norm_x = nullptr;                   // pre-norm activations of one layer, fp32 [points][channels]
+    long long norm_x_floats = 0;
     long long launches = 0;
     // per-launch CUDA-event timing of the layer kernel (bench roofline), off by default
     bool profile = false;
@@ -121,6 +130,8 @@ void free_workspace(pifu_ctx* c) {
     for (auto& b : c->bufs) if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; }
     if (c->mask) { cudaFree(c->mask); c->mask = nullptr; }
     if (c->pred_chunk) { cudaFree(c->pred_chunk); c->pred_chunk = nullptr; }
+    if (c->norm_stats) { cudaFree(c->norm_stats); c->norm_stats = nullptr; }
+    if (c->norm_x) { cudaFree(c->norm_x); c->norm_x = nullptr; c->norm_x_floats = 0; }
     c->alloc_tiles = 0;
 }
 
@@ -136,6 +147,7 @@ int ensure_workspace(pifu_ctx* c) {
         if (!b.ptr) PIFU_CUDA(cudaMalloc(&b.ptr, static_cast<size_t>(c->chunk_tiles) * b.nkb * ABLOCK_BYTES));
     if (!c->mask) PIFU_CUDA(cudaMalloc(&c->mask, static_cast<size_t>(c->chunk_tiles) * TILE_M));
     if (!c->pred_chunk) PIFU_CUDA(cudaMalloc(&c->pred_chunk, static_cast<size_t>(c->chunk_tiles) * TILE_M * sizeof(float)));
+    if (!c->norm_stats) PIFU_CUDA(cudaMalloc(&c->norm_stats, 2 * sizeof(double) * 4096));
     c->alloc_tiles = c->chunk_tiles;
     return 0;
 }
@@ -144,6 +156,10 @@ void free_level(Level& L) {
     for (auto& l : L.hidden) { if (l.w) cudaFree(l.w); if (l.bias) cudaFree(l.bias); }
     L.hidden.clear();
     if (L.head_w) { cudaFree(L.head_w); L.head_w = nullptr; }
+    for (float* g : L.gamma) if (g) cudaFree(g);
+    for (float* b : L.beta) if (b) cudaFree(b);
+    L.gamma.clear(); L.beta.clear();
+    L.norm = 0;
     L.set = false;
 }
 
@@ -202,10 +218,17 @@ int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_ti
         g.m_tiles = m_tiles;
         g.leaky = 1;
         g.n_valid = n_valid;
-        const bool with_head = (i == L.n_layers - 2) && head_out != nullptr;
+        const bool wants_head = (i == L.n_layers - 2) && head_out != nullptr;
+        const bool with_head = wants_head && !L.norm;      // a normalised last hidden layer cannot fuse the Conv1d -> 1
         const bool tap = coarse && (i == L.merge);   // `phi` (MLP.py:70-71)
         const bool feeds_next = (i < L.n_layers - 2);
-        if (feeds_next || tap || !with_head) {
+        if (L.norm) {
+            // pre-norm activations in fp32; leaky_relu and the fp16 operand image follow the normalisation
+            g.leaky = 0;
+            g.out_f32 = c->norm_x;
+            g.f32_ld = l.cout;
+            g.f32_col0 = 0;
+        } else if (feeds_next || tap || !with_head) {
             g.out = c->bufs[l.out_buf].ptr;
             g.out_kb_stride = c->bufs[l.out_buf].nkb;
         }
@@ -222,6 +245,23 @@ int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_ti
         double flops = 2.0 * n_valid * static_cast<double>(l.cin) * l.cout;
         if (with_head) flops += 2.0 * n_valid * (L.dims[L.n_layers - 1] + (L.is_res(L.n_layers - 1) ? L.dims[0] : 0));
         if (run_gemm(c, g, flops, s)) return -1;
+        if (L.norm) {
+            const int groups = L.norm_groups > 0 ? L.norm_groups : l.cout;
+            if (groups > 4096) { set_error("normalisation: too many groups"); return -1; }
+            c->launches += 2;
+            if (launch_group_norm(c->norm_x, c->bufs[l.out_buf].ptr, c->bufs[l.out_buf].nkb, l.cout, groups, m_tiles,
+                                  n_valid, L.gamma[i], L.beta[i], L.norm_eps, c->norm_stats, s)) return -1;
+            if (wants_head) {
+                ASeg segs[MAX_SEGS + 1];
+                int ns = 0;
+                segs[ns].base = c->bufs[l.out_buf].ptr; segs[ns].kb_stride = c->bufs[l.out_buf].nkb;
+                segs[ns].kb_off = 0; segs[ns].nkb = l.cout / KB; ++ns;
+                for (const SegRef& r : L.head_segs) segs[ns++] = make_seg(c, r);
+                c->launches += 1;
+                if (launch_head(segs, ns, L.head_w, L.head_b, mask_bit >= 0 ? c->mask : nullptr, mask_bit >= 0 ? mask_bit : 0,
+                                head_out, m_tiles, n_valid, s)) return -1;
+            }
+        }
     }
     return 0;
 }
@@ -397,6 +437,7 @@ int build_chain_fine(pifu_ctx* c, const float* const* weights, const float* cons
 bool chain_eligible(const pifu_ctx* c, int levels, int R2, const float* calib, const double* calib_inv) {
     const ChainPlan& P = c->cplan;
     // x and y of the projected point must not depend on the lattice index along axis 2
+    if (c->lv[0].norm || c->lv[1].norm) return false;       // statistics couple the points of a call
     return levels == 2 && P.enabled && P.coarse_ok && P.fine_ok && c->gemm_impl == PIFU_GEMM_TCGEN05 &&
            !c->perspective && R2 % TILE_M == 0 && calib[2] == 0.f && calib[6] == 0.f &&
            calib_inv[2] == 0.0 && calib_inv[6] == 0.0;
@@ -502,6 +543,31 @@ int check_ready(pifu_ctx* c, int levels) {
     return ensure_workspace(c);
 }
 
+// With a normalised MLP every entry call is ONE statistics domain, like one reference query() call
+// (`MLP.py:66-69` on [1, C, N]): the call may not be cut into chunks, so the workspace grows to hold it.
+constexpr long long NORM_MAX_POINTS = 1LL << 22;
+bool normalised(const pifu_ctx* c, int levels) { return c->lv[0].norm || (levels == 2 && c->lv[1].norm); }
+int fit_call(pifu_ctx* c, int levels, long long n) {
+    if (!normalised(c, levels)) return 0;
+    if (n > NORM_MAX_POINTS) {
+        set_error("a normalised MLP (mlp_norm group/batch) takes at most %lld points per call, got %lld: the statistics "
+                  "run over the whole call; split it the way the reference's num_samples does", NORM_MAX_POINTS, n);
+        return -1;
+    }
+    const int tiles = static_cast<int>((n + TILE_M - 1) / TILE_M);
+    if (tiles > c->chunk_tiles) { c->chunk_tiles = tiles; if (ensure_workspace(c)) return -1; }
+    int maxc = 0;
+    for (int l = 0; l < levels; ++l)
+        for (const Layer& h : c->lv[l].hidden) maxc = h.cout > maxc ? h.cout : maxc;
+    const long long need = static_cast<long long>(c->chunk_tiles) * TILE_M * maxc;
+    if (need > c->norm_x_floats) {
+        if (c->norm_x) { cudaFree(c->norm_x); c->norm_x = nullptr; c->norm_x_floats = 0; }
+        PIFU_CUDA(cudaMalloc(&c->norm_x, static_cast<size_t>(need) * sizeof(float)));
+        c->norm_x_floats = need;
+    }
+    return 0;
+}
+
 void lattice_source(PointSource& src, int R0, int R1, int R2, const double* calib_inv) {
     memset(&src, 0, sizeof(src));
     src.mode = 1;
@@ -532,6 +598,7 @@ int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* i
     return 0;
 }
 int ctx_check_ready(pifu_ctx* c, int levels) { return check_ready(c, levels); }
+bool ctx_normalised(pifu_ctx* c, int levels) { return normalised(c, levels); }
 int ctx_num_sms(pifu_ctx* c) { return c->num_sms; }
 void ctx_count_launch(pifu_ctx* c, int n) { c->launches += n; }
 OctreeState*& ctx_octree(pifu_ctx* c) { return c->octree; }
@@ -798,12 +865,40 @@ int pifu_set_mlp(pifu_ctx* c, int level, int n_channels, const int* ch, int n_re
     return 0;
 }
 
+int pifu_set_mlp_norm(pifu_ctx* c, int level, int groups, double eps, const float* const* gammas,
+                      const float* const* betas, void* stream) {
+    if (!c || level < 0 || level > 1 || groups < 0 || !gammas || !betas) { set_error("bad arguments to pifu_set_mlp_norm"); return -1; }
+    Level& L = c->lv[level];
+    if (!L.set) { set_error("pifu_set_mlp_norm: set the MLP first"); return -1; }
+    PIFU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (float* g : L.gamma) if (g) cudaFree(g);
+    for (float* b : L.beta) if (b) cudaFree(b);
+    L.gamma.assign(L.n_layers - 1, nullptr);
+    L.beta.assign(L.n_layers - 1, nullptr);
+    for (int i = 0; i < L.n_layers - 1; ++i) {
+        const int cout = L.hidden[i].cout;
+        if (groups > 0 && cout % groups) { set_error("layer %d: %d channels not divisible into %d groups", i, cout, groups); return -1; }
+        if (!gammas[i] || !betas[i]) { set_error("pifu_set_mlp_norm: null affine parameters for layer %d", i); return -1; }
+        PIFU_CUDA(cudaMalloc(&L.gamma[i], cout * sizeof(float)));
+        PIFU_CUDA(cudaMalloc(&L.beta[i], cout * sizeof(float)));
+        PIFU_CUDA(cudaMemcpyAsync(L.gamma[i], gammas[i], cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        PIFU_CUDA(cudaMemcpyAsync(L.beta[i], betas[i], cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    PIFU_CUDA(cudaStreamSynchronize(s));
+    L.norm = 1;
+    L.norm_groups = groups;
+    L.norm_eps = eps;
+    return 0;
+}
+
 int pifu_query(pifu_ctx* c, int levels, int flags, const float* points, long long pstride, long long n,
                const float* calib_local, const float* calib_global, float* out_pred, float* out_pred_low,
                float* out_phi, void* stream) {
     if (check_ready(c, levels)) return -1;
     if (!points || !calib_local || !calib_global) { set_error("null points/calib"); return -1; }
     PIFU_CUDA(cudaSetDevice(c->device));
+    if (fit_call(c, levels, n)) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PointSource src;
     memset(&src, 0, sizeof(src));
@@ -830,6 +925,7 @@ int pifu_eval_grid(pifu_ctx* c, int levels, int R0, int R1, int R2, long long id
     if (!calib || !calib_inv || !out || id_begin < 0 || id_end < id_begin ||
         id_end > static_cast<long long>(R0) * R1 * R2) { set_error("bad arguments to pifu_eval_grid"); return -1; }
     PIFU_CUDA(cudaSetDevice(c->device));
+    if (fit_call(c, levels, id_end - id_begin)) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // whole 128-point tiles of lattice columns go through the chain kernel; ragged ends (and
     // every configuration chain_eligible() rejects) through the per-layer kernels
@@ -861,6 +957,7 @@ int pifu_eval_lattice_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const
     if (check_ready(c, levels)) return -1;
     if (!calib || !calib_inv || !out || !ids) { set_error("bad arguments to pifu_eval_lattice_ids"); return -1; }
     PIFU_CUDA(cudaSetDevice(c->device));
+    if (fit_call(c, levels, n)) return -1;
     return pifu::eval_ids(c, levels, R0, R1, R2, ids, n, calib, calib_inv, out, static_cast<cudaStream_t>(stream));
 }
 

@@ -14,10 +14,18 @@ int launch_nchw_to_nhwc(const float* in, float* out, int C, int HW, cudaStream_t
 int launch_unblock(const uint8_t* buf, int kb_stride, int kb_off, int C, int n, float* dst, long long ld,
                    cudaStream_t s);
 
+// norm.cu: normalised stacks (GroupNorm / batch statistics) and the un-fused last layer
+struct ASeg;
+int launch_group_norm(const float* x, uint8_t* buf, int nkb, int channels, int groups, int m_tiles, int n_valid,
+                      const float* gamma, const float* beta, double eps, double* stats, cudaStream_t s);
+int launch_head(const ASeg* segs, int nseg, const float* w, float b, const uint8_t* mask, int mask_bit, float* out,
+                int m_tiles, int n_valid, cudaStream_t s);
+
 // api.cu services used by the octree driver
 int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
              const float* calib, const double* calib_inv, float* out, cudaStream_t s);
 int ctx_check_ready(pifu_ctx* c, int levels);      // MLPs + feature maps set, workspace allocated
+bool ctx_normalised(pifu_ctx* c, int levels);      // a normalised MLP: every entry call is one statistics domain
 int ctx_num_sms(pifu_ctx* c);
 void ctx_count_launch(pifu_ctx* c, int n);
 

@@ -372,6 +372,11 @@ int pifu_eval_grid_octree(pifu_ctx* c, int levels, int R0, int R1, int R2, int i
                           long long* evaluated_per_level, int max_levels, void* stream) {
     if (!c || !calib || !calib_inv) { set_error("bad arguments to pifu_eval_grid_octree"); return -1; }
     if (ctx_check_ready(c, levels)) return -1;
+    if (ctx_normalised(c, levels)) {
+        set_error("pifu_eval_grid_octree: with a normalised MLP the statistics follow the caller's chunks "
+                  "(num_samples); drive the stepwise form and evaluate each chunk with pifu_eval_lattice_ids");
+        return -1;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (octree_begin(c, R0, R1, R2, init_resolution, threshold, s)) return -1;
     int lvl = 0;

@@ -47,6 +47,7 @@ class Engine:
         self._mlp_key = [None, None]
         self._feat_key = [None, None]
         self._opt_key = None
+        self._normalised = [False, False]
         self._keep = {}
 
     def __del__(self):
@@ -63,25 +64,38 @@ class Engine:
         return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
 
     def sync_mlp(self, level, mlp, owner_id):
-        """mlp: object with .filters (Conv1d list), .res_layers, .merge_layer, .norm, .filter_channels"""
-        if mlp.norm in ("batch", "group"):
-            raise NotImplementedError(
-                "mlp_norm=%r couples the points of one query() call through its statistics "
-                "(MLP.py:38-41); the fused path supports mlp_norm='none' only" % (mlp.norm,))
+        """mlp: object with .filters (Conv1d list), .norms, .res_layers, .merge_layer, .norm, .filter_channels.
+
+        mlp_norm (`MLP.py:36-41`): 'group' -> GroupNorm(32) statistics over the points of each call;
+        'batch' in train mode -> batch statistics per channel; 'batch' in eval mode is a per-channel
+        affine map of the running statistics and is folded into the Conv1d weights here."""
+        norm = mlp.norm if mlp.norm in ("batch", "group") else "none"
+        norms = list(mlp.norms) if norm != "none" else []
+        fold = norm == "batch" and not mlp.training
         params = []
         for f in mlp.filters:
             params += [f.weight, f.bias]
-        key = (owner_id, self._tensor_key(params))
+        for nm in norms:
+            params += [nm.weight, nm.bias]
+            if fold:
+                params += [nm.running_mean, nm.running_var]
+        key = (owner_id, norm, fold, self._tensor_key(params))
         if self._mlp_key[level] == key:
             return
         if level == 0:
             self._mlp_key[1] = None
         ws, bs = [], []
-        for f in mlp.filters:
-            w = f.weight.detach().to(self.device, torch.float32).reshape(f.weight.shape[0], -1).contiguous()
-            b = f.bias.detach().to(self.device, torch.float32).contiguous()
-            ws.append(w)
-            bs.append(b)
+        for i, f in enumerate(mlp.filters):
+            w = f.weight.detach().to(self.device, torch.float32).reshape(f.weight.shape[0], -1)
+            b = f.bias.detach().to(self.device, torch.float32)
+            if fold and i < len(norms):
+                nm = norms[i]
+                scale = (nm.weight.detach().double() / torch.sqrt(nm.running_var.detach().double() + nm.eps)).to(self.device)
+                shift = nm.bias.detach().double().to(self.device) - nm.running_mean.detach().double().to(self.device) * scale
+                w = (w.double() * scale[:, None]).float()
+                b = (b.double() * scale + shift).float()
+            ws.append(w.contiguous())
+            bs.append(b.contiguous())
         ch = list(mlp.filter_channels)
         res = list(mlp.res_layers)
         n = len(ws)
@@ -90,8 +104,21 @@ class Engine:
         _lib.check(self.lib.pifu_set_mlp(self.h, level, len(ch), (ctypes.c_int * len(ch))(*ch), len(res),
                                          (ctypes.c_int * max(len(res), 1))(*(res or [0])),
                                          int(mlp.merge_layer), wp, bp, _stream(self.device_index)))
+        if norm != "none" and not fold:
+            gs = [nm.weight.detach().to(self.device, torch.float32).contiguous() for nm in norms]
+            be = [nm.bias.detach().to(self.device, torch.float32).contiguous() for nm in norms]
+            gp = (ctypes.c_void_p * len(gs))(*[t.data_ptr() for t in gs])
+            bp2 = (ctypes.c_void_p * len(be))(*[t.data_ptr() for t in be])
+            groups = norms[0].num_groups if norm == "group" else 0
+            _lib.check(self.lib.pifu_set_mlp_norm(self.h, level, int(groups), float(norms[0].eps), gp, bp2,
+                                                  _stream(self.device_index)))
         torch.cuda.current_stream(self.device_index).synchronize()
         self._mlp_key[level] = key
+        self._normalised[level] = norm != "none" and not fold
+
+    def normalised(self, levels):
+        """True when a level's MLP carries call-wide statistics (every call is one statistics domain)."""
+        return any(self._normalised[:levels])
 
     def sync_features(self, level, feat):
         """feat: [1, C, H, W] tensor (any device/dtype)."""

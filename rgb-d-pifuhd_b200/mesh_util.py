@@ -123,12 +123,45 @@ def _prepare_native(net, device):
     return eng, 1
 
 
+def _eval_field_normalised(eng, levels, resolution, calib, use_octree, init_resolution, threshold, num_samples, stats):
+    """mlp_norm 'group' / 'batch' (train mode): the statistics of every normalised layer run over the
+    points of one query() call, so the field depends on how the lattice is cut into calls
+    (SURVEY §7.3-1).  Reproduce the reference's cuts: consecutive runs of `num_samples` points, in
+    lattice order for the dense grid (`mesh_util.py:98-120`) and in frontier order per octree level
+    (`:142-149`); each run is one statistics domain on the device."""
+    num_samples = int(num_samples)
+    total = resolution ** 3
+    if not use_octree:
+        out = torch.empty(total, device=eng.device, dtype=torch.float32)
+        for b in range(0, total, num_samples):
+            e = min(b + num_samples, total)
+            eng.eval_grid(levels, resolution, calib, id_begin=b, id_end=e, out=out[b:e])
+        return out.view(resolution, resolution, resolution)
+    eng.octree_begin(resolution, init_resolution, threshold)
+    while True:
+        step, ids = eng.octree_frontier()
+        if step == 0:
+            break
+        if stats is not None:
+            stats.append(ids.numel())
+        vals = [eng.eval_lattice_ids(levels, resolution, ids[b:b + num_samples], calib)
+                for b in range(0, ids.numel(), num_samples)]
+        eng.octree_commit(torch.cat(vals) if vals else torch.empty(0, device=eng.device))
+    return eng.octree_export(want64=False, want32=True)[1]
+
+
 def eval_field_device(net, cuda, calib_tensor, resolution, use_octree, init_resolution=64, threshold=0.05,
-                      group=None, stats=None):
+                      group=None, stats=None, num_samples=10000):
     """Occupancy lattice as a device float32 tensor [R, R, R] (native nets only)."""
     from . import dist as pdist
     eng, levels = _prepare_native(net, cuda)
     calib = calib_tensor[0]
+    if eng.normalised(levels):
+        if group is not None or pdist.world_size() > 1:
+            raise NotImplementedError("a normalised MLP (mlp_norm group/batch) couples the points of a call; "
+                                      "sharding would change the statistics - run one replica per GPU instead")
+        return _eval_field_normalised(eng, levels, resolution, calib, use_octree, init_resolution, threshold,
+                                      num_samples, stats)
     if group is not None or pdist.world_size() > 1:
         if use_octree:
             return pdist.sharded_eval_grid_octree(eng, levels, resolution, calib, init_resolution, threshold,
@@ -149,7 +182,9 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
     values float32) or -1 when no iso-surface exists.  As in the reference, `b_min`/`b_max`/
     `transform` are accepted and ignored (`:59`), the lattice is [-1, 1)^3 pre-multiplied by
     inv(calib), and faces are flipped when the index->world transform mirrors (`:91-92`).
-    `num_samples` only chunks host callbacks; the fused path is chunk-invariant."""
+    `num_samples` chunks host callbacks and, for a normalised MLP (mlp_norm 'group'/'batch'), cuts the
+    lattice into the same statistics domains as the reference; with mlp_norm 'none' the fused path is
+    chunk-invariant."""
     device = torch.device(cuda)
     mat = np.eye(4)
     mat[0, 0] = mat[1, 1] = mat[2, 2] = 2.0 / resolution
@@ -158,10 +193,14 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
     from . import dist as pdist
     sharded = _is_native(net) and (group is not None or pdist.world_size() > 1)
     field = None
+    if sharded and _prepare_native(net, device)[0].normalised(2):
+        raise NotImplementedError("a normalised MLP (mlp_norm group/batch) couples the points of a call; "
+                                  "sharding would change the statistics - run one replica per GPU instead")
     if sharded:
         pass                             # field and iso-surface are extracted slab by slab below
     elif _is_native(net):
-        field = eval_field_device(net, device, calib_tensor, resolution, use_octree, group=group)
+        field = eval_field_device(net, device, calib_tensor, resolution, use_octree, group=group,
+                                  num_samples=num_samples)
         eng = get_engine(device)
     else:
         coords, _ = create_grid(resolution, resolution, resolution)
