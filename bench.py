@@ -39,6 +39,18 @@ def load_peaks():
     return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu
+    capture of the same workload shape (profiles/ncu_traffic.json); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p)).get(kernel)
+        return None if not d else {"bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"],
+                                   "queries_per_launch": d["queries_per_launch"], "source": d["source"]}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def build_problem():
     """Seeded random-init two-level net + band-limited feature maps (pifu_b200.synthetic)."""
     from pifu_b200 import synthetic as syn
@@ -362,7 +374,7 @@ def main():
             achieved = chain_flops / (chain_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "chain_kernel (tcgen05 CTA-pair MLP chain, activations on-chip)",
                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                        "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_c,
+                        "traffic": ncu_traffic("chain_kernel"), "peak_source": peaks["source"], "launches_per_step": n_c,
                         "avg_launch_us": chain_ms * 1e3 / n_c, "share_of_step": chain_ms / ms_per_step,
                         "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
                         "executed_flop_per_query": 2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128),

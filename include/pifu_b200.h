@@ -118,6 +118,9 @@ int pifu_octree_begin(pifu_ctx* ctx, int R0, int R1, int R2, int init_resolution
                       void* stream);
 int pifu_octree_frontier(pifu_ctx* ctx, long long* n, const long long** ids_device, int* step, void* stream);
 int pifu_octree_commit(pifu_ctx* ctx, const float* values_device, void* stream);
+/* Same with float64 values: the generic eval_grid_octree(coords, eval_func) form stores whatever
+ * the caller's eval_func returns into the float64 field (mesh_util.py:148-149). */
+int pifu_octree_commit64(pifu_ctx* ctx, const double* values_device, void* stream);
 int pifu_octree_export(pifu_ctx* ctx, double* sdf64, float* sdf32, void* stream);
 
 /* Marching cubes on a device float32 volume [n0][n1][n2] at `level` (strict v > level is

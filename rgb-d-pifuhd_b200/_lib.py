@@ -39,6 +39,7 @@ SIGNATURES = {
     "pifu_octree_begin": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, VP]),
     "pifu_octree_frontier": (ctypes.c_int, [VP, c_ll_p, ctypes.POINTER(VP), c_int_p, VP]),
     "pifu_octree_commit": (ctypes.c_int, [VP, VP, VP]),
+    "pifu_octree_commit64": (ctypes.c_int, [VP, VP, VP]),
     "pifu_octree_export": (ctypes.c_int, [VP, VP, VP, VP]),
     "pifu_mc_count": (ctypes.c_int, [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                      c_ll_p, c_ll_p, VP]),

@@ -32,7 +32,7 @@ void ctx_count_launch(pifu_ctx* c, int n);
 int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s);
 int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s);
 const long long* octree_ids(pifu_ctx* c);
-int octree_commit(pifu_ctx* c, const float* vals, cudaStream_t s);
+int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStream_t s);
 int octree_export(pifu_ctx* c, double* sdf64, float* sdf32, cudaStream_t s);
 int octree_vals(pifu_ctx* c, long long n, float** out);
 

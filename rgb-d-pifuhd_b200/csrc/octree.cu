@@ -133,12 +133,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK) frontier_write_kernel(const uint8_
         if (bits & (1u << m)) ids[o++] = vox0 + static_cast<long long>(m) * step;
 }
 
-__global__ void commit_kernel(const float* __restrict__ vals, const long long* __restrict__ ids, long long n,
+template <typename T>
+__global__ void commit_kernel(const T* __restrict__ vals, const long long* __restrict__ ids, long long n,
                               double* __restrict__ sdf, uint8_t* __restrict__ todo) {
     const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (p >= n) return;
     const long long v = ids[p];
-    sdf[v] = static_cast<double>(vals[p]);       // float32 widened into the float64 field (`:148`)
+    sdf[v] = static_cast<double>(vals[p]);       // the callable's values stored into the float64 field (`:148`)
     todo[v] = 0;
 }
 
@@ -288,11 +289,15 @@ int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s) {
 const long long* octree_ids(pifu_ctx* c) { return ctx_octree(c) ? ctx_octree(c)->ids : nullptr; }
 
 // Scatter the frontier's occupancies, then (step > 1) skip test + fill, then halve the stride.
-int octree_commit(pifu_ctx* c, const float* vals, cudaStream_t s) {
+int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStream_t s) {
     OctreeState* st = ctx_octree(c);
     if (!st || st->step <= 0) { set_error("octree: nothing to commit"); return -1; }
     if (st->frontier) {
-        commit_kernel<<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals, st->ids, st->frontier, st->sdf, st->todo);
+        if (!vals && !vals64) { set_error("octree: null values for a frontier of %lld points", st->frontier); return -1; }
+        if (vals64)
+            commit_kernel<double><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals64, st->ids, st->frontier, st->sdf, st->todo);
+        else
+            commit_kernel<float><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals, st->ids, st->frontier, st->sdf, st->todo);
         ctx_count_launch(c, 1);
     }
     const int step = st->step;
@@ -359,7 +364,12 @@ int pifu_octree_frontier(pifu_ctx* c, long long* n, const long long** ids, int* 
 
 int pifu_octree_commit(pifu_ctx* c, const float* vals, void* stream) {
     if (!c) { set_error("null context"); return -1; }
-    return octree_commit(c, vals, static_cast<cudaStream_t>(stream));
+    return octree_commit(c, vals, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int pifu_octree_commit64(pifu_ctx* c, const double* vals, void* stream) {
+    if (!c) { set_error("null context"); return -1; }
+    return octree_commit(c, nullptr, vals, static_cast<cudaStream_t>(stream));
 }
 
 int pifu_octree_export(pifu_ctx* c, double* sdf64, float* sdf32, void* stream) {
@@ -391,7 +401,7 @@ int pifu_eval_grid_octree(pifu_ctx* c, int levels, int R0, int R1, int R2, int i
             if (octree_vals(c, n, &vals)) return -1;
             if (eval_ids(c, levels, R0, R1, R2, octree_ids(c), n, calib, calib_inv, vals, s)) return -1;
         }
-        if (octree_commit(c, vals, s)) return -1;
+        if (octree_commit(c, vals, nullptr, s)) return -1;
         ++lvl;
     }
     for (; evaluated_per_level && lvl < max_levels; ++lvl) evaluated_per_level[lvl] = -1;

@@ -267,9 +267,15 @@ class Engine:
         return step.value, ids
 
     def octree_commit(self, vals):
-        vals = vals.to(self.device, torch.float32).contiguous()
-        _lib.check(self.lib.pifu_octree_commit(self.h, ctypes.c_void_p(vals.data_ptr()) if vals.numel() else None,
-                                               _stream(self.device_index)))
+        """Values of the whole frontier, in frontier order; float64 tensors are stored as they are
+        (generic callables), anything else as float32 (what `get_preds` returns)."""
+        if vals.dtype == torch.float64:
+            vals = vals.to(self.device).contiguous()
+            fn = self.lib.pifu_octree_commit64
+        else:
+            vals = vals.to(self.device, torch.float32).contiguous()
+            fn = self.lib.pifu_octree_commit
+        _lib.check(fn(self.h, ctypes.c_void_p(vals.data_ptr()) if vals.numel() else None, _stream(self.device_index)))
 
     def octree_export(self, want64=True, want32=False):
         R0, R1, R2 = self._oct_res

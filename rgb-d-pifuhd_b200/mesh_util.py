@@ -4,9 +4,9 @@
 When `net` is one of this package's nets the whole path runs on the device: the lattice is
 generated in-kernel (no `create_grid` arrays), occupancy comes from the fused query kernels
 (dense or device octree), the iso-surface from the CUDA marching cubes, and only the mesh
-crosses back to the host.  The callback forms (`eval_grid`, `eval_grid_octree`, `batch_eval`
-with an arbitrary `eval_func`) keep reference semantics on the host because the callable *is*
-the computation there.
+crosses back to the host.  The callback forms (`eval_grid`, `batch_eval` with an arbitrary
+`eval_func`) only drive the caller's callable; `eval_grid_octree(coords, eval_func)` runs its
+bookkeeping on the device too.
 """
 import numpy as np
 import torch
@@ -45,58 +45,30 @@ def eval_grid(coords, eval_func, num_samples=512 * 512 * 512):
     return batch_eval(coords.reshape(3, -1), eval_func, num_samples=num_samples).reshape(shape)
 
 
-def _fill_from_skip_cells(sdf, todo, skip, mid, step):
-    """Vectorised form of the reference's per-cell fill loop (`mesh_util.py:181-184`): a voxel
-    takes the value of the lexicographically largest skip cell covering it (that cell wrote
-    last); cell p//step covers p, and cell p//step - 1 only when p % step == 0."""
-    found = np.zeros(sdf.shape, dtype=bool)
-    value = np.zeros(sdf.shape)
-    axes = [np.arange(r) for r in sdf.shape]
-    for o in np.ndindex(2, 2, 2):                  # (0,0,0) first: the high cell on every axis
-        cell, ok = [], []
-        for ax in range(3):
-            c = axes[ax] // step - o[ax]
-            good = (c >= 0) & (c < skip.shape[ax])
-            if o[ax]:
-                good &= axes[ax] % step == 0
-            cell.append(np.clip(c, 0, max(skip.shape[ax] - 1, 0)))
-            ok.append(good)
-        hit = skip[np.ix_(*cell)] & ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :] & ~found
-        value[hit] = mid[np.ix_(*cell)][hit]
-        found |= hit
-    sdf[found] = value[found]
-    todo[found] = False
-
-
-def eval_grid_octree(coords, eval_func, init_resolution=64, threshold=0.05, num_samples=512 * 512 * 512):
-    """`mesh_util.py:124-187` for an arbitrary `eval_func` (host bookkeeping, same field
-    bit for bit as the reference loop).  The device version used by `reconstruction()` is
-    `Engine.eval_grid_octree`."""
-    res = coords.shape[1:4]
-    sdf = np.zeros(res)
-    todo = np.zeros(res, dtype=bool)
-    todo[:-1, :-1, :-1] = True
-    on_lattice = np.zeros(res, dtype=bool)
-    step = res[0] // init_resolution
-    while step > 0:
-        on_lattice[::step, ::step, ::step] = True
-        test = on_lattice & todo
-        sdf[test] = batch_eval(coords[:, test], eval_func, num_samples=num_samples)
-        todo[test] = False
-        if step <= 1:
+def eval_grid_octree(coords, eval_func, init_resolution=64, threshold=0.05, num_samples=512 * 512 * 512, device=None):
+    """`mesh_util.py:124-187` for an arbitrary `eval_func` (points float64 [3, n] -> values [n]).
+    The callable is the caller's computation and runs where it runs; the octree itself - frontier
+    compaction in the C order of the reference's boolean mask, the float64 field, the skip test on
+    the 8 cell corners and the inclusive fill - is the same device code `reconstruction()` uses
+    (octree.cu), so the returned float64 field equals the reference loop's bit for bit.  `device`
+    defaults to the current CUDA device; there is no host implementation."""
+    res = tuple(int(r) for r in coords.shape[1:4])
+    if device is None:
+        if not torch.cuda.is_available():
+            from ._lib import PifuError
+            raise PifuError("eval_grid_octree needs a CUDA device: the octree bookkeeping runs in libpifu_b200.so "
+                            "(there is no CPU path)")
+        device = torch.device("cuda", torch.cuda.current_device())
+    eng = get_engine(device)
+    flat = coords.reshape(3, -1)
+    eng.octree_begin(res, init_resolution, threshold)
+    while True:
+        step, ids = eng.octree_frontier()
+        if step == 0:
             break
-        v = sdf[::step, ::step, ::step]
-        if min(v.shape) >= 2:
-            n = [s - 1 for s in v.shape]
-            corners = [v[a:a + n[0], b:b + n[1], c:c + n[2]] for a in (0, 1) for b in (0, 1) for c in (0, 1)]
-            lo = np.minimum.reduce(corners)
-            hi = np.maximum.reduce(corners)
-            h = step // 2
-            centre = todo[h::step, h::step, h::step][:n[0], :n[1], :n[2]]
-            skip = ((hi - lo) < threshold) & centre
-            _fill_from_skip_cells(sdf, todo, skip, 0.5 * (lo + hi), step)
-        step //= 2
-    return sdf.reshape(res)
+        vals = batch_eval(flat[:, ids.cpu().numpy()], eval_func, num_samples=num_samples)
+        eng.octree_commit(torch.from_numpy(vals))
+    return eng.octree_export(want64=True, want32=False)[0].cpu().numpy()
 
 
 # ----------------------------------------------------------------------------- driver
@@ -213,7 +185,10 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
             net.query(samples, calib_tensor)
             return net.get_preds()[0][0].detach().cpu().numpy()
 
-        sdf = (eval_grid_octree if use_octree else eval_grid)(coords, eval_func, num_samples=num_samples)
+        if use_octree:
+            sdf = eval_grid_octree(coords, eval_func, num_samples=num_samples, device=device)
+        else:
+            sdf = eval_grid(coords, eval_func, num_samples=num_samples)
         eng = get_engine(device)
         field = torch.from_numpy(sdf.astype(np.float32)).to(device)
     try:

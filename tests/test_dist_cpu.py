@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helpers import ROOT
+from helpers import ROOT, orc
 
 from pifu_b200 import dist as pdist
 
@@ -35,12 +35,12 @@ class FakeEngine:
         return self.fn(ids)
 
     def octree_begin(self, res, init_resolution, threshold):
-        from pifu_b200 import mesh_util
+        from oracle import pifu_oracle
         self.sdf = np.zeros((res,) * 3)
         self.todo = np.zeros((res,) * 3, bool)
         self.todo[:-1, :-1, :-1] = True
         self.lat = np.zeros((res,) * 3, bool)
-        self.step, self.thr, self.mu = res // init_resolution, threshold, mesh_util
+        self.step, self.thr, self.mu = res // init_resolution, threshold, pifu_oracle
 
     def octree_frontier(self):
         if self.step <= 0:
@@ -59,7 +59,7 @@ class FakeEngine:
             cs = [v[a:a + n[0], b:b + n[1], c:c + n[2]] for a in (0, 1) for b in (0, 1) for c in (0, 1)]
             lo, hi = np.minimum.reduce(cs), np.maximum.reduce(cs)
             centre = self.todo[s // 2::s, s // 2::s, s // 2::s][:n[0], :n[1], :n[2]]
-            self.mu._fill_from_skip_cells(self.sdf, self.todo, ((hi - lo) < self.thr) & centre, 0.5 * (lo + hi), s)
+            self.mu.octree_fill_gather(self.sdf, self.todo, ((hi - lo) < self.thr) & centre, 0.5 * (lo + hi), s)
         self.step = 0 if s <= 1 else s // 2
 
     def octree_export(self, want64=False, want32=True):
@@ -109,8 +109,8 @@ def test_two_rank_sharding_matches_single(tmp_path):
         ids = (p[0] * res + p[1]) * res + p[2]
         return fn(torch.from_numpy(ids.astype(np.int64))).numpy()
     calls = []
-    ref_oct = mesh_util.eval_grid_octree(coords, lambda p: (calls.append(p.shape[1]), eval_func(p))[1],
-                                         init_resolution=8, num_samples=10 ** 9)
+    ref_oct = orc.eval_grid_octree(coords, lambda p: (calls.append(p.shape[1]), eval_func(p))[1],
+                                   init_resolution=8, num_samples=10 ** 9)
     assert np.array_equal(got["octree"].numpy(), ref_oct.astype(np.float32))
     assert got["stats"] == calls
 
@@ -161,7 +161,7 @@ def test_sharded_mesh_equals_whole_volume(tmp_path, world, res):
     fn = _field(res)
     dense = fn(torch.arange(res ** 3)).view(res, res, res).numpy()
     coords = np.indices((res,) * 3).astype(np.float64)
-    octo = mesh_util.eval_grid_octree(
+    octo = orc.eval_grid_octree(
         coords, lambda p: fn(torch.from_numpy(((p[0] * res + p[1]) * res + p[2]).astype(np.int64))).numpy(),
         init_resolution=8, num_samples=10 ** 9).astype(np.float32)
     for mode, vol in (("dense", dense), ("octree", octo)):

@@ -69,6 +69,31 @@ def test_device_octree_bit_exact_vs_reference_loop(name, res, init):
     assert np.array_equal(sdf32.cpu().numpy(), f.astype(np.float32))
 
 
+@pytest.mark.parametrize("name", ["ellipsoid", "ripple"])
+@pytest.mark.parametrize("res,init", [(64, 8), (96, 12), (128, 32), (32, 64)])
+def test_callback_octree_bit_exact_vs_reference(name, res, init):
+    """mesh_util.eval_grid_octree(coords, eval_func) with an arbitrary host callable: device
+    bookkeeping, float64 values committed as they are -> the reference's field bit for bit
+    (sha256 recorded from the reference's own loop) and the same chunked calls."""
+    from pifu_b200 import mesh_util
+    coords, _ = mesh_util.create_grid(res, res, res)
+    calls = []
+    f = mesh_util.eval_grid_octree(coords, lambda p: (calls.append(p.shape[1]), ANALYTIC[name](p))[1],
+                                   init_resolution=init, num_samples=50000)
+    assert f.dtype == np.float64 and f.shape == (res, res, res)
+    if init > res:                      # `mesh_util.py:138`: reso = 0, the loop never runs
+        assert not f.any() and not calls
+        return
+    g = golden("octree_analytic.npz")
+    key = "%s_%d_%d" % (name, res, init)
+    assert sum(calls) == int(g[key + "_evaluated"]) and max(calls) <= 50000
+    assert np.array_equal(sha(f), g[key + "_sha"])
+    # a float64-valued callable keeps its precision in the field (reference: sdf[test_mask] = values)
+    f64 = mesh_util.eval_grid_octree(coords, lambda p: 0.5 + 0.1 * p[0] + 1e-12 * p[1], init_resolution=init)
+    ref = orc.eval_grid_octree(coords, lambda p: 0.5 + 0.1 * p[0] + 1e-12 * p[1], init_resolution=init)
+    assert np.array_equal(f64, ref)
+
+
 def test_octree_with_net(sat):
     """Same evaluated values -> identical field: run the oracle's restatement of the reference
     loop on the GPU's own dense field and compare with the device octree bit for bit; then
