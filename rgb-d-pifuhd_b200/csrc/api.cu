@@ -1,5 +1,7 @@
 // Context + C ABI (include/pifu_b200.h): snapshots of the two MLPs and feature maps, the
 // per-chunk workspace in HBM, and the layer schedule of one query.
+#include <cuda.h>
+
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -83,6 +85,8 @@ struct ChainPlan {
     float b3 = 0.f;
     float* cc = nullptr;             // per-column constants of the current column chunk
     int cc_cols = 0;
+    TmaDesc tm256, tm128;            // tensor maps over wstream (rows of 128 B; boxes of 128 / 64 rows)
+    bool tmap_ok = false;
     int* colmaps = nullptr;          // scratch for the packer
 };
 constexpr int CHAIN_COLS_PER_CHUNK = 148 * 32;
@@ -327,6 +331,36 @@ void free_chain(ChainPlan& P, bool coarse_too) {
     P.fine_ok = false;
 }
 
+// The weight stream seen as a [rows][64] fp16 tensor: the TMA unit then fetches whole 128-byte
+// lines (1-D bulk copies ran at ~26 B/cycle/SM and starved the tensor pipe).
+int chain_encode_tmaps(ChainPlan& P) {
+    P.tmap_ok = false;
+    static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "tensor map size");
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return 0;                                      // stay on the 1-D bulk copies
+    }
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(KB), chain::WSTREAM_BYTES / ROW_BYTES};
+    const cuuint64_t strides[1] = {ROW_BYTES};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int v = 0; v < 2; ++v) {
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(KB), v == 0 ? 128u : 64u};
+        CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(v == 0 ? &P.tm256 : &P.tm128);
+        const CUresult r = reinterpret_cast<Encode>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, P.wstream, dims, strides, box, estr,
+                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    P.tmap_ok = true;
+    return 0;
+}
+
 size_t chain_stage_offset(int s) {
     return s < chain::STAGES_256 ? static_cast<size_t>(s) * 256 * ROW_BYTES
                                  : static_cast<size_t>(chain::STAGES_256) * 256 * ROW_BYTES +
@@ -371,6 +405,7 @@ int build_chain_coarse(pifu_ctx* c, const float* const* weights, const float* co
     if (!(L.n_layers >= 4 && L.dims[0] == 257 && L.dims[1] == C0 && L.dims[2] == C1 && L.dims[3] == C2 &&
           !L.is_res(1) && L.is_res(2) && L.merge == 2 && c->bufs[c->buf_F].nkb == 5)) return 0;
     PIFU_CUDA(cudaMalloc(&P.wstream, WSTREAM_BYTES));
+    chain_encode_tmaps(P);
     PIFU_CUDA(cudaMalloc(&P.colmaps, (static_cast<size_t>(STAGES) + 8 + 16) * KB * sizeof(int)));
     PIFU_CUDA(cudaMalloc(&P.w_colA, static_cast<size_t>(C0 + C2) * 5 * ROW_BYTES));
     PIFU_CUDA(cudaMalloc(&P.bias_colA, (C0 + C2) * sizeof(float)));
@@ -504,6 +539,9 @@ int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_
         if (t1 <= t0) continue;
         ChainArgs ca;
         memset(&ca, 0, sizeof(ca));
+        static const bool tmap_env = !(getenv("PIFU_CHAIN_TMAP") && atoi(getenv("PIFU_CHAIN_TMAP")) == 0);
+        ca.use_tmap = (P.tmap_ok && tmap_env) ? 1 : 0;
+        ca.tm256 = P.tm256; ca.tm128 = P.tm128;
         ca.wstream = P.wstream; ca.cc = P.cc; ca.colmask = c->mask;
         ca.wz0 = P.wz0; ca.wz2 = P.wz2; ca.b1 = P.b1; ca.w3 = P.w3; ca.b3 = P.b3;
         ca.tile0 = t0; ca.n_tiles = static_cast<int>(t1 - t0); ca.col0 = cb;
@@ -515,10 +553,29 @@ int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_
         ca.z_mul = c->z_mul; ca.z_div = c->z_div;
         ca.out = out + (t0 * TILE_M - id_a);
         c->launches += 1;
+        static long long* trace_dev = nullptr;
+        static bool trace_on = getenv("PIFU_CHAIN_TRACE") != nullptr, trace_done = false;
+        if (trace_on && !trace_done) {
+            if (!trace_dev) PIFU_CUDA(cudaMalloc(&trace_dev, 8 * 64 * sizeof(long long)));
+            PIFU_CUDA(cudaMemsetAsync(trace_dev, 0, 8 * 64 * sizeof(long long), s));
+            ca.trace = trace_dev;
+        }
         // algorithmic work: the get_preds() layer stack of every point (coarse L0-L2, fine L0-L3)
         const double flops = static_cast<double>(ca.n_tiles) * TILE_M * 2.0 *
                              (257.0 * C0 + 1.0 * C0 * C1 + 769.0 * C2 + 272.0 * F0 + 784.0 * F1 + 528.0 * F2 + F2);
         if (run_timed(c, 1, flops, s, [&]() { return launch_chain(ca, c->num_sms, s); })) return -1;
+        if (ca.trace) {                      // debug aid: print the stamps of CTA 0's first tiles, once
+            long long h[8 * 64];
+            PIFU_CUDA(cudaStreamSynchronize(s));
+            PIFU_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+            for (int it = 0; it < 8; ++it) {
+                fprintf(stderr, "chain trace tile %d:", it);
+                for (int i = 0; i < 64; ++i)
+                    if (h[it * 64 + i]) fprintf(stderr, " %d:%lld", i, (i >= 13 && i <= 16) ? h[it * 64 + i] : h[it * 64 + i] - h[0]);
+                fprintf(stderr, "\n");
+            }
+            trace_done = true;
+        }
     }
     return 0;
 }

@@ -28,6 +28,8 @@
 //   J3 F0[:256] -> Hb   J4 F0[256:] -> Ha   J5 F1 -> Hb   J6 F2 -> Ha[0:128]
 // Shared memory: P = 4 k-block slots (y0 ring during J0/J1, then phi, which stays resident for
 // J3-J6), D = 4 k-block slots (ring for y1 / fine activations), W = weight ring.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -101,6 +103,12 @@ __device__ __forceinline__ float lattice_z(const ChainArgs& a, long long id) {
     return __fdiv_rn(__fmul_rn(zg, a.z_mul), a.z_div);
 }
 
+// timeline stamps of CTA 0 (debug aid, PIFU_CHAIN_TRACE=1): slot `i` of tile iteration `it`
+#define CHAIN_TRACE(it, i)                                                                    \
+    do {                                                                                      \
+        if (a.trace != nullptr && blockIdx.x == 0 && (it) < 8) a.trace[(it) * 64 + (i)] = clock64(); \
+    } while (0)
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t rank = ptx::cluster_ctarank();
@@ -119,11 +127,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* g_full = acc_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+    const uint32_t ready_a = ptx::smem_u32(smem + OFF_TMEM + 8);     // scout -> issuer token count
     float* s_z = reinterpret_cast<float*>(smem + OFF_Z);
     float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NW; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); ptx::mbar_init(&w_pfull[s], 1); }
+        // leader: a weight stage is usable when its own half landed AND the peer forwarded "my half landed"
+        // (one barrier, one wait per stage for the MMA thread: each mbarrier wait costs ~90 cycles of its time)
+        for (int s = 0; s < NW; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); ptx::mbar_init(&w_pfull[s], 2); }
         for (int s = 0; s < NP; ++s) { ptx::mbar_init(&p_full[s], 2 * ALU_WARPS); ptx::mbar_init(&p_empty[s], 1); }
         for (int s = 0; s < ND; ++s) { ptx::mbar_init(&d_full[s], 2 * ALU_WARPS); ptx::mbar_init(&d_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&acc_full[s], 1); ptx::mbar_init(&acc_empty[s], 2 * ALU_WARPS); }
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         ptx::tmem_alloc<2>(tmem_slot, 512);
     }
     if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM + 8) = 0u;
     {
         float* d0 = reinterpret_cast<float*>(smem + OFF_WZ0);
         float* d2 = reinterpret_cast<float*>(smem + OFF_WZ2);
@@ -158,15 +170,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             // ------------------------------------------------ TMA producer: weight stream
             int ws = 0;
             uint32_t ph = 0;
+            if (a.use_tmap) { ptx::prefetch_tmap(&a.tm256); ptx::prefetch_tmap(&a.tm128); }
             for (int pt = first; pt < n_pairs; pt += stride) {
                 const uint8_t* src = a.wstream;
+                int row = 0;                                   // first 128-byte row of the stage in the stream
                 for (int s = 0; s < STAGES; ++s) {
-                    const uint32_t total = (s < STAGES_256 ? 256u : 128u) * ROW_BYTES;
+                    const uint32_t rows = s < STAGES_256 ? 256u : 128u;
+                    const uint32_t total = rows * ROW_BYTES;
                     const uint32_t half = total >> 1;
+                    // leader: its half lands on w_pfull, the barrier the peer's forwarder also arrives on
+                    uint64_t* full = leader ? &w_pfull[ws] : &w_full[ws];
                     ptx::mbar_wait(&w_empty[ws], ph ^ 1u);
-                    ptx::mbar_arrive_expect_tx(&w_full[ws], half);
-                    ptx::bulk_g2s(smem + OFF_W + ws * SLOT, src + rank * half, half, &w_full[ws]);
+                    ptx::mbar_arrive_expect_tx(full, half);
+                    if (a.use_tmap)
+                        ptx::tma_load_2d(smem + OFF_W + ws * SLOT, s < STAGES_256 ? &a.tm256 : &a.tm128, 0,
+                                         row + static_cast<int>(rank * (rows >> 1)), full);
+                    else
+                        ptx::bulk_g2s(smem + OFF_W + ws * SLOT, src + rank * half, half, full);
                     src += total;
+                    row += static_cast<int>(rows);
                     if (++ws == NW) { ws = 0; ph ^= 1u; }
                 }
             }
@@ -184,84 +206,167 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                     if (++ws == NW) { ws = 0; ph ^= 1u; }
                 }
             }
-        } else if (lane == 0) {
+        } else if (leader) {
             // ------------------------------------------------ MMA issuer (leader of the pair)
+            // The whole warp walks the schedule with warp-uniform values and one elected lane issues:
+            // descriptors built under a divergent `lane == 0` made ptxas wrap every tcgen05.mma in an
+            // ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY loop, ~110 cycles per instruction - slower than the
+            // 128 cycles the instruction keeps the tensor pipe busy.
+            // tcgen05.mma issue is back-pressured after ~1 queued instruction, so every cycle this
+            // thread spends elsewhere is a cycle the tensor pipe idles.  It therefore waits on no
+            // mbarrier itself (~90 cycles each, ~180 per tile): the scout thread (warp 3) walks the
+            // same schedule ahead of it, does the waits and publishes a running token count; one
+            // ~30-cycle acquire-load per batch of MMAs is all that is left here.
             constexpr uint32_t I256 = ptx::make_idesc_f16(256, 256);
             constexpr uint32_t I128 = ptx::make_idesc_f16(256, 128);
             int ws = 0;
-            uint32_t wph = 0;
-            uint32_t pf = 0, df = 0, ae = 3;          // parities to wait on (bit per barrier)
-            auto wait_bit = [&](uint64_t* bar, uint32_t& bits, int i) {
-                ptx::mbar_wait(&bar[i], (bits >> i) & 1u);
-                bits ^= (1u << i);
+            uint32_t tok = 0;
+            const bool tracing = a.trace != nullptr && blockIdx.x == 0 && lane == 0;
+            long long t_poll = 0;
+            const uint32_t u_ready = __shfl_sync(0xffffffffu, ready_a, 0);
+            const uint32_t u_sW = __shfl_sync(0xffffffffu, sW, 0);
+            const uint32_t sP = __shfl_sync(0xffffffffu, ptx::smem_u32(smem + OFF_P), 0);      // warp-uniform copies
+            const uint32_t sD = __shfl_sync(0xffffffffu, ptx::smem_u32(smem + OFF_D), 0);
+            const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t u_bars = __shfl_sync(0xffffffffu, ptx::smem_u32(bars), 0);
+            auto ubar = [&](const uint64_t* b) {         // warp-uniform shared address of one of the barriers
+                return u_bars + static_cast<uint32_t>(reinterpret_cast<const uint8_t*>(b) - reinterpret_cast<const uint8_t*>(bars));
+            };
+            auto acquire = [&]() {                 // operands + weights of the next batch are in place
+                ++tok;
+                const long long t0 = tracing ? clock64() : 0;
+                while (static_cast<int>(ptx::ld_acquire_shared(u_ready) - tok) < 0) { }
+                if (tracing) t_poll += clock64() - t0;
+                ptx::tc_fence_after();
+            };
+            auto commit = [&](const uint64_t* b) {
+                const uint32_t addr = ubar(b);
+                if (ptx::elect_one()) ptx::umma_commit_addr<2>(addr);
+                __syncwarp();
             };
             auto kblock = [&](uint32_t a_addr, uint32_t d_tmem, uint32_t idesc, bool accum) {
-                ptx::mbar_wait(&w_full[ws], wph);
-                ptx::mbar_wait(&w_pfull[ws], wph);
-                ptx::tc_fence_after();
                 const uint64_t ad = ptx::make_sw128_desc(a_addr);
-                const uint64_t bd = ptx::make_sw128_desc(sW + ws * SLOT);
+                const uint64_t bd = ptx::make_sw128_desc(u_sW + ws * SLOT);
+                const uint32_t wbar = ubar(&w_empty[ws]);
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < KB / 16; ++k)
-                    ptx::umma_f16_ss<2>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (accum || k > 0) ? 1u : 0u);
-                ptx::umma_commit<2>(&w_empty[ws]);
-                if (++ws == NW) { ws = 0; wph ^= 1u; }
+                    for (int k = 0; k < KB / 16; ++k)
+                        ptx::umma_f16_ss<2>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (accum || k > 0) ? 1u : 0u);
+                    ptx::umma_commit_addr<2>(wbar);
+                }
+                __syncwarp();
+                if (++ws == NW) ws = 0;
             };
-            const uint32_t tHa = tmem_base, tHb = tmem_base + 256;
-            for (int pt = first; pt < n_pairs; pt += stride) {
+            const uint32_t tHa = u_tmem, tHb = u_tmem + 256;
+            int mit = 0;
+            for (int pt = first; pt < n_pairs; pt += stride, ++mit) {
                 // J01: coarse L1, both output halves per y0 k-block (y0 is generated once)
-                wait_bit(acc_empty, ae, 0);
-                wait_bit(acc_empty, ae, 1);
+                if (lane == 0) CHAIN_TRACE(mit, 0);
                 for (int kb = 0; kb < C0 / KB; ++kb) {
                     const int s = kb & 3;
-                    wait_bit(p_full, pf, s);
+                    acquire();
+                    if (kb == 0) if (lane == 0) CHAIN_TRACE(mit, 1);
                     kblock(sP + s * SLOT, tHa, I256, kb > 0);
                     kblock(sP + s * SLOT, tHb, I256, kb > 0);
-                    ptx::umma_commit<2>(&p_empty[s]);
+                    commit(&p_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[0]);
-                ptx::umma_commit<2>(&acc_full[1]);
+                commit(&acc_full[0]);
+                commit(&acc_full[1]);
+                if (lane == 0) CHAIN_TRACE(mit, 2);
                 // J2: coarse L2, A = y1 through the D ring
-                wait_bit(acc_empty, ae, 0);
                 for (int kb = 0; kb < C1 / KB; ++kb) {
                     const int s = kb & 3;
-                    wait_bit(d_full, df, s);
+                    acquire();
+                    if (kb == 0) if (lane == 0) CHAIN_TRACE(mit, 3);
                     kblock(sD + s * SLOT, tHa, I256, kb > 0);
-                    ptx::umma_commit<2>(&d_empty[s]);
+                    commit(&d_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[0]);
+                commit(&acc_full[0]);
+                if (lane == 0) CHAIN_TRACE(mit, 4);
                 // J3 / J4: fine L0 output halves, A = phi (resident in P)
-                wait_bit(acc_empty, ae, 1);
                 for (int s = 0; s < 4; ++s) {
-                    wait_bit(p_full, pf, s);
+                    acquire();
+                    if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 5);
                     kblock(sP + s * SLOT, tHb, I256, s > 0);
                 }
-                ptx::umma_commit<2>(&acc_full[1]);
-                wait_bit(acc_empty, ae, 0);
-                for (int s = 0; s < 4; ++s) kblock(sP + s * SLOT, tHa, I256, s > 0);
-                ptx::umma_commit<2>(&acc_full[0]);
+                commit(&acc_full[1]);
+                if (lane == 0) CHAIN_TRACE(mit, 6);
+                for (int s = 0; s < 4; ++s) {
+                    acquire();
+                    if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 7);
+                    kblock(sP + s * SLOT, tHa, I256, s > 0);
+                }
+                commit(&acc_full[0]);
+                if (lane == 0) CHAIN_TRACE(mit, 8);
                 // J5: fine L1, A = phi then yF0 through the D ring
-                wait_bit(acc_empty, ae, 1);
-                for (int s = 0; s < 4; ++s) kblock(sP + s * SLOT, tHb, I256, s > 0);
+                for (int s = 0; s < 4; ++s) {
+                    acquire();
+                    if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 9);
+                    kblock(sP + s * SLOT, tHb, I256, s > 0);
+                }
                 for (int kb = 0; kb < F0 / KB; ++kb) {
                     const int s = kb & 3;
-                    wait_bit(d_full, df, s);
+                    acquire();
                     kblock(sD + s * SLOT, tHb, I256, true);
-                    ptx::umma_commit<2>(&d_empty[s]);
+                    commit(&d_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[1]);
+                commit(&acc_full[1]);
+                if (lane == 0) CHAIN_TRACE(mit, 10);
                 // J6: fine L2 (128 wide), A = phi (last use: release P) then yF1
-                wait_bit(acc_empty, ae, 0);
                 for (int s = 0; s < 4; ++s) {
+                    acquire();
+                    if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 11);
                     kblock(sP + s * SLOT, tHa, I128, s > 0);
-                    ptx::umma_commit<2>(&p_empty[s]);
+                    commit(&p_empty[s]);
                 }
                 for (int s = 0; s < 4; ++s) {
-                    wait_bit(d_full, df, s);
+                    acquire();
                     kblock(sD + s * SLOT, tHa, I128, true);
-                    ptx::umma_commit<2>(&d_empty[s]);
+                    commit(&d_empty[s]);
                 }
-                ptx::umma_commit<2>(&acc_full[0]);
+                commit(&acc_full[0]);
+                if (lane == 0) CHAIN_TRACE(mit, 12);
+                if (tracing && mit < 8) { a.trace[mit * 64 + 13] = t_poll; t_poll = 0; }
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0 && leader) {
+            // ------------------------------------------------ scout: the issuer's waits, one batch ahead
+            int ws = 0;
+            uint32_t wph = 0, pf = 0, df = 0, ae = 3, tok = 0;      // parities to wait on (bit per barrier)
+            const bool tracing = a.trace != nullptr && blockIdx.x == 0;
+            long long t_op = 0, t_w = 0;
+            int sit = 0;
+            auto need = [&](uint64_t* bar, uint32_t& bits, int i) {
+                const long long t0 = tracing ? clock64() : 0;
+                ptx::mbar_wait(&bar[i], (bits >> i) & 1u);
+                if (tracing) t_op += clock64() - t0;
+                bits ^= (1u << i);
+            };
+            auto weights = [&]() {                                  // both halves of the next stage have landed
+                const long long t0 = tracing ? clock64() : 0;
+                ptx::mbar_wait(&w_pfull[ws], wph);
+                if (tracing) t_w += clock64() - t0;
+                if (++ws == NW) { ws = 0; wph ^= 1u; }
+            };
+            auto publish = [&]() { ptx::st_release_shared(ready_a, ++tok); };
+            for (int pt = first; pt < n_pairs; pt += stride, ++sit) {
+                if (tracing && sit > 0 && sit <= 8) { a.trace[(sit - 1) * 64 + 14] = t_op; a.trace[(sit - 1) * 64 + 15] = t_w; t_op = t_w = 0; }
+                need(acc_empty, ae, 0);
+                need(acc_empty, ae, 1);
+                for (int kb = 0; kb < C0 / KB; ++kb) { need(p_full, pf, kb & 3); weights(); weights(); publish(); }   // J01
+                need(acc_empty, ae, 0);
+                for (int kb = 0; kb < C1 / KB; ++kb) { need(d_full, df, kb & 3); weights(); publish(); }              // J2
+                need(acc_empty, ae, 1);
+                for (int s = 0; s < 4; ++s) { need(p_full, pf, s); weights(); publish(); }                            // J3
+                need(acc_empty, ae, 0);
+                for (int s = 0; s < 4; ++s) { weights(); publish(); }                                                 // J4
+                need(acc_empty, ae, 1);
+                for (int s = 0; s < 4; ++s) { weights(); publish(); }                                                 // J5: phi
+                for (int kb = 0; kb < F0 / KB; ++kb) { need(d_full, df, kb & 3); weights(); publish(); }              //     yF0
+                need(acc_empty, ae, 0);
+                for (int s = 0; s < 4; ++s) { weights(); publish(); }                                                 // J6: phi
+                for (int s = 0; s < 4; ++s) { need(d_full, df, s); weights(); publish(); }                            //     yF1
             }
         }
     } else if (warp >= ALU_WARP0) {
@@ -354,9 +459,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         };
         // drain the 256-column accumulator half H into four k-block slots (D ring, or P for phi);
         // the TMEM load of k-block j + 1 is in flight while k-block j is converted
+        int it = 0;
         auto drain_half = [&](int H, uint32_t slot0, uint64_t* empty_bar, uint32_t& empty_bits, uint32_t full_addr,
-                              uint32_t bias_a, uint32_t wz_a, float z) {
+                              uint32_t bias_a, uint32_t wz_a, float z, int ti) {
             wait_bit(acc_full, af, H);
+            if (atid == 0) CHAIN_TRACE(it, ti);
             ptx::tc_fence_after();
             uint32_t v[2][32];
             const uint32_t t0 = tq + H * 256 + 32 * hh;
@@ -370,6 +477,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 emit(v[j & 1], 64 * j + 32 * hh, slot0 + j * SLOT, bias_a, wz_a, z);
                 signal(full_addr + j * 8);
             }
+            if (atid == 0) CHAIN_TRACE(it, ti + 1);
         };
 
         if (first < n_pairs) {
@@ -382,8 +490,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             for (int i = 0; i < 4; ++i) zr[i] = s_z[grow0 + 4 * i];
             for (int kb = 0; kb < 4; ++kb) gen(kb);
         }
-        int it = 0;
         for (int pt = first; pt < n_pairs; pt += stride, ++it) {
+            if (atid == 0) CHAIN_TRACE(it, 20);
             const bool has_next = pt + stride < n_pairs;
             const int t = 2 * pt + static_cast<int>(rank);
             const bool live = t < a.n_tiles;
@@ -394,26 +502,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
 
             // feed J01 (k-blocks 0..3 were generated ahead)
             for (int kb = 4; kb < C0 / KB; ++kb) gen(kb);
+            if (atid == 0) CHAIN_TRACE(it, 21);
             alu_bar();                                   // c0 / z registers of this tile no longer read
             if (has_next && atid == 0) load_g1(tn);
             // J01 done -> y1 = leaky(acc + b1): Ha -> D slots (J2 starts), then Hb as J2 frees them
-            drain_half(0, sD, d_empty, de, df_addr, b1_a, 0u, 0.f);
-            drain_half(1, sD, d_empty, de, df_addr, b1_a + 256 * 4, 0u, 0.f);
+            drain_half(0, sD, d_empty, de, df_addr, b1_a, 0u, 0.f, 22);
+            drain_half(1, sD, d_empty, de, df_addr, b1_a + 256 * 4, 0u, 0.f, 24);
             // J2 done -> phi = leaky(acc + c2 + wz2 * z) into the P slots (resident until J6)
             wait_bit(g_full, gph, 1);
-            drain_half(0, sP, p_empty, pe, pf_addr, g2_a, wz2_a, zcur[row]);
-            drain_half(1, sD, d_empty, de, df_addr, g2_a + C2 * 4, 0u, 0.f);             // J3 -> yF0[:256]
-            drain_half(0, sD, d_empty, de, df_addr, g2_a + (C2 + 256) * 4, 0u, 0.f);     // J4 -> yF0[256:]
-            drain_half(1, sD, d_empty, de, df_addr, g2_a + (C2 + F0) * 4, 0u, 0.f);      // J5 -> yF1
+            drain_half(0, sP, p_empty, pe, pf_addr, g2_a, wz2_a, zcur[row], 26);
+            drain_half(1, sD, d_empty, de, df_addr, g2_a + C2 * 4, 0u, 0.f, 28);             // J3 -> yF0[:256]
+            drain_half(0, sD, d_empty, de, df_addr, g2_a + (C2 + 256) * 4, 0u, 0.f, 30);     // J4 -> yF0[256:]
+            drain_half(1, sD, d_empty, de, df_addr, g2_a + (C2 + F0) * 4, 0u, 0.f, 32);      // J5 -> yF1
             if (has_next) {                                      // next tile's first y0 k-blocks
                 wait_bit(g_full, gph, 0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) zr[i] = znext[grow0 + 4 * i];
                 for (int kb = 0; kb < 4; ++kb) gen(kb);
             }
+            if (atid == 0) CHAIN_TRACE(it, 34);
             // J6 done -> fused Conv1d -> 1 + sigmoid + in-bounds mask (`MLP.py:72-73`, `PIFuMRNet.py:173-174`)
             {
                 wait_bit(acc_full, af, 0);
+                if (atid == 0) CHAIN_TRACE(it, 35);
                 ptx::tc_fence_after();
                 uint32_t v[2][32];
                 ptx::tmem_ld32(tq + 64 * hh, v[0]);
@@ -444,6 +555,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 }
             }
             alu_bar();                                   // G2 constants / s_part of this tile consumed
+            if (atid == 0) CHAIN_TRACE(it, 36);
             if (has_next && atid == 0) load_g2(tn);
         }
     }
@@ -468,6 +580,8 @@ int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s) {
         configured[dev & 31] = true;
     }
     const int pairs = (a.n_tiles + 1) / 2;
+    static const int sms_override = getenv("PIFU_CHAIN_SMS") ? atoi(getenv("PIFU_CHAIN_SMS")) : 0;   // experiments only
+    if (sms_override > 1) num_sms = sms_override;
     const int max_pairs = num_sms / 2;
     const int grid = (pairs < max_pairs ? pairs : max_pairs) * 2;
     cudaLaunchConfig_t cfg = {};

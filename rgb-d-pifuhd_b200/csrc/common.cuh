@@ -131,7 +131,12 @@ constexpr size_t WSTREAM_BYTES = static_cast<size_t>(STAGES_256) * 256 * ROW_BYT
                                  static_cast<size_t>(STAGES_128) * 128 * ROW_BYTES;
 }  // namespace chain
 
+// 128-byte opaque tensor map (CUtensorMap of <cuda.h>, kept opaque so this header needs no driver API)
+struct alignas(64) TmaDesc { unsigned long long opaque[16]; };
+
 struct ChainArgs {
+    TmaDesc tm256, tm128;     // the weight stream as rows of 128 B: boxes of 128 rows / 64 rows (one CTA's half of a stage)
+    int use_tmap;             // 0: 1-D bulk copies (A/B measurements, PIFU_CHAIN_TMAP=0)
     const uint8_t* wstream;   // chain::STAGES packed weight stages in consumption order
     const float* cc;          // [ncols][chain::CC_FLOATS] per-column constants (bias folded in)
     const uint8_t* colmask;   // [ncols] gather mask of the column (bit1 = fine in-bounds)
@@ -148,6 +153,7 @@ struct ChainArgs {
     float cg[12];
     float z_mul, z_div;
     float* out;               // out[t * 128 + row], t relative to tile0
+    long long* trace;         // optional [8][64] clock64 stamps of CTA 0's first tiles (PIFU_CHAIN_TRACE=1), else null
 };
 int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s);
 

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
             ptx::mbar_init(&empty[s], 1);
-            ptx::mbar_init(&pfull[s], 1);
+            ptx::mbar_init(&pfull[s], 2);                         // leader of a pair: own loads + the peer's "landed"
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull[s], 1);
@@ -127,21 +127,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const uint8_t* ab = seg.base +
                         (static_cast<size_t>(mt) * seg.kb_stride + seg.kb_off) * ABLOCK_BYTES;
                     for (int kb = 0; kb < seg.nkb; ++kb, ++kbg) {
+                        // leader of a pair: its loads land on pfull, the barrier the peer's forwarder also
+                        // arrives on, so the MMA warp waits on ONE barrier per stage
+                        uint64_t* fb = (CL == 2 && leader) ? &pfull[stage] : &full[stage];
                         ptx::mbar_wait(&empty[stage], phase ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                        ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
                         ptx::bulk_g2s(sA + stage * ABLOCK_BYTES, ab + static_cast<size_t>(kb) * ABLOCK_BYTES,
-                                      ABLOCK_BYTES, &full[stage]);
+                                      ABLOCK_BYTES, fb);
                         ptx::bulk_g2s(sB + stage * C::BLOAD_BYTES, wt + static_cast<size_t>(kbg) * C::BBLOCK_BYTES,
-                                      C::BLOAD_BYTES, &full[stage]);
+                                      C::BLOAD_BYTES, fb);
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             // ------------------------------------------------ MMA issuer (leader CTA of the group)
+            // The whole warp walks the loop with warp-uniform values and one elected lane issues: under
+            // a divergent `lane == 0` ptxas wrapped every tcgen05.mma in an ELECT / R2UR.BROADCAST /
+            // BRA.U.ANY loop (~110 cycles per instruction, measured in the chain kernel).
             constexpr uint32_t idesc = ptx::make_idesc_f16(TILE_M * CL, BN);
+            const uint32_t u_sA = __shfl_sync(0xffffffffu, ptx::smem_u32(sA), 0);
+            const uint32_t u_sB = __shfl_sync(0xffffffffu, ptx::smem_u32(sB), 0);
+            const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t u_empty = __shfl_sync(0xffffffffu, ptx::smem_u32(empty), 0);
+            const uint32_t u_tfull = __shfl_sync(0xffffffffu, ptx::smem_u32(tfull), 0);
+            uint64_t* ready = CL == 2 ? pfull : full;        // pair: own loads + the peer's "landed" on one barrier
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -150,18 +162,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = u_tmem + acc * BN;
                 for (int kb = 0; kb < a.num_kb; ++kb) {
-                    ptx::mbar_wait(&full[stage], phase);
-                    if (CL == 2) ptx::mbar_wait(&pfull[stage], phase);
+                    ptx::mbar_wait(&ready[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t adesc = ptx::make_sw128_desc(ptx::smem_u32(sA + stage * ABLOCK_BYTES));
-                    const uint64_t bdesc = ptx::make_sw128_desc(ptx::smem_u32(sB + stage * C::BLOAD_BYTES));
+                    const uint64_t adesc = ptx::make_sw128_desc(u_sA + stage * ABLOCK_BYTES);
+                    const uint64_t bdesc = ptx::make_sw128_desc(u_sB + stage * C::BLOAD_BYTES);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < KB / 16; ++k)       // 32 bytes (16 fp16) per MMA along K
-                        ptx::umma_f16_ss<CL>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    ptx::umma_commit<CL>(&empty[stage]);     // frees the smem slot(s) when the MMAs retire
-                    if (kb == a.num_kb - 1) ptx::umma_commit<CL>(&tfull[acc]);
+                        for (int k = 0; k < KB / 16; ++k)       // 32 bytes (16 fp16) per MMA along K
+                            ptx::umma_f16_ss<CL>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        ptx::umma_commit_addr<CL>(u_empty + stage * 8);     // frees the smem slot(s) when the MMAs retire
+                        if (kb == a.num_kb - 1) ptx::umma_commit_addr<CL>(u_tfull + acc * 8);
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }

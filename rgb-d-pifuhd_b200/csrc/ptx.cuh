@@ -48,6 +48,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// plain shared-memory flag (a ~30-cycle poll instead of the ~90-cycle mbarrier.try_wait; used to hand
+// "operands ready" from a scout thread to the MMA-issuing thread).  Volatile on purpose: the
+// .release/.acquire forms compile to MEMBAR.ALL.CTA around every access.  Ordering comes from the
+// scout's mbarrier wait (acquire) before its store, the control dependency of the reader's spin
+// loop, and the tcgen05.fence::after_thread_sync the reader issues before its MMAs.
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+    asm volatile("st.volatile.shared::cta.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -83,6 +96,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// global -> shared through a 2-D tensor map (box = whole rows of 128 B): the TMA unit then asks L2
+// for full 128-byte lines; completion counted in bytes on an mbarrier like the 1-D form.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }
 // shared -> global, tracked by the bulk async-group of the issuing thread.
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
@@ -153,6 +176,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     } else {
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                      :: "r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+    }
+}
+
+// same, the barrier given as a shared-space address (lets the caller keep it in a uniform register)
+template <int CG>
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     :: "r"(bar_addr) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     :: "r"(bar_addr), "h"(static_cast<uint16_t>(3)) : "memory");
     }
 }
 
