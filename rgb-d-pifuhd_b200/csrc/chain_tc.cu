@@ -60,6 +60,12 @@ constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB of shared memory a CTA may use");
 static_assert(OFF_C0 % 16 == 0 && OFF_G2 % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
+// 1: a scout thread does the MMA warp's mbarrier waits and hands over tokens; 0: the MMA warp waits itself
+#ifndef CHAIN_SCOUT
+#define CHAIN_SCOUT 0      // measured: 604 M queries/s without, 591 M with (the token hand-over adds ~200 cycles of latency)
+#endif
+constexpr bool SCOUT = CHAIN_SCOUT != 0;
+
 constexpr int NUM_THREADS = 384;
 constexpr int ALU_WARP0 = 4;
 constexpr int ALU_THREADS = 256;
@@ -232,11 +238,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             auto ubar = [&](const uint64_t* b) {         // warp-uniform shared address of one of the barriers
                 return u_bars + static_cast<uint32_t>(reinterpret_cast<const uint8_t*>(b) - reinterpret_cast<const uint8_t*>(bars));
             };
+            int wws = 0;
+            uint32_t wph = 0, pf = 0, df = 0, ae = 3;      // !SCOUT: parities this warp waits on itself
+            auto need = [&](uint64_t* bar, uint32_t& bits, int i) {
+                if constexpr (!SCOUT) {
+                    const long long t0 = tracing ? clock64() : 0;
+                    ptx::mbar_wait(&bar[i], (bits >> i) & 1u);
+                    if (tracing) t_poll += clock64() - t0;
+                    bits ^= (1u << i);
+                }
+            };
+            auto weights = [&]() {
+                if constexpr (!SCOUT) {
+                    const long long t0 = tracing ? clock64() : 0;
+                    ptx::mbar_wait(&w_pfull[wws], wph);
+                    if (tracing) t_poll += clock64() - t0;
+                    if (++wws == NW) { wws = 0; wph ^= 1u; }
+                }
+            };
             auto acquire = [&]() {                 // operands + weights of the next batch are in place
-                ++tok;
-                const long long t0 = tracing ? clock64() : 0;
-                while (static_cast<int>(ptx::ld_acquire_shared(u_ready) - tok) < 0) { }
-                if (tracing) t_poll += clock64() - t0;
+                if constexpr (SCOUT) {
+                    ++tok;
+                    const long long t0 = tracing ? clock64() : 0;
+                    while (static_cast<int>(ptx::ld_acquire_shared(u_ready) - tok) < 0) { }
+                    if (tracing) t_poll += clock64() - t0;
+                }
                 ptx::tc_fence_after();
             };
             auto commit = [&](const uint64_t* b) {
@@ -262,8 +288,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             for (int pt = first; pt < n_pairs; pt += stride, ++mit) {
                 // J01: coarse L1, both output halves per y0 k-block (y0 is generated once)
                 if (lane == 0) CHAIN_TRACE(mit, 0);
+                // (waits in the order the events are expected, so only the last one's latency is exposed)
                 for (int kb = 0; kb < C0 / KB; ++kb) {
                     const int s = kb & 3;
+                    weights(); weights(); need(p_full, pf, s);
+                    if (kb == 0) { need(acc_empty, ae, 1); need(acc_empty, ae, 0); }
                     acquire();
                     if (kb == 0) if (lane == 0) CHAIN_TRACE(mit, 1);
                     kblock(sP + s * SLOT, tHa, I256, kb > 0);
@@ -276,6 +305,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 // J2: coarse L2, A = y1 through the D ring
                 for (int kb = 0; kb < C1 / KB; ++kb) {
                     const int s = kb & 3;
+                    weights(); need(d_full, df, s);
+                    if (kb == 0) need(acc_empty, ae, 0);
                     acquire();
                     if (kb == 0) if (lane == 0) CHAIN_TRACE(mit, 3);
                     kblock(sD + s * SLOT, tHa, I256, kb > 0);
@@ -284,14 +315,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 commit(&acc_full[0]);
                 if (lane == 0) CHAIN_TRACE(mit, 4);
                 // J3 / J4: fine L0 output halves, A = phi (resident in P)
+                need(acc_empty, ae, 1);
                 for (int s = 0; s < 4; ++s) {
+                    weights(); need(p_full, pf, s);
                     acquire();
                     if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 5);
                     kblock(sP + s * SLOT, tHb, I256, s > 0);
                 }
                 commit(&acc_full[1]);
                 if (lane == 0) CHAIN_TRACE(mit, 6);
+                need(acc_empty, ae, 0);
                 for (int s = 0; s < 4; ++s) {
+                    weights();
                     acquire();
                     if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 7);
                     kblock(sP + s * SLOT, tHa, I256, s > 0);
@@ -299,13 +334,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 commit(&acc_full[0]);
                 if (lane == 0) CHAIN_TRACE(mit, 8);
                 // J5: fine L1, A = phi then yF0 through the D ring
+                need(acc_empty, ae, 1);
                 for (int s = 0; s < 4; ++s) {
+                    weights();
                     acquire();
                     if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 9);
                     kblock(sP + s * SLOT, tHb, I256, s > 0);
                 }
                 for (int kb = 0; kb < F0 / KB; ++kb) {
                     const int s = kb & 3;
+                    weights(); need(d_full, df, s);
                     acquire();
                     kblock(sD + s * SLOT, tHb, I256, true);
                     commit(&d_empty[s]);
@@ -313,13 +351,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 commit(&acc_full[1]);
                 if (lane == 0) CHAIN_TRACE(mit, 10);
                 // J6: fine L2 (128 wide), A = phi (last use: release P) then yF1
+                need(acc_empty, ae, 0);
                 for (int s = 0; s < 4; ++s) {
+                    weights();
                     acquire();
                     if (s == 0) if (lane == 0) CHAIN_TRACE(mit, 11);
                     kblock(sP + s * SLOT, tHa, I128, s > 0);
                     commit(&p_empty[s]);
                 }
                 for (int s = 0; s < 4; ++s) {
+                    weights(); need(d_full, df, s);
                     acquire();
                     kblock(sD + s * SLOT, tHa, I128, true);
                     commit(&d_empty[s]);
@@ -330,7 +371,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             }
         }
     } else if (warp == 3) {
-        if (lane == 0 && leader) {
+        if (SCOUT && lane == 0 && leader) {
             // ------------------------------------------------ scout: the issuer's waits, one batch ahead
             int ws = 0;
             uint32_t wph = 0, pf = 0, df = 0, ae = 3, tok = 0;      // parities to wait on (bit per barrier)
@@ -518,7 +559,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 wait_bit(g_full, gph, 0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) zr[i] = znext[grow0 + 4 * i];
-                for (int kb = 0; kb < 4; ++kb) gen(kb);
+                // two k-blocks before the head, two after: the next tile's first GEMM can start as soon as
+                // the head has emptied the accumulator, and finds its second k-block waiting
+                gen(0);
+                gen(1);
             }
             if (atid == 0) CHAIN_TRACE(it, 34);
             // J6 done -> fused Conv1d -> 1 + sigmoid + in-bounds mask (`MLP.py:72-73`, `PIFuMRNet.py:173-174`)
@@ -554,6 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                     a.out[static_cast<size_t>(t) * TILE_M + row] = inb ? p : 0.f;
                 }
             }
+            if (has_next) { gen(2); gen(3); }
             alu_bar();                                   // G2 constants / s_part of this tile consumed
             if (atid == 0) CHAIN_TRACE(it, 36);
             if (has_next && atid == 0) load_g2(tn);
