@@ -148,6 +148,13 @@ int pifu_mc_count_slab(pifu_ctx* ctx, const float* field, int n0, int n1, int n2
                        int i_global0, int global_n0, int cell_layers, int ghost_layers,
                        long long* nverts, long long* nfaces, long long* ghost_verts, void* stream);
 
+/* Host-side OBJ writer (no GPU involved).  Replaces save_obj_mesh_with_color (mesh_util.py:189-198):
+ * "v %.4f %.4f %.4f %.4f %.4f %.4f" per vertex (host double verts [nverts][3], colors [nverts][3]) then
+ * "f %d %d %d" per face (host int32 faces [nfaces][3], written 1-based as f0, f2, f1); the text is
+ * byte-identical to the reference's. */
+int pifu_write_obj(const char* path, const double* verts, const double* colors, long long nverts,
+                   const int* faces, long long nfaces);
+
 /* Number of kernels launched by this context since creation (bench accounting). */
 long long pifu_launch_count(pifu_ctx* ctx);
 

@@ -181,6 +181,8 @@ class Engine:
         pred = torch.empty(n, device=self.device, dtype=torch.float32)
         low = torch.empty(n, device=self.device, dtype=torch.float32) if want_low else None
         phi = torch.empty(want_phi, n, device=self.device, dtype=torch.float32) if want_phi else None
+        if n == 0:                     # e.g. gen_mesh's last colour chunk `left:-1` (reconstruction.py:64-68)
+            return pred, low, phi
         cl, _ = _calib16(calib_local)
         cg, _ = _calib16(calib_global)
         _lib.check(self.lib.pifu_query(

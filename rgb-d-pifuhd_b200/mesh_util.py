@@ -213,16 +213,16 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
 
 
 def save_obj_mesh_with_color(mesh_path, verts, faces, colors):
-    """`mesh_util.py:189-198`, vectorised: 'v x y z r g b' with %.4f, faces 1-based as (f0, f2, f1)."""
-    verts = np.asarray(verts)
-    colors = np.asarray(colors)
-    faces = np.asarray(faces)
-    with open(mesh_path, 'w') as f:
-        if len(verts):
-            vc = np.concatenate([verts[:, :3], colors[:len(verts), :3]], 1)
-            f.write('\n'.join('v %.4f %.4f %.4f %.4f %.4f %.4f' % tuple(r) for r in vc.tolist()))
-            f.write('\n')
-        if len(faces):
-            fp = faces.astype(np.int64) + 1
-            f.write('\n'.join('f %d %d %d' % (r[0], r[2], r[1]) for r in fp.tolist()))
-            f.write('\n')
+    """`mesh_util.py:189-198`: 'v x y z r g b' with %.4f, faces 1-based as (f0, f2, f1); same bytes as the
+    reference's per-line loop, written by the library's multi-threaded host formatter (obj.cu)."""
+    import ctypes
+    from . import _lib
+    verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float64)[:, :3]) if len(verts) else np.zeros((0, 3))
+    colors = np.ascontiguousarray(np.asarray(colors, dtype=np.float64)[:len(verts), :3]) if len(verts) else np.zeros((0, 3))
+    if len(colors) != len(verts):
+        raise IndexError("colors has fewer rows than verts")
+    faces = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1, 3)) if len(faces) else np.zeros((0, 3), np.int32)
+    lib = _lib.load()
+    _lib.check(lib.pifu_write_obj(str(mesh_path).encode(), verts.ctypes.data_as(ctypes.c_void_p),
+                                  colors.ctypes.data_as(ctypes.c_void_p), len(verts),
+                                  faces.ctypes.data_as(ctypes.c_void_p), len(faces)))

@@ -68,3 +68,35 @@ def test_save_obj_format(tmp_path):
     lines = open(p).read().splitlines()
     assert lines[0] == "v 0.1235 -1.5000 2.0000 0.5000 0.2500 1.0000"
     assert lines[2] == "f 1 2 2"
+
+
+def test_save_obj_bytes_identical_to_reference_loop(tmp_path):
+    """The native writer reproduces printf('%.4f') exactly: random values, exact decimal ties
+    (k/32 * 1e-3 style dyadic values), values just below / above a tie, signed zeros, huge values."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    v = rng.uniform(-3, 3, (n, 3))
+    ties = np.array([0.03125, 0.09375, 0.00005, 0.00015, 0.12345, 2.5e-5, 1.00005, 0.99995, 9.99995, 8191.99995,
+                     65536.00005, 123456.78905, 1e-300, -1e-9, 0.0, -0.0, 1e14, 3e15, 1e22, -7.5e15])
+    near = np.concatenate([np.nextafter(ties, np.inf), np.nextafter(ties, -np.inf)])
+    sp = np.concatenate([ties, near, -ties])
+    v[:len(sp), 0] = sp
+    v[:len(sp), 2] = sp[::-1]
+    c = rng.uniform(0, 1, (n, 3))
+    c[:len(sp), 1] = np.abs(sp) % 1.0
+    f = rng.integers(0, n, (3 * n, 3)).astype(np.int32)
+    f[0] = [2 ** 31 - 2, 0, 5]
+    p = str(tmp_path / "native.obj")
+    mesh_util.save_obj_mesh_with_color(p, v, f, c)
+    ref = io.StringIO()
+    for idx, vv in enumerate(v):                       # the reference's loop, `mesh_util.py:192-197`
+        cc = c[idx]
+        ref.write('v %.4f %.4f %.4f %.4f %.4f %.4f\n' % (vv[0], vv[1], vv[2], cc[0], cc[1], cc[2]))
+    for ff in f.astype(np.int64):
+        ref.write('f %d %d %d\n' % (ff[0] + 1, ff[2] + 1, ff[1] + 1))
+    assert open(p).read() == ref.getvalue()
+    # empty mesh -> empty file; fewer colours than vertices is an error like the reference's IndexError
+    mesh_util.save_obj_mesh_with_color(p, np.zeros((0, 3)), np.zeros((0, 3), np.int32), np.zeros((0, 3)))
+    assert os.path.getsize(p) == 0
+    with pytest.raises(IndexError):
+        mesh_util.save_obj_mesh_with_color(p, v[:10], f[:1], c[:5])
