@@ -159,7 +159,7 @@ class PIFuMRNet(BasePIFuNet):
             pred = torch.stack(out, 0).view(B1, 1, N, 4)
             d = [pred[:, :, :, a + 1] - pred[:, :, :, 0] for a in range(3)]
             nmls.append(F.normalize(-torch.cat(d, 1), dim=1, eps=1e-8))
-        self.nmls = torch.stack(nmls, 1).view(-1, 3, N)
+        self.nmls = torch.stack(nmls, 1).reshape(B1 * B2, 3, N)      # `.view(-1, 3, N)` in the reference; explicit so N == 0 works
 
     def get_im_feat(self):
         return self.im_feat_list[-1]
