@@ -218,6 +218,16 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
         if mode == "octree":
             d["evaluated_per_level"] = stats
             d["evaluated_fraction"] = sum(stats) / float(res ** 3)
+            # how the frontier points were evaluated: chain kernel in its run-list form (kind 2) and/or
+            # per-layer kernels (kind 0, which also computes the per-run constants), per-launch CUDA events
+            eng.profile(True)
+            mesh_util.eval_field_device(netMR, dev, cal, res, True)
+            n2, ms2, fl2 = eng.profile_read_kind(2)
+            n0, ms0, fl0 = eng.profile_read_kind(0)
+            eng.profile(False)
+            d["frontier_mlp"] = {"runlist_chain_launches": n2, "runlist_chain_ms": ms2,
+                                 "runlist_chain_algorithmic_tflops": (fl2 / (ms2 * 1e-3) / 1e12) if ms2 > 0 else None,
+                                 "layer_kernel_launches": n0, "layer_kernel_ms": ms0}
         out[mode] = d
         del field, verts, faces, normals, values, host
     return out

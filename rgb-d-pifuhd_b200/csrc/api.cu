@@ -88,6 +88,14 @@ struct ChainPlan {
     TmaDesc tm256, tm128;            // tensor maps over wstream (rows of 128 B; boxes of 128 / 64 rows)
     bool tmap_ok = false;
     int* colmaps = nullptr;          // scratch for the packer
+    // run-list form (octree frontiers): segmentation scratch
+    bool rows_enabled = true;
+    uint32_t* block_heads = nullptr; // segments started per 1024-row block of the id list
+    long long cap_blocks = 0;
+    int* rowseg = nullptr;           // chunk-local segment of every row of the current chunk
+    long long* seg_ids = nullptr;    // lattice id of the first row of every segment of the current chunk
+    long long cap_rows = 0;
+    std::vector<uint32_t> heads_host;
 };
 constexpr int CHAIN_COLS_PER_CHUNK = 148 * 32;
 
@@ -325,6 +333,8 @@ void free_chain(ChainPlan& P, bool coarse_too) {
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     if (coarse_too) {
         fr(P.wstream); fr(P.w_colA); fr(P.bias_colA); fr(P.wz0); fr(P.wz2); fr(P.b1); fr(P.colmaps);
+        fr(P.block_heads); fr(P.rowseg); fr(P.seg_ids);
+        P.cap_blocks = P.cap_rows = 0;
         P.coarse_ok = false;
     }
     fr(P.w_colB); fr(P.bias_colB); fr(P.w3);
@@ -479,6 +489,9 @@ bool chain_eligible(const pifu_ctx* c, int levels, int R2, const float* calib, c
 }
 
 void lattice_source(PointSource& src, int R0, int R1, int R2, const double* calib_inv);
+void lattice_chain_args(pifu_ctx* c, ChainArgs& ca, const PointSource& src, int R0, int R1, int R2, const float* calib);
+int chain_constants(pifu_ctx* c, const PointSource& src, int ncol, const float* calib, cudaStream_t s);
+int grow_cc(ChainPlan& P, long long cols);
 
 // lattice ids [id_a, id_b), both multiples of 128, through the chain kernel
 int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_b, const float* calib,
@@ -491,66 +504,23 @@ int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_
     long long per_chunk = CHAIN_COLS_PER_CHUNK;
     const long long ws_cols = static_cast<long long>(c->chunk_tiles) * TILE_M;
     if (per_chunk > ws_cols) per_chunk = ws_cols;
-    if (P.cc_cols < per_chunk) {
-        if (P.cc) { cudaFree(P.cc); P.cc = nullptr; }
-        PIFU_CUDA(cudaMalloc(&P.cc, static_cast<size_t>(per_chunk) * CC_FLOATS * sizeof(float)));
-        P.cc_cols = static_cast<int>(per_chunk);
-    }
-    Level& LC = c->lv[0];
-    Level& LF = c->lv[1];
+    if (grow_cc(P, per_chunk)) return -1;
     for (long long cb = col_a; cb < col_b; cb += per_chunk) {
         const long long ce = cb + per_chunk < col_b ? cb + per_chunk : col_b;
         const int ncol = static_cast<int>(ce - cb);
-        const int m_tiles = (ncol + TILE_M - 1) / TILE_M;
-        // ---- one sample per column (k = 0): feature rows + in-bounds masks of the column
-        GatherArgs ga;
-        memset(&ga, 0, sizeof(ga));
-        lattice_source(ga.src, R0, R1, R2, calib_inv);
-        ga.src.id0 = cb * R2;
-        ga.src.id_stride = R2;
-        ga.n = ncol;
-        memcpy(ga.cg, calib, 12 * sizeof(float));
-        memcpy(ga.cl, calib, 12 * sizeof(float));
-        ga.z_mul = c->z_mul; ga.z_div = c->z_div;
-        ga.feat_c = LC.feat; ga.Hc = LC.H; ga.Wc = LC.W; ga.Cc = LC.C;
-        ga.F = c->bufs[c->buf_F].ptr; ga.kbF = c->bufs[c->buf_F].nkb;
-        ga.feat_f = LF.feat; ga.Hf = LF.H; ga.Wf = LF.W; ga.Cf = LF.C;
-        ga.FF = c->bufs[c->buf_FF].ptr; ga.kbFF = c->bufs[c->buf_FF].nkb;
-        ga.mask = c->mask;
-        c->launches += 1;
-        if (launch_gather(ga, s)) return -1;
-        // ---- per-column constants cc = [W0f feat + b0 | W2f feat + b2 | WF0f ff + bF0 | WF1f ff + bF1 | WF2f ff + bF2]
-        GemmArgs g;
-        memset(&g, 0, sizeof(g));
-        g.nseg = 1;
-        g.seg[0].base = ga.F; g.seg[0].kb_stride = ga.kbF; g.seg[0].kb_off = 0; g.seg[0].nkb = ga.kbF;
-        g.num_kb = ga.kbF;
-        g.w = P.w_colA; g.bias = P.bias_colA; g.N = C0 + C2; g.m_tiles = m_tiles; g.n_valid = ncol;
-        g.out_f32 = P.cc; g.f32_ld = CC_FLOATS; g.f32_col0 = 0;
-        if (run_gemm(c, g, 2.0 * ncol * 256.0 * (C0 + C2), s)) return -1;
-        g.seg[0].base = ga.FF; g.seg[0].kb_stride = ga.kbFF; g.seg[0].nkb = ga.kbFF;
-        g.num_kb = ga.kbFF;
-        g.w = P.w_colB; g.bias = P.bias_colB; g.N = F0 + F1 + F2;
-        g.f32_col0 = C0 + C2;
-        if (run_gemm(c, g, 2.0 * ncol * 16.0 * (F0 + F1 + F2), s)) return -1;
+        // ---- one sample per column (k = 0): feature rows + in-bounds masks of the column, then its constants
+        PointSource csrc;
+        lattice_source(csrc, R0, R1, R2, calib_inv);
+        csrc.id0 = cb * R2;
+        csrc.id_stride = R2;
+        if (chain_constants(c, csrc, ncol, calib, s)) return -1;
         // ---- the tiles of these columns
         const long long t0 = ta > cb * tpc ? ta : cb * tpc;
         const long long t1 = tb < ce * tpc ? tb : ce * tpc;
         if (t1 <= t0) continue;
         ChainArgs ca;
-        memset(&ca, 0, sizeof(ca));
-        static const bool tmap_env = !(getenv("PIFU_CHAIN_TMAP") && atoi(getenv("PIFU_CHAIN_TMAP")) == 0);
-        ca.use_tmap = (P.tmap_ok && tmap_env) ? 1 : 0;
-        ca.tm256 = P.tm256; ca.tm128 = P.tm128;
-        ca.wstream = P.wstream; ca.cc = P.cc; ca.colmask = c->mask;
-        ca.wz0 = P.wz0; ca.wz2 = P.wz2; ca.b1 = P.b1; ca.w3 = P.w3; ca.b3 = P.b3;
+        lattice_chain_args(c, ca, csrc, R0, R1, R2, calib);
         ca.tile0 = t0; ca.n_tiles = static_cast<int>(t1 - t0); ca.col0 = cb;
-        ca.R0 = R0; ca.R1 = R1; ca.R2 = R2;
-        memcpy(ca.step, ga.src.step, sizeof(ca.step));
-        memcpy(ca.bmin, ga.src.bmin, sizeof(ca.bmin));
-        memcpy(ca.cinv, ga.src.cinv, sizeof(ca.cinv));
-        memcpy(ca.cg, calib, 12 * sizeof(float));
-        ca.z_mul = c->z_mul; ca.z_div = c->z_div;
         ca.out = out + (t0 * TILE_M - id_a);
         c->launches += 1;
         static long long* trace_dev = nullptr;
@@ -576,6 +546,142 @@ int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_
             }
             trace_done = true;
         }
+    }
+    return 0;
+}
+
+void lattice_chain_args(pifu_ctx* c, ChainArgs& ca, const PointSource& src, int R0, int R1, int R2, const float* calib) {
+    ChainPlan& P = c->cplan;
+    memset(&ca, 0, sizeof(ca));
+    static const bool tmap_env = !(getenv("PIFU_CHAIN_TMAP") && atoi(getenv("PIFU_CHAIN_TMAP")) == 0);
+    ca.use_tmap = (P.tmap_ok && tmap_env) ? 1 : 0;
+    ca.tm256 = P.tm256; ca.tm128 = P.tm128;
+    ca.wstream = P.wstream; ca.cc = P.cc; ca.colmask = c->mask;
+    ca.wz0 = P.wz0; ca.wz2 = P.wz2; ca.b1 = P.b1; ca.w3 = P.w3; ca.b3 = P.b3;
+    ca.R0 = R0; ca.R1 = R1; ca.R2 = R2;
+    memcpy(ca.step, src.step, sizeof(ca.step));
+    memcpy(ca.bmin, src.bmin, sizeof(ca.bmin));
+    memcpy(ca.cinv, src.cinv, sizeof(ca.cinv));
+    memcpy(ca.cg, calib, 12 * sizeof(float));
+    ca.z_mul = c->z_mul; ca.z_div = c->z_div;
+}
+
+// one sample per segment -> cc = [W0f feat + b0 | W2f feat + b2 | WF0f ff + bF0 | WF1f ff + bF1 | WF2f ff + bF2]
+int chain_constants(pifu_ctx* c, const PointSource& src, int ncol, const float* calib, cudaStream_t s) {
+    using namespace chain;
+    ChainPlan& P = c->cplan;
+    Level& LC = c->lv[0];
+    Level& LF = c->lv[1];
+    const int m_tiles = (ncol + TILE_M - 1) / TILE_M;
+    GatherArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.src = src;
+    ga.n = ncol;
+    memcpy(ga.cg, calib, 12 * sizeof(float));
+    memcpy(ga.cl, calib, 12 * sizeof(float));
+    ga.z_mul = c->z_mul; ga.z_div = c->z_div;
+    ga.feat_c = LC.feat; ga.Hc = LC.H; ga.Wc = LC.W; ga.Cc = LC.C;
+    ga.F = c->bufs[c->buf_F].ptr; ga.kbF = c->bufs[c->buf_F].nkb;
+    ga.feat_f = LF.feat; ga.Hf = LF.H; ga.Wf = LF.W; ga.Cf = LF.C;
+    ga.FF = c->bufs[c->buf_FF].ptr; ga.kbFF = c->bufs[c->buf_FF].nkb;
+    ga.mask = c->mask;
+    c->launches += 1;
+    if (launch_gather(ga, s)) return -1;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.nseg = 1;
+    g.seg[0].base = ga.F; g.seg[0].kb_stride = ga.kbF; g.seg[0].kb_off = 0; g.seg[0].nkb = ga.kbF;
+    g.num_kb = ga.kbF;
+    g.w = P.w_colA; g.bias = P.bias_colA; g.N = C0 + C2; g.m_tiles = m_tiles; g.n_valid = ncol;
+    g.out_f32 = P.cc; g.f32_ld = CC_FLOATS; g.f32_col0 = 0;
+    if (run_gemm(c, g, 2.0 * ncol * 256.0 * (C0 + C2), s)) return -1;
+    g.seg[0].base = ga.FF; g.seg[0].kb_stride = ga.kbFF; g.seg[0].nkb = ga.kbFF;
+    g.num_kb = ga.kbFF;
+    g.w = P.w_colB; g.bias = P.bias_colB; g.N = F0 + F1 + F2;
+    g.f32_col0 = C0 + C2;
+    return run_gemm(c, g, 2.0 * ncol * 16.0 * (F0 + F1 + F2), s);
+}
+
+int grow_cc(ChainPlan& P, long long cols) {
+    if (P.cc_cols >= cols) return 0;
+    if (P.cc) { cudaFree(P.cc); P.cc = nullptr; P.cc_cols = 0; }
+    PIFU_CUDA(cudaMalloc(&P.cc, static_cast<size_t>(cols) * chain::CC_FLOATS * sizeof(float)));
+    P.cc_cols = static_cast<int>(cols);
+    return 0;
+}
+
+int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const float* cl, const float* cg,
+              const QueryOut& o, cudaStream_t s);
+
+// A sorted list of lattice ids (an octree frontier) through the chain kernel's run-list form.  The
+// list is cut into chunks of `chunk` rows; the runs of one chunk are its segments.  A chunk whose
+// runs are too short to pay for their constants (fewer than 4 rows per run) takes the per-layer path.
+constexpr int CHAIN_MIN_RUN = 4;
+int run_chain_ids(pifu_ctx* c, int R0, int R1, int R2, const long long* ids, long long n, const float* calib,
+                  const double* calib_inv, float* out, cudaStream_t s) {
+    using namespace chain;
+    ChainPlan& P = c->cplan;
+    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M / RUN_BLOCK_ROWS * RUN_BLOCK_ROWS;
+    const long long nblocks = (n + RUN_BLOCK_ROWS - 1) / RUN_BLOCK_ROWS;
+    const int bpc = static_cast<int>(chunk / RUN_BLOCK_ROWS);
+    if (P.cap_blocks < nblocks) {
+        if (P.block_heads) { cudaFree(P.block_heads); P.block_heads = nullptr; P.cap_blocks = 0; }
+        PIFU_CUDA(cudaMalloc(&P.block_heads, static_cast<size_t>(nblocks) * sizeof(uint32_t)));
+        P.cap_blocks = nblocks;
+    }
+    if (P.cap_rows < chunk) {
+        if (P.rowseg) { cudaFree(P.rowseg); P.rowseg = nullptr; }
+        if (P.seg_ids) { cudaFree(P.seg_ids); P.seg_ids = nullptr; }
+        P.cap_rows = 0;
+        PIFU_CUDA(cudaMalloc(&P.rowseg, static_cast<size_t>(chunk) * sizeof(int)));
+        PIFU_CUDA(cudaMalloc(&P.seg_ids, static_cast<size_t>(chunk) * sizeof(long long)));
+        P.cap_rows = chunk;
+    }
+    c->launches += 1;
+    if (launch_run_heads(ids, n, R2, chunk, P.block_heads, s)) return -1;
+    P.heads_host.resize(static_cast<size_t>(nblocks));
+    PIFU_CUDA(cudaMemcpyAsync(P.heads_host.data(), P.block_heads, static_cast<size_t>(nblocks) * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, s));
+    PIFU_CUDA(cudaStreamSynchronize(s));
+    // segments per chunk; the constants buffer holds the largest chunk that takes the chain
+    std::vector<long long> nseg;
+    long long cc_need = 0;
+    for (long long b = 0; b < nblocks; b += bpc) {
+        long long t = 0;
+        for (long long k = b; k < nblocks && k < b + bpc; ++k) t += P.heads_host[static_cast<size_t>(k)];
+        const long long rows = (n - b * RUN_BLOCK_ROWS) < chunk ? (n - b * RUN_BLOCK_ROWS) : chunk;
+        nseg.push_back(t);
+        if (t * CHAIN_MIN_RUN <= rows && t > cc_need) cc_need = t;
+    }
+    if (grow_cc(P, cc_need)) return -1;
+    PointSource src;
+    lattice_source(src, R0, R1, R2, calib_inv);
+    for (size_t ci = 0; ci < nseg.size(); ++ci) {
+        const long long row0 = static_cast<long long>(ci) * chunk;
+        const int m = static_cast<int>(n - row0 < chunk ? n - row0 : chunk);
+        if (nseg[ci] * CHAIN_MIN_RUN > m) {
+            src.ids = ids + row0;
+            QueryOut o;
+            o.pred = out + row0;
+            if (run_chunk(c, 2, src, m, calib, calib, o, s)) return -1;
+            continue;
+        }
+        const int ns = static_cast<int>(nseg[ci]);
+        c->launches += 1;
+        if (launch_run_assign(ids, row0, m, R2, chunk, P.block_heads + ci * bpc, P.rowseg, P.seg_ids, s)) return -1;
+        src.ids = P.seg_ids;
+        if (chain_constants(c, src, ns, calib, s)) return -1;
+        ChainArgs ca;
+        lattice_chain_args(c, ca, src, R0, R1, R2, calib);
+        ca.n_tiles = (m + TILE_M - 1) / TILE_M;
+        ca.ids = ids + row0;
+        ca.rowseg = P.rowseg;
+        ca.n_rows = m;
+        ca.out = out + row0;
+        c->launches += 1;
+        const double flops = static_cast<double>(m) * 2.0 *
+                             (257.0 * C0 + 1.0 * C0 * C1 + 769.0 * C2 + 272.0 * F0 + 784.0 * F1 + 528.0 * F2 + F2);
+        if (run_timed(c, 2, flops, s, [&]() { return launch_chain(ca, c->num_sms, s); })) return -1;
     }
     return 0;
 }
@@ -642,6 +748,9 @@ namespace pifu {
 // used by octree.cu: evaluate `n` lattice ids (device list) into out (device fp32 [n])
 int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
              const float* calib, const double* calib_inv, float* out, cudaStream_t s) {
+    if (c->cplan.rows_enabled && n >= TILE_M && c->chunk_tiles * TILE_M >= RUN_BLOCK_ROWS &&
+        chain_eligible(c, levels, TILE_M, calib, calib_inv))
+        return run_chain_ids(c, R0, R1, R2, ids, n, calib, calib_inv, out, s);
     PointSource src;
     lattice_source(src, R0, R1, R2, calib_inv);
     const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
@@ -683,6 +792,7 @@ int pifu_create(int device, pifu_ctx** out) {
     c->chunk_tiles = 16 * c->num_sms;      // 16 waves per layer launch amortise pipeline fill/drain (measured)
     if (const char* e = getenv("PIFU_CHUNK_TILES")) { int v = atoi(e); if (v > 0) c->chunk_tiles = v; }
     if (const char* e = getenv("PIFU_CHAIN")) c->cplan.enabled = atoi(e) != 0;
+    if (const char* e = getenv("PIFU_CHAIN_ROWS")) c->cplan.rows_enabled = atoi(e) != 0;     // A/B measurements
     if (const char* e = getenv("PIFU_GEMM_IMPL")) {
         if (!strcmp(e, "simt")) c->gemm_impl = PIFU_GEMM_SIMT;
         if (!strcmp(e, "tc1")) c->gemm_impl = PIFU_GEMM_TCGEN05_1CTA;
@@ -773,7 +883,8 @@ int pifu_profile_read_kind(pifu_ctx* c, int kind, long long* launches, double* t
 
 int pifu_set_chain(pifu_ctx* c, int enabled) {
     if (!c) { set_error("null context"); return -1; }
-    c->cplan.enabled = enabled != 0;
+    c->cplan.enabled = enabled != 0;              // 0: per-layer kernels only; 1: both chain forms; 2: lattice form only
+    c->cplan.rows_enabled = enabled == 1;
     return 0;
 }
 

@@ -115,6 +115,11 @@ __device__ __forceinline__ float lattice_z(const ChainArgs& a, long long id) {
         if (a.trace != nullptr && blockIdx.x == 0 && (it) < 8) a.trace[(it) * 64 + (i)] = clock64(); \
     } while (0)
 
+// ROWS = false: tile t is 128 consecutive points of ONE lattice column, its constants arrive by TMA in shared memory.
+// ROWS = true (run-list form, octree frontiers): row p of the launch is lattice point a.ids[p]; consecutive rows of
+// one column form a run and share cc[a.rowseg[p]]; every CUDA-core thread reads its own row's constants from
+// global memory (rows of one run hit the same 128-byte lines, so a warp's load is a handful of L1 wavefronts).
+template <bool ROWS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t rank = ptx::cluster_ctarank();
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const uint32_t ready_a = ptx::smem_u32(smem + OFF_TMEM + 8);     // scout -> issuer token count
     float* s_z = reinterpret_cast<float*>(smem + OFF_Z);
+    int* s_seg = reinterpret_cast<int*>(smem + OFF_C0);            // ROWS: segment of the rows, [2][128] (the c0 slot is unused)
     float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
 
     if (warp == 1 && lane == 0) {
@@ -449,24 +455,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         };
         auto col_of = [&](int t) { return ((a.tile0 + t) * TILE_M) / a.R2 - a.col0; };
         auto load_g1 = [&](int t) {
+            if constexpr (ROWS) return;
             ptx::mbar_arrive_expect_tx(&g_full[0], C0 * 4);
             ptx::bulk_g2s(smem + OFF_C0, a.cc + col_of(t) * CC_FLOATS, C0 * 4, &g_full[0]);
         };
         auto load_g2 = [&](int t) {
+            if constexpr (ROWS) return;
             ptx::mbar_arrive_expect_tx(&g_full[1], G2_FLOATS * 4);
             ptx::bulk_g2s(smem + OFF_G2, a.cc + col_of(t) * CC_FLOATS + C0, G2_FLOATS * 4, &g_full[1]);
+        };
+        auto wait_g = [&](int i) { if constexpr (!ROWS) wait_bit(g_full, gph, i); };
+        // rows of tile t: z feature (and, ROWS, the segment) of row `atid` into the staging arrays
+        auto stage_rows = [&](int t, float* zdst, int* sdst) {
+            if (atid < TILE_M) {
+                if constexpr (ROWS) {
+                    long long p = static_cast<long long>(t) * TILE_M + atid;
+                    if (p >= a.n_rows) p = a.n_rows - 1;             // padding rows repeat the last point
+                    zdst[atid] = lattice_z(a, __ldg(a.ids + p));
+                    sdst[atid] = __ldg(a.rowseg + p);
+                } else {
+                    zdst[atid] = lattice_z(a, (a.tile0 + t) * TILE_M + atid);
+                }
+            }
+        };
+        const float* crow[4] = {a.cc, a.cc, a.cc, a.cc};      // ROWS: constants of the four rows gen() writes
+        const float* myc = a.cc;                              // ROWS: constants of this thread's drain row
+        int myseg = 0;
+        auto ldg128 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+        auto prefetch_row = [&](const float* p) {             // the 128-byte line a later emit() of this thread reads
+            if constexpr (ROWS) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
         };
         // y0 k-block kb = leaky(c0 + wz0 * z) for channels [64 kb, 64 kb + 64) -> P slot kb & 3
         auto gen = [&](int kb) {
             const int s = kb & 3;
             const uint32_t slot = sP + s * SLOT;
             const uint32_t n0 = static_cast<uint32_t>(kb * KB + gchunk * 8) * 4u;
-            const float4 ca = lds128(c0_a + n0), cb = lds128(c0_a + n0 + 16);
+            float4 cra[4], crb[4];
+            if constexpr (ROWS) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { cra[i] = ldg128(crow[i] + kb * KB + gchunk * 8); crb[i] = ldg128(crow[i] + kb * KB + gchunk * 8 + 4); }
+            } else {
+                cra[0] = lds128(c0_a + n0); crb[0] = lds128(c0_a + n0 + 16);
+            }
             const float4 wa = lds128(wz0_a + n0), wb = lds128(wz0_a + n0 + 16);
             wait_bit(p_empty, pe, s);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float z = zr[i];
+                const float4 ca = cra[ROWS ? i : 0], cb = crb[ROWS ? i : 0];
                 uint4 pk;
                 pk.x = pack2_leaky(fmaf(wa.x, z, ca.x), fmaf(wa.y, z, ca.y));
                 pk.y = pack2_leaky(fmaf(wa.z, z, ca.z), fmaf(wa.w, z, ca.w));
@@ -478,11 +514,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         };
         // 32 accumulator columns of this thread's row (already in registers) ->
         // leaky(acc + bias (+ wz * z)) -> fp16 -> chunks 4 hh .. 4 hh + 3 of the row in `slot`
-        auto emit = [&](const uint32_t (&v)[32], int c0, uint32_t slot, uint32_t bias_a, uint32_t wz_a, float z) {
+        auto emit = [&](const uint32_t (&v)[32], int c0, uint32_t slot, uint32_t bias_a, const float* bias_g, uint32_t wz_a, float z) {
+            float4 gb[8];
+            if (ROWS && bias_g != nullptr) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) gb[g] = ldg128(bias_g + c0 + 4 * g);
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float x[8];
-                const float4 ba = lds128(bias_a + (c0 + 8 * g) * 4), bb = lds128(bias_a + (c0 + 8 * g + 4) * 4);
+                float4 ba, bb;
+                if (ROWS && bias_g != nullptr) { ba = gb[2 * g]; bb = gb[2 * g + 1]; }
+                else { ba = lds128(bias_a + (c0 + 8 * g) * 4); bb = lds128(bias_a + (c0 + 8 * g + 4) * 4); }
                 x[0] = __uint_as_float(v[8 * g + 0]) + ba.x; x[1] = __uint_as_float(v[8 * g + 1]) + ba.y;
                 x[2] = __uint_as_float(v[8 * g + 2]) + ba.z; x[3] = __uint_as_float(v[8 * g + 3]) + ba.w;
                 x[4] = __uint_as_float(v[8 * g + 4]) + bb.x; x[5] = __uint_as_float(v[8 * g + 5]) + bb.y;
@@ -502,7 +545,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         // the TMEM load of k-block j + 1 is in flight while k-block j is converted
         int it = 0;
         auto drain_half = [&](int H, uint32_t slot0, uint64_t* empty_bar, uint32_t& empty_bits, uint32_t full_addr,
-                              uint32_t bias_a, uint32_t wz_a, float z, int ti) {
+                              uint32_t bias_a, int cc_off, uint32_t wz_a, float z, int ti) {
+            // cc_off >= 0: the bias is the per-column constant block at cc_off (shared memory copy at bias_a,
+            // or, ROWS, this thread's row of cc in global memory); cc_off < 0: a plain bias vector at bias_a
+            const float* bias_g = (ROWS && cc_off >= 0) ? myc + cc_off : nullptr;
+            if (ROWS && cc_off >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) prefetch_row(bias_g + 64 * j + 32 * hh);
+            }
             wait_bit(acc_full, af, H);
             if (atid == 0) CHAIN_TRACE(it, ti);
             ptx::tc_fence_after();
@@ -515,7 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 if (j < 3) ptx::tmem_ld32(t0 + 64 * (j + 1), v[(j + 1) & 1]);
                 else release_acc(H);                     // every column of the half is in registers
                 wait_bit(empty_bar, empty_bits, j);
-                emit(v[j & 1], 64 * j + 32 * hh, slot0 + j * SLOT, bias_a, wz_a, z);
+                emit(v[j & 1], 64 * j + 32 * hh, slot0 + j * SLOT, bias_a, bias_g, wz_a, z);
                 signal(full_addr + j * 8);
             }
             if (atid == 0) CHAIN_TRACE(it, ti + 1);
@@ -524,11 +574,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         if (first < n_pairs) {
             const int t0 = tile_of(first);
             if (atid == 0) { load_g1(t0); load_g2(t0); }
-            if (atid < TILE_M) s_z[atid] = lattice_z(a, (a.tile0 + t0) * TILE_M + atid);
+            stage_rows(t0, s_z, s_seg);
             alu_bar();
-            wait_bit(g_full, gph, 0);
+            wait_g(0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) zr[i] = s_z[grow0 + 4 * i];
+            for (int i = 0; i < 4; ++i) {
+                zr[i] = s_z[grow0 + 4 * i];
+                if constexpr (ROWS) crow[i] = a.cc + static_cast<size_t>(s_seg[grow0 + 4 * i]) * CC_FLOATS;
+            }
             for (int kb = 0; kb < 4; ++kb) gen(kb);
         }
         for (int pt = first; pt < n_pairs; pt += stride, ++it) {
@@ -539,7 +592,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             const int tn = has_next ? tile_of(pt + stride) : 0;
             float* zcur = s_z + (it & 1) * TILE_M;
             float* znext = s_z + ((it + 1) & 1) * TILE_M;
-            if (has_next && atid < TILE_M) znext[atid] = lattice_z(a, (a.tile0 + tn) * TILE_M + atid);
+            int* segnext = s_seg + ((it + 1) & 1) * TILE_M;
+            if constexpr (ROWS) {
+                myseg = s_seg[(it & 1) * TILE_M + row];
+                myc = a.cc + static_cast<size_t>(myseg) * CC_FLOATS;
+            }
+            if (has_next) stage_rows(tn, znext, segnext);
 
             // feed J01 (k-blocks 0..3 were generated ahead)
             for (int kb = 4; kb < C0 / KB; ++kb) gen(kb);
@@ -547,18 +605,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             alu_bar();                                   // c0 / z registers of this tile no longer read
             if (has_next && atid == 0) load_g1(tn);
             // J01 done -> y1 = leaky(acc + b1): Ha -> D slots (J2 starts), then Hb as J2 frees them
-            drain_half(0, sD, d_empty, de, df_addr, b1_a, 0u, 0.f, 22);
-            drain_half(1, sD, d_empty, de, df_addr, b1_a + 256 * 4, 0u, 0.f, 24);
+            drain_half(0, sD, d_empty, de, df_addr, b1_a, -1, 0u, 0.f, 22);
+            drain_half(1, sD, d_empty, de, df_addr, b1_a + 256 * 4, -1, 0u, 0.f, 24);
             // J2 done -> phi = leaky(acc + c2 + wz2 * z) into the P slots (resident until J6)
-            wait_bit(g_full, gph, 1);
-            drain_half(0, sP, p_empty, pe, pf_addr, g2_a, wz2_a, zcur[row], 26);
-            drain_half(1, sD, d_empty, de, df_addr, g2_a + C2 * 4, 0u, 0.f, 28);             // J3 -> yF0[:256]
-            drain_half(0, sD, d_empty, de, df_addr, g2_a + (C2 + 256) * 4, 0u, 0.f, 30);     // J4 -> yF0[256:]
-            drain_half(1, sD, d_empty, de, df_addr, g2_a + (C2 + F0) * 4, 0u, 0.f, 32);      // J5 -> yF1
+            wait_g(1);
+            drain_half(0, sP, p_empty, pe, pf_addr, g2_a, CC_OFF_C2, wz2_a, zcur[row], 26);
+            drain_half(1, sD, d_empty, de, df_addr, g2_a + C2 * 4, CC_OFF_F0, 0u, 0.f, 28);             // J3 -> yF0[:256]
+            drain_half(0, sD, d_empty, de, df_addr, g2_a + (C2 + 256) * 4, CC_OFF_F0 + 256, 0u, 0.f, 30);     // J4 -> yF0[256:]
+            drain_half(1, sD, d_empty, de, df_addr, g2_a + (C2 + F0) * 4, CC_OFF_F1, 0u, 0.f, 32);      // J5 -> yF1
             if (has_next) {                                      // next tile's first y0 k-blocks
-                wait_bit(g_full, gph, 0);
+                wait_g(0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) zr[i] = znext[grow0 + 4 * i];
+                for (int i = 0; i < 4; ++i) {
+                    zr[i] = znext[grow0 + 4 * i];
+                    if constexpr (ROWS) crow[i] = a.cc + static_cast<size_t>(segnext[grow0 + 4 * i]) * CC_FLOATS;
+                }
                 // two k-blocks before the head, two after: the next tile's first GEMM can start as soon as
                 // the head has emptied the accumulator, and finds its second k-block waiting
                 gen(0);
@@ -567,6 +628,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             if (atid == 0) CHAIN_TRACE(it, 34);
             // J6 done -> fused Conv1d -> 1 + sigmoid + in-bounds mask (`MLP.py:72-73`, `PIFuMRNet.py:173-174`)
             {
+                if constexpr (ROWS) { prefetch_row(myc + CC_OFF_F2 + 64 * hh); prefetch_row(myc + CC_OFF_F2 + 64 * hh + 32); }
                 wait_bit(acc_full, af, 0);
                 if (atid == 0) CHAIN_TRACE(it, 35);
                 ptx::tc_fence_after();
@@ -582,7 +644,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const int c = 64 * hh + 32 * u + 4 * g;
-                        const float4 b = lds128(cf2 + c * 4), wv = lds128(w3_a + c * 4);
+                        const float4 wv = lds128(w3_a + c * 4);
+                        float4 b;
+                        if constexpr (ROWS) b = ldg128(myc + CC_OFF_F2 + c); else b = lds128(cf2 + c * 4);
                         hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 0]) + b.x), wv.x, hacc);
                         hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 1]) + b.y), wv.y, hacc);
                         hacc = fmaf(leaky(__uint_as_float(v[u][4 * g + 2]) + b.z), wv.z, hacc);
@@ -594,8 +658,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 if (hh == 0 && live) {
                     const float logit = hacc + s_part[row] + a.b3;
                     const float p = 1.f / (1.f + expf(-logit));
-                    const bool inb = (__ldg(a.colmask + col_of(t)) >> 1) & 1;
-                    a.out[static_cast<size_t>(t) * TILE_M + row] = inb ? p : 0.f;
+                    if constexpr (ROWS) {
+                        const bool inb = (__ldg(a.colmask + myseg) >> 1) & 1;
+                        if (static_cast<long long>(t) * TILE_M + row < a.n_rows) a.out[static_cast<size_t>(t) * TILE_M + row] = inb ? p : 0.f;
+                    } else {
+                        const bool inb = (__ldg(a.colmask + col_of(t)) >> 1) & 1;
+                        a.out[static_cast<size_t>(t) * TILE_M + row] = inb ? p : 0.f;
+                    }
                 }
             }
             if (has_next) { gen(2); gen(3); }
@@ -616,12 +685,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
 
 int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s) {
     if (a.n_tiles <= 0) return 0;
-    if (a.R2 % TILE_M != 0) { set_error("chain: lattice depth %d is not a multiple of 128", a.R2); return -1; }
+    const bool rows = a.n_rows > 0;
+    if (!rows && a.R2 % TILE_M != 0) { set_error("chain: lattice depth %d is not a multiple of 128", a.R2); return -1; }
+    if (rows && (!a.ids || !a.rowseg)) { set_error("chain: run-list form without ids / segments"); return -1; }
     static bool configured[32] = {};
     int dev = 0;
     PIFU_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 31]) {
-        PIFU_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PIFU_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PIFU_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured[dev & 31] = true;
     }
     const int pairs = (a.n_tiles + 1) / 2;
@@ -641,7 +713,8 @@ int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PIFU_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, a));
+    if (rows) PIFU_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel<true>, a));
+    else PIFU_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel<false>, a));
     return 0;
 }
 

@@ -153,6 +153,11 @@ struct ChainArgs {
     float cg[12];
     float z_mul, z_div;
     float* out;               // out[t * 128 + row], t relative to tile0
+    // run-list form (n_rows > 0): the rows are arbitrary lattice points, consecutive rows that share a
+    // lattice column form a run; cc / colmask hold one entry per run ("segment") of the launch
+    const long long* ids;     // [n_rows] lattice id of each row
+    const int* rowseg;        // [n_rows] segment of each row
+    long long n_rows;
     long long* trace;         // optional [8][64] clock64 stamps of CTA 0's first tiles (PIFU_CHAIN_TRACE=1), else null
 };
 int launch_chain(const ChainArgs& a, int num_sms, cudaStream_t s);

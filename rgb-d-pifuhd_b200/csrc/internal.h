@@ -21,6 +21,12 @@ int launch_group_norm(const float* x, uint8_t* buf, int nkb, int channels, int g
 int launch_head(const ASeg* segs, int nseg, const float* w, float b, const uint8_t* mask, int mask_bit, float* out,
                 int m_tiles, int n_valid, cudaStream_t s);
 
+// runs.cu: segmentation of a sorted lattice-id list into runs of rows that share a lattice column
+constexpr int RUN_BLOCK_ROWS = 1024;
+int launch_run_heads(const long long* ids, long long n, int R2, long long chunk, uint32_t* block_heads, cudaStream_t s);
+int launch_run_assign(const long long* ids, long long row0, int m, int R2, long long chunk, const uint32_t* block_heads,
+                      int* rowseg, long long* seg_ids, cudaStream_t s);
+
 // api.cu services used by the octree driver
 int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
              const float* calib, const double* calib_inv, float* out, cudaStream_t s);

@@ -155,14 +155,16 @@ class Engine:
         return n.value, ms.value, fl.value
 
     def profile_read_kind(self, kind):
-        """-> (launches, total_ms, total_flops) of one kernel kind (0 layer kernel, 1 chain kernel)."""
+        """-> (launches, total_ms, total_flops) of one kernel kind (0 layer kernel, 1 chain kernel on lattice
+        columns, 2 chain kernel on id lists)."""
         n, ms, fl = ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
         _lib.check(self.lib.pifu_profile_read_kind(self.h, int(kind), ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
         return n.value, ms.value, fl.value
 
     def set_chain(self, enabled):
-        """Enable / disable the lattice chain kernel (eval_grid falls back to the per-layer kernels)."""
-        _lib.check(self.lib.pifu_set_chain(self.h, int(bool(enabled))))
+        """0 / False: per-layer kernels only; 1 / True: chain kernel for lattice columns (eval_grid) and for sorted
+        id lists (octree frontiers, run-list form); 2: lattice-column form only."""
+        _lib.check(self.lib.pifu_set_chain(self.h, int(enabled)))
 
     def chain_ready(self):
         return bool(self.lib.pifu_chain_ready(self.h))

@@ -103,3 +103,82 @@ def test_chain_saturated_field():
     out = eng.eval_grid(2, R, calib[0]).cpu().numpy()
     assert np.abs(out - ref).max() < 8e-3
     assert sign_agreement(out, ref) >= 0.9999
+
+
+# ---------------------------------------------------------------- run-list form (octree frontiers)
+def band_ids(R, width, seed):
+    """Sorted lattice ids of a wavy band |k - f(i, j)| < w(i, j): per column one run of 1 .. 2 width points,
+    the shape of an octree frontier around a surface (`mesh_util.py:142-149`)."""
+    R0, R1, R2 = R
+    g = np.random.default_rng(seed)
+    i, j = np.meshgrid(np.arange(R0), np.arange(R1), indexing="ij")
+    centre = R2 / 2 + 0.3 * R2 * np.sin(0.37 * i + 0.2) * np.cos(0.23 * j)
+    w = g.integers(1, width + 1, size=(R0, R1))
+    k = np.arange(R2)[None, None, :]
+    keep = np.abs(k - centre[..., None]) < w[..., None]
+    keep &= g.random((R0, R1, 1)) > 0.2                      # some columns have no points at all
+    return np.flatnonzero(keep.reshape(-1)).astype(np.int64)
+
+
+RUN_CASES = [
+    # lattice, ids, chunk tiles, calib            what it exercises
+    ((8, 8, 64), "all", None, "default"),         # short columns: two runs per tile, every run whole
+    ((16, 16, 96), "band12", None, "default"),    # runs of 1..24 rows, ragged last tile
+    ((16, 16, 96), "band12", None, "scaled"),     # some columns out of the fine bounding box (masked to 0)
+    ((24, 24, 128), "band20", 8, "default"),      # chunks of 1024 rows: runs cut at chunk boundaries, many launches
+    ((48, 48, 8), "random", None, "default"),     # ~1.3 rows per column: the chunk takes the per-layer kernels
+    ((5, 3, 64), "band3", None, "default"),       # fewer than 128 rows: per-layer path
+]
+
+
+@pytest.mark.parametrize("R,kind,tiles,calib_name", RUN_CASES, ids=[c[1] + "-" + "x".join(map(str, c[0])) + ("-" + c[3] if c[3] != "default" else "") for c in RUN_CASES])
+def test_chain_runlist_vs_oracle(setup, R, kind, tiles, calib_name):
+    prob, fine, netMR, eng = setup
+    calib = syn.default_calib() if calib_name == "default" else syn.scaled_calib()
+    netMR.query(syn.random_points(256).cuda(), calib.cuda())     # the engine is per device: re-snapshot this net's MLPs
+    total = R[0] * R[1] * R[2]
+    if kind == "all":
+        ids = np.arange(total, dtype=np.int64)
+    elif kind == "random":
+        ids = np.sort(np.random.default_rng(5).choice(total, 3000, replace=False)).astype(np.int64)
+    else:
+        ids = band_ids(R, int(kind[4:]), 11)
+    ref = orc.query_fine(fine, lattice_points(R, calib, ids), calib)[0].numpy().ravel()
+    tid = torch.from_numpy(ids)
+    if tiles:
+        eng.set_chunk_tiles(tiles)
+    try:
+        eng.set_chain(1)
+        eng.profile(True)
+        out = eng.eval_lattice_ids(2, R, tid, calib[0]).cpu().numpy()
+        n_rows_launches = eng.profile_read_kind(2)[0]
+        eng.profile(False)
+        eng.set_chain(2)
+        layer = eng.eval_lattice_ids(2, R, tid, calib[0]).cpu().numpy()
+    finally:
+        eng.set_chain(1)
+        if tiles:
+            eng.set_chunk_tiles(16 * 148)
+    expect_chain = kind not in ("random", "band3")
+    assert (n_rows_launches > 0) == expect_chain, "run-list chain %staken" % ("not " if expect_chain else "")
+    if tiles:
+        assert n_rows_launches >= -(-len(ids) // (tiles * 128)) - 1      # a short last chunk may take the per-layer path
+    assert np.abs(out - ref).max() < OCC_TOL
+    assert np.array_equal(out == 0, ref == 0)              # identical in-bounds masks
+    assert np.abs(out - layer).max() < OCC_TOL
+
+
+def test_chain_runlist_unsorted_ids(setup):
+    """Runs are found by adjacency only: an unsorted list is still evaluated point by point."""
+    prob, fine, netMR, eng = setup
+    R = (16, 16, 96)
+    calib = syn.default_calib()
+    netMR.query(syn.random_points(256).cuda(), calib.cuda())
+    ids = band_ids(R, 12, 3)
+    g = np.random.default_rng(0)
+    blocks = np.array_split(ids, 40)
+    g.shuffle(blocks)
+    ids = np.concatenate(blocks)
+    ref = orc.query_fine(fine, lattice_points(R, calib, ids), calib)[0].numpy().ravel()
+    out = eng.eval_lattice_ids(2, R, torch.from_numpy(ids), calib[0]).cpu().numpy()
+    assert np.abs(out - ref).max() < OCC_TOL
