@@ -493,6 +493,38 @@ void lattice_chain_args(pifu_ctx* c, ChainArgs& ca, const PointSource& src, int 
 int chain_constants(pifu_ctx* c, const PointSource& src, int ncol, const float* calib, cudaStream_t s);
 int grow_cc(ChainPlan& P, long long cols);
 
+// Debug aid (PIFU_CHAIN_TRACE=<form>: 1 lattice columns, 2 run lists): clock64 stamps of CTA 0's first tiles of the
+// first eligible launch (with PIFU_CHAIN_TRACE_MIN_TILES, the first launch of at least that many tiles), printed once.
+struct ChainTrace {
+    bool armed = false;
+    static long long*& dev() { static long long* p = nullptr; return p; }
+    static bool& done() { static bool d = false; return d; }
+    int begin(ChainArgs& ca, int form, cudaStream_t s) {
+        static const int want = getenv("PIFU_CHAIN_TRACE") ? atoi(getenv("PIFU_CHAIN_TRACE")) : 0;
+        static const int min_tiles = getenv("PIFU_CHAIN_TRACE_MIN_TILES") ? atoi(getenv("PIFU_CHAIN_TRACE_MIN_TILES")) : 0;
+        if (want != form || done() || ca.n_tiles < min_tiles) return 0;
+        if (!dev()) PIFU_CUDA(cudaMalloc(&dev(), 8 * 64 * sizeof(long long)));
+        PIFU_CUDA(cudaMemsetAsync(dev(), 0, 8 * 64 * sizeof(long long), s));
+        ca.trace = dev();
+        armed = true;
+        return 0;
+    }
+    int end(cudaStream_t s) {
+        if (!armed) return 0;
+        long long h[8 * 64];
+        PIFU_CUDA(cudaStreamSynchronize(s));
+        PIFU_CUDA(cudaMemcpy(h, dev(), sizeof(h), cudaMemcpyDeviceToHost));
+        for (int it = 0; it < 8; ++it) {
+            fprintf(stderr, "chain trace tile %d:", it);
+            for (int i = 0; i < 64; ++i)
+                if (h[it * 64 + i]) fprintf(stderr, " %d:%lld", i, (i >= 13 && i <= 16) ? h[it * 64 + i] : h[it * 64 + i] - h[0]);
+            fprintf(stderr, "\n");
+        }
+        done() = true;
+        return 0;
+    }
+};
+
 // lattice ids [id_a, id_b), both multiples of 128, through the chain kernel
 int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_b, const float* calib,
               const double* calib_inv, float* out, cudaStream_t s) {
@@ -523,29 +555,13 @@ int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_
         ca.tile0 = t0; ca.n_tiles = static_cast<int>(t1 - t0); ca.col0 = cb;
         ca.out = out + (t0 * TILE_M - id_a);
         c->launches += 1;
-        static long long* trace_dev = nullptr;
-        static bool trace_on = getenv("PIFU_CHAIN_TRACE") != nullptr, trace_done = false;
-        if (trace_on && !trace_done) {
-            if (!trace_dev) PIFU_CUDA(cudaMalloc(&trace_dev, 8 * 64 * sizeof(long long)));
-            PIFU_CUDA(cudaMemsetAsync(trace_dev, 0, 8 * 64 * sizeof(long long), s));
-            ca.trace = trace_dev;
-        }
+        ChainTrace tr;
+        if (tr.begin(ca, 1, s)) return -1;
         // algorithmic work: the get_preds() layer stack of every point (coarse L0-L2, fine L0-L3)
         const double flops = static_cast<double>(ca.n_tiles) * TILE_M * 2.0 *
                              (257.0 * C0 + 1.0 * C0 * C1 + 769.0 * C2 + 272.0 * F0 + 784.0 * F1 + 528.0 * F2 + F2);
         if (run_timed(c, 1, flops, s, [&]() { return launch_chain(ca, c->num_sms, s); })) return -1;
-        if (ca.trace) {                      // debug aid: print the stamps of CTA 0's first tiles, once
-            long long h[8 * 64];
-            PIFU_CUDA(cudaStreamSynchronize(s));
-            PIFU_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
-            for (int it = 0; it < 8; ++it) {
-                fprintf(stderr, "chain trace tile %d:", it);
-                for (int i = 0; i < 64; ++i)
-                    if (h[it * 64 + i]) fprintf(stderr, " %d:%lld", i, (i >= 13 && i <= 16) ? h[it * 64 + i] : h[it * 64 + i] - h[0]);
-                fprintf(stderr, "\n");
-            }
-            trace_done = true;
-        }
+        if (tr.end(s)) return -1;
     }
     return 0;
 }
@@ -681,7 +697,10 @@ int run_chain_ids(pifu_ctx* c, int R0, int R1, int R2, const long long* ids, lon
         c->launches += 1;
         const double flops = static_cast<double>(m) * 2.0 *
                              (257.0 * C0 + 1.0 * C0 * C1 + 769.0 * C2 + 272.0 * F0 + 784.0 * F1 + 528.0 * F2 + F2);
+        ChainTrace tr;
+        if (tr.begin(ca, 2, s)) return -1;
         if (run_timed(c, 2, flops, s, [&]() { return launch_chain(ca, c->num_sms, s); })) return -1;
+        if (tr.end(s)) return -1;
     }
     return 0;
 }

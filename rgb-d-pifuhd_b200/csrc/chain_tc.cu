@@ -93,10 +93,19 @@ __device__ __forceinline__ uint32_t pack2_leaky(float a, float b) {
 // DepthNormalizer feature of lattice point `id` (`mesh_util.py:12-38,59-65,70`,
 // `BasePIFuNet.py:35-38`, `DepthNormalizer.py:23`), identical arithmetic to gather.cu
 __device__ __forceinline__ float lattice_z(const ChainArgs& a, long long id) {
-    const int k = static_cast<int>(id % a.R2);
-    const long long ij = id / a.R2;
-    const int j = static_cast<int>(ij % a.R1);
-    const int i = static_cast<int>(ij / a.R1);
+    int i, j, k;
+    if (id < 0x7fffffffLL) {                     // 32-bit divisions (the 64-bit ones are ~100-instruction routines)
+        const uint32_t u = static_cast<uint32_t>(id), r2 = static_cast<uint32_t>(a.R2), r1 = static_cast<uint32_t>(a.R1);
+        const uint32_t ij = u / r2;
+        k = static_cast<int>(u - ij * r2);
+        i = static_cast<int>(ij / r1);
+        j = static_cast<int>(ij - static_cast<uint32_t>(i) * r1);
+    } else {
+        k = static_cast<int>(id % a.R2);
+        const long long ij = id / a.R2;
+        j = static_cast<int>(ij % a.R1);
+        i = static_cast<int>(ij / a.R1);
+    }
     const double c0 = __dadd_rn(__dmul_rn(a.step[0], static_cast<double>(i)), a.bmin[0]);
     const double c1 = __dadd_rn(__dmul_rn(a.step[1], static_cast<double>(j)), a.bmin[1]);
     const double c2 = __dadd_rn(__dmul_rn(a.step[2], static_cast<double>(k)), a.bmin[2]);
@@ -485,18 +494,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         auto prefetch_row = [&](const float* p) {             // the 128-byte line a later emit() of this thread reads
             if constexpr (ROWS) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
         };
-        // y0 k-block kb = leaky(c0 + wz0 * z) for channels [64 kb, 64 kb + 64) -> P slot kb & 3
-        auto gen = [&](int kb) {
+        // y0 k-blocks [kb0, kb1): k-block kb = leaky(c0 + wz0 * z) for channels [64 kb, 64 kb + 64) -> P slot kb & 3.
+        // ROWS: the constants come from global memory, four rows per thread; the loads of k-block kb + 1 are
+        // issued before k-block kb is converted, so only the first k-block of a range exposes their latency.
+        auto gen_load = [&](int kb, float4 (&ca)[4], float4 (&cb)[4]) {
+            if constexpr (ROWS) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ca[i] = ldg128(crow[i] + kb * KB + gchunk * 8); cb[i] = ldg128(crow[i] + kb * KB + gchunk * 8 + 4); }
+            } else {
+                const uint32_t n0 = static_cast<uint32_t>(kb * KB + gchunk * 8) * 4u;
+                ca[0] = lds128(c0_a + n0); cb[0] = lds128(c0_a + n0 + 16);
+            }
+        };
+        auto gen_store = [&](int kb, const float4 (&cra)[4], const float4 (&crb)[4]) {
             const int s = kb & 3;
             const uint32_t slot = sP + s * SLOT;
             const uint32_t n0 = static_cast<uint32_t>(kb * KB + gchunk * 8) * 4u;
-            float4 cra[4], crb[4];
-            if constexpr (ROWS) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { cra[i] = ldg128(crow[i] + kb * KB + gchunk * 8); crb[i] = ldg128(crow[i] + kb * KB + gchunk * 8 + 4); }
-            } else {
-                cra[0] = lds128(c0_a + n0); crb[0] = lds128(c0_a + n0 + 16);
-            }
             const float4 wa = lds128(wz0_a + n0), wb = lds128(wz0_a + n0 + 16);
             wait_bit(p_empty, pe, s);
 #pragma unroll
@@ -512,14 +525,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             }
             signal(pf_addr + s * 8);
         };
+        auto gen_range = [&](int kb0, int kb1) {
+            if constexpr (ROWS) {
+                float4 ca[2][4], cb[2][4];
+                gen_load(kb0, ca[0], cb[0]);
+#pragma unroll 2
+                for (int kb = kb0; kb < kb1; kb += 2) {
+                    if (kb + 1 < kb1) gen_load(kb + 1, ca[1], cb[1]);
+                    gen_store(kb, ca[0], cb[0]);
+                    if (kb + 1 < kb1) {
+                        if (kb + 2 < kb1) gen_load(kb + 2, ca[0], cb[0]);
+                        gen_store(kb + 1, ca[1], cb[1]);
+                    }
+                }
+            } else {
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    float4 ca[4], cb[4];
+                    gen_load(kb, ca, cb);
+                    gen_store(kb, ca, cb);
+                }
+            }
+        };
         // 32 accumulator columns of this thread's row (already in registers) ->
         // leaky(acc + bias (+ wz * z)) -> fp16 -> chunks 4 hh .. 4 hh + 3 of the row in `slot`
-        auto emit = [&](const uint32_t (&v)[32], int c0, uint32_t slot, uint32_t bias_a, const float* bias_g, uint32_t wz_a, float z) {
-            float4 gb[8];
-            if (ROWS && bias_g != nullptr) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) gb[g] = ldg128(bias_g + c0 + 4 * g);
-            }
+        auto emit = [&](const uint32_t (&v)[32], int c0, uint32_t slot, uint32_t bias_a, const float* bias_g, const float4 (&gb)[8],
+                        uint32_t wz_a, float z) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float x[8];
@@ -561,11 +591,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             ptx::tmem_ld32(t0, v[0]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                float4 gb[8];
+                if (ROWS && bias_g != nullptr) {         // this row's constants: in flight while the TMEM load lands
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) gb[g] = ldg128(bias_g + 64 * j + 32 * hh + 4 * g);
+                }
                 ptx::tmem_ld_wait();
                 if (j < 3) ptx::tmem_ld32(t0 + 64 * (j + 1), v[(j + 1) & 1]);
                 else release_acc(H);                     // every column of the half is in registers
                 wait_bit(empty_bar, empty_bits, j);
-                emit(v[j & 1], 64 * j + 32 * hh, slot0 + j * SLOT, bias_a, bias_g, wz_a, z);
+                emit(v[j & 1], 64 * j + 32 * hh, slot0 + j * SLOT, bias_a, bias_g, gb, wz_a, z);
                 signal(full_addr + j * 8);
             }
             if (atid == 0) CHAIN_TRACE(it, ti + 1);
@@ -580,9 +615,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 zr[i] = s_z[grow0 + 4 * i];
-                if constexpr (ROWS) crow[i] = a.cc + static_cast<size_t>(s_seg[grow0 + 4 * i]) * CC_FLOATS;
+                if constexpr (ROWS) {
+                    crow[i] = a.cc + static_cast<size_t>(s_seg[grow0 + 4 * i]) * CC_FLOATS;
+                    prefetch_row(crow[i] + gchunk * 8);
+                    prefetch_row(crow[i] + KB + gchunk * 8);
+                }
             }
-            for (int kb = 0; kb < 4; ++kb) gen(kb);
+            gen_range(0, 4);
         }
         for (int pt = first; pt < n_pairs; pt += stride, ++it) {
             if (atid == 0) CHAIN_TRACE(it, 20);
@@ -600,7 +639,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             if (has_next) stage_rows(tn, znext, segnext);
 
             // feed J01 (k-blocks 0..3 were generated ahead)
-            for (int kb = 4; kb < C0 / KB; ++kb) gen(kb);
+            gen_range(4, C0 / KB);
             if (atid == 0) CHAIN_TRACE(it, 21);
             alu_bar();                                   // c0 / z registers of this tile no longer read
             if (has_next && atid == 0) load_g1(tn);
@@ -612,6 +651,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
             drain_half(0, sP, p_empty, pe, pf_addr, g2_a, CC_OFF_C2, wz2_a, zcur[row], 26);
             drain_half(1, sD, d_empty, de, df_addr, g2_a + C2 * 4, CC_OFF_F0, 0u, 0.f, 28);             // J3 -> yF0[:256]
             drain_half(0, sD, d_empty, de, df_addr, g2_a + (C2 + 256) * 4, CC_OFF_F0 + 256, 0u, 0.f, 30);     // J4 -> yF0[256:]
+            if (ROWS && has_next) {                              // next tile's first two c0 k-blocks on their way into L1
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* nx = a.cc + static_cast<size_t>(segnext[grow0 + 4 * i]) * CC_FLOATS + gchunk * 8;
+                    prefetch_row(nx);
+                    prefetch_row(nx + KB);
+                }
+            }
             drain_half(1, sD, d_empty, de, df_addr, g2_a + (C2 + F0) * 4, CC_OFF_F1, 0u, 0.f, 32);      // J5 -> yF1
             if (has_next) {                                      // next tile's first y0 k-blocks
                 wait_g(0);
@@ -622,8 +669,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                 }
                 // two k-blocks before the head, two after: the next tile's first GEMM can start as soon as
                 // the head has emptied the accumulator, and finds its second k-block waiting
-                gen(0);
-                gen(1);
+                gen_range(0, 2);
             }
             if (atid == 0) CHAIN_TRACE(it, 34);
             // J6 done -> fused Conv1d -> 1 + sigmoid + in-bounds mask (`MLP.py:72-73`, `PIFuMRNet.py:173-174`)
@@ -667,7 +713,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
                     }
                 }
             }
-            if (has_next) { gen(2); gen(3); }
+            if (has_next) gen_range(2, 4);
             alu_bar();                                   // G2 constants / s_part of this tile consumed
             if (atid == 0) CHAIN_TRACE(it, 36);
             if (has_next && atid == 0) load_g2(tn);

@@ -50,15 +50,45 @@ void octree_free(OctreeState* s) {
 
 namespace {
 
-__global__ void init_kernel(double* sdf, uint8_t* todo, int R0, int R1, int R2) {
-    const long long n = static_cast<long long>(R0) * R1 * R2;
-    for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n;
-         v += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(v % R2);
-        const int j = static_cast<int>((v / R2) % R1);
-        const int i = static_cast<int>(v / (static_cast<long long>(R2) * R1));
-        sdf[v] = 0.0;
-        todo[v] = (i < R0 - 1 && j < R1 - 1 && k < R2 - 1) ? 1 : 0;      // `mesh_util.py:134-135`
+// `notprocessed` (`mesh_util.py:134-135`): everything but the last plane of each axis.  One thread per 4 voxels
+// of a lattice row.
+__global__ void init_todo_kernel(uint8_t* __restrict__ todo, int R0, int R1, int R2, int quads) {
+    const long long n = static_cast<long long>(R0) * R1 * quads;
+    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (t >= n) return;
+    const int qk = static_cast<int>(t % quads);
+    const long long ij = t / quads;
+    const int j = static_cast<int>(ij % R1);
+    const int i = static_cast<int>(ij / R1);
+    const bool row_ok = i < R0 - 1 && j < R1 - 1;
+    const int k0 = 4 * qk;
+    const long long v0 = ij * R2 + k0;
+    uint32_t w = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (row_ok && k0 + q < R2 - 1) w |= 1u << (8 * q);
+    if ((R2 & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(todo + v0) = w;
+    } else {
+        for (int q = 0; q < 4 && k0 + q < R2; ++q) todo[v0 + q] = (w >> (8 * q)) & 1u;
+    }
+}
+
+// The field only has to start at 0.0 where the octree never writes: the last plane of each axis (`:135`;
+// those planes stay 0.0 in the reference's result and can be read as cell corners when R - 1 is a multiple
+// of the stride).  Every other voxel is evaluated or filled before anything reads it: a level's corners are
+// stride-lattice points, each either processed earlier or in this level's frontier, and the last level
+// evaluates all that is left.
+__global__ void zero_last_planes_kernel(double* __restrict__ sdf, int R0, int R1, int R2) {
+    const long long a = static_cast<long long>(R1) * R2, b = static_cast<long long>(R0) * R2, c = static_cast<long long>(R0) * R1;
+    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (t < a) {
+        sdf[static_cast<long long>(R0 - 1) * a + t] = 0.0;
+    } else if (t < a + b) {
+        const long long u = t - a;
+        sdf[((u / R2) * R1 + (R1 - 1)) * R2 + u % R2] = 0.0;
+    } else if (t < a + b + c) {
+        sdf[(t - a - b) * R2 + (R2 - 1)] = 0.0;
     }
 }
 
@@ -166,20 +196,21 @@ __global__ void cells_kernel(const double* __restrict__ sdf, const uint8_t* __re
     mid[c] = 0.5 * (lo + hi);
 }
 
-// One thread per run of `step` voxels (i, j, ck*step .. ck*step + step - 1): they share their
-// candidate cells, except that the run's first voxel may also lie on the high face of cell ck - 1.
-__global__ void fill_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo, const uint8_t* __restrict__ skip,
-                            const double* __restrict__ mid, int step, int c0, int c1, int c2,
-                            int R0, int R1, int R2, int runs) {
-    const long long n = static_cast<long long>(R0) * R1 * runs;
-    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (t >= n) return;
-    const int ck = static_cast<int>(t % runs);
-    const int j = static_cast<int>((t / runs) % R1);
-    const int i = static_cast<int>(t / (static_cast<long long>(runs) * R1));
+// One thread per 4 consecutive voxels of a lattice row (i, j, 4 qk .. 4 qk + 3), so a warp's stores cover
+// 1 KiB of the float64 field contiguously.  The voxels of one run of `step` share their candidate cells,
+// except that a run's first voxel may also lie on the high face of cell ck - 1.
+__global__ void __launch_bounds__(256) fill_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo,
+                                                   const uint8_t* __restrict__ skip, const double* __restrict__ mid, int step,
+                                                   int shift, int c0, int c1, int c2, int R0, int R1, int R2, int quads) {
+    // grid (quads, rows j, planes i): no index divisions; `shift` >= 0 when step == 1 << shift
+    const int qk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = blockIdx.z;
+    if (qk >= quads || j >= R1) return;
+    const long long ij = static_cast<long long>(i) * R1 + j;
     // the (x, y) candidates in descending lexicographic order: high cell first on each axis
-    const int hi_i = i / step, hi_j = j / step;
-    const bool two_i = (i % step) == 0, two_j = (j % step) == 0;
+    const int hi_i = shift >= 0 ? i >> shift : i / step, hi_j = shift >= 0 ? j >> shift : j / step;
+    const bool two_i = i - hi_i * step == 0, two_j = j - hi_j * step == 0;
     long long rowc[4];
     bool rok[4];
 #pragma unroll
@@ -189,27 +220,52 @@ __global__ void fill_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo
         rok[m] = (oi == 0 || two_i) && (oj == 0 || two_j) && ci >= 0 && ci < c0 && cj >= 0 && cj < c1;
         rowc[m] = (static_cast<long long>(ci) * c1 + cj) * c2;
     }
-    const bool hi_ok = ck < c2, lo_ok = ck >= 1 && ck - 1 < c2;
-    // voxels 1 .. step-1 of the run: only cell ck along z
-    int hit_rest = -1;
-    if (hi_ok) {
+    const int k0 = 4 * qk;
+    const long long v0 = ij * R2 + k0;
+    double val[4];
+    uint32_t hit_mask = 0;
+    int rest_ck = -1;
+    long long rest_hit = -1;
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
-            if (hit_rest < 0 && rok[m] && skip[rowc[m] + ck]) hit_rest = m;
-    }
-    // voxel 0: for each (x, y) candidate, cell ck then cell ck - 1
-    long long hit0 = -1;
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + q;
+        if (k >= R2) break;
+        const int ck = shift >= 0 ? k >> shift : k / step;
+        const bool first = k - ck * step == 0;
+        const bool hi_ok = ck < c2, lo_ok = ck >= 1 && ck - 1 < c2;
+        long long hit = -1;
+        if (first) {
+            // for each (x, y) candidate, cell ck then cell ck - 1
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        if (hit0 >= 0 || !rok[m]) continue;
-        if (hi_ok && skip[rowc[m] + ck]) hit0 = rowc[m] + ck;
-        else if (lo_ok && skip[rowc[m] + ck - 1]) hit0 = rowc[m] + ck - 1;
+            for (int m = 0; m < 4; ++m) {
+                if (hit >= 0 || !rok[m]) continue;
+                if (hi_ok && skip[rowc[m] + ck]) hit = rowc[m] + ck;
+                else if (lo_ok && skip[rowc[m] + ck - 1]) hit = rowc[m] + ck - 1;
+            }
+        } else {
+            // voxels 1 .. step-1 of a run: only cell ck along z, the same for the whole run
+            if (ck != rest_ck) {
+                rest_ck = ck;
+                rest_hit = -1;
+                if (hi_ok) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (rest_hit < 0 && rok[m] && skip[rowc[m] + ck]) rest_hit = rowc[m] + ck;
+                }
+            }
+            hit = rest_hit;
+        }
+        if (hit >= 0) { val[q] = mid[hit]; hit_mask |= 1u << q; }
     }
-    const long long v0 = (static_cast<long long>(i) * R1 + j) * R2 + static_cast<long long>(ck) * step;
-    if (hit0 >= 0) { sdf[v0] = mid[hit0]; todo[v0] = 0; }
-    if (hit_rest >= 0) {
-        const double val = mid[rowc[hit_rest] + ck];
-        for (int q = 1; q < step && ck * step + q < R2; ++q) { sdf[v0 + q] = val; todo[v0 + q] = 0; }
+    if (hit_mask == 0) return;
+    if (hit_mask == 0xFu && (v0 & 3) == 0) {
+        *reinterpret_cast<double2*>(sdf + v0) = make_double2(val[0], val[1]);
+        *reinterpret_cast<double2*>(sdf + v0 + 2) = make_double2(val[2], val[3]);
+        *reinterpret_cast<uint32_t*>(todo + v0) = 0u;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (hit_mask & (1u << q)) { sdf[v0 + q] = val[q]; todo[v0 + q] = 0; }
     }
 }
 
@@ -248,9 +304,17 @@ int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double thres
     if (grow(&st->todo, &capv, st->voxels)) return -1;
     st->cap_vox = capv;
     if (!st->total_dev) PIFU_CUDA(cudaMalloc(&st->total_dev, 2 * sizeof(unsigned long long)));
-    init_kernel<<<4096, 256, 0, s>>>(st->sdf, st->todo, R0, R1, R2);
+    const int quads = ceil_div(R2, 4);
+    init_todo_kernel<<<ceil_div(static_cast<long long>(R0) * R1 * quads, 256), 256, 0, s>>>(st->todo, R0, R1, R2, quads);
+    if (st->step > 0) {
+        const long long planes = static_cast<long long>(R1) * R2 + static_cast<long long>(R0) * R2 + static_cast<long long>(R0) * R1;
+        zero_last_planes_kernel<<<ceil_div(planes, 256), 256, 0, s>>>(st->sdf, R0, R1, R2);
+    } else {
+        // resolution < init_resolution: the reference's loop never runs and the field stays all zero (`:138-140`)
+        PIFU_CUDA(cudaMemsetAsync(st->sdf, 0, static_cast<size_t>(st->voxels) * sizeof(double), s));
+    }
     PIFU_CUDA(cudaGetLastError());
-    ctx_count_launch(c, 1);
+    ctx_count_launch(c, 2);
     st->frontier = 0;
     return 0;
 }
@@ -312,9 +376,16 @@ int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStre
             st->cap_cells = cap;
             cells_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(st->sdf, st->todo, step, c0, c1, c2, st->R[1], st->R[2],
                                                           st->threshold, st->skip, st->mid);
-            const int runs = ceil_div(st->R[2], step);
-            fill_kernel<<<ceil_div(static_cast<long long>(st->R[0]) * st->R[1] * runs, 256), 256, 0, s>>>(
-                st->sdf, st->todo, st->skip, st->mid, step, c0, c1, c2, st->R[0], st->R[1], st->R[2], runs);
+            const int quads = ceil_div(st->R[2], 4);
+            int shift = -1;
+            for (int b = 0; b < 30; ++b) if (step == (1 << b)) shift = b;
+            int tx = 32;
+            while (tx < quads && tx < 256) tx *= 2;
+            const dim3 blk(tx, 256 / tx, 1);
+            if (st->R[0] > 65535 || st->R[1] > 65535) { set_error("octree: resolution above 65535"); return -1; }
+            const dim3 grd(ceil_div(quads, tx), ceil_div(st->R[1], blk.y), st->R[0]);
+            fill_kernel<<<grd, blk, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, step, shift, c0, c1, c2,
+                                           st->R[0], st->R[1], st->R[2], quads);
             ctx_count_launch(c, 2);
         }
     }

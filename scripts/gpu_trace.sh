@@ -1,0 +1,3 @@
+#!/bin/bash
+PIFU_CHAIN_TRACE=2 PIFU_CHAIN_TRACE_MIN_TILES=2000 timeout 300 python scripts/recon_phases.py 512 2>&1 | grep -E "chain trace tile [3-5]|rep 3|step 8" | tail -6
+timeout 300 python -m pytest tests/test_chain_gpu.py -m gpu -q --no-header -x 2>&1 | tail -2
