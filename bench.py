@@ -201,7 +201,7 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
         l0 = eng.launch_count()
         verts, faces, normals, values = eng.marching_cubes(field, 0.5)
         ev[2].record()
-        host = [t.cpu() for t in (verts, faces, normals, values)]
+        host = mesh_util._to_host(verts, faces, normals, values)       # pinned, as reconstruction() does
         ev[3].record()
         torch.cuda.synchronize(dev)
         mc_ms = ev[1].elapsed_time(ev[2])
@@ -230,6 +230,35 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
                                  "layer_kernel_launches": n0, "layer_kernel_ms": ms0}
         out[mode] = d
         del field, verts, faces, normals, values, host
+    return out
+
+
+def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3):
+    """The same figure at N > 1 (one rank per GPU): dense lattices are cut into slabs along axis 0, an octree
+    level's frontier into equal shares; every rank extracts the iso-surface of its own slab after one halo
+    exchange and the fragments are gathered on rank 0 (pifu_b200.dist).  Wall clock between barriers, best of
+    `reps`; every rank returns the same dict."""
+    import torch.distributed as dist
+    from pifu_b200 import mesh_util
+    cal = calib.to(dev)
+    out = {"resolution": res, "ranks": dist.get_world_size()}
+    for mode in ("octree", "dense"):
+        best, shape = None, None
+        for _ in range(reps + 1):
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            mesh = mesh_util.reconstruction(netMR, dev, cal, res, None, None, thresh=0.5,
+                                            use_octree=(mode == "octree"), num_samples=5000)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+            if mesh is not None and mesh != -1:
+                shape = (len(mesh[0]), len(mesh[1]))
+        t = torch.tensor([best], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[mode] = {"latency_ms": float(t.item()), "verts": shape[0] if shape else None, "faces": shape[1] if shape else None}
     return out
 
 
@@ -413,6 +442,12 @@ def main():
         torch.cuda.empty_cache()
         _, netMR2, eng2, calib2 = build_mesh_problem(dev)
         mesh = mesh_latency(netMR2, eng2, calib2, dev, 512, 3)
+
+    if world > 1 and not args.no_mesh:
+        del flush, slab, gathered
+        torch.cuda.empty_cache()
+        _, netMR2, eng2, calib2 = build_mesh_problem(dev)        # seeded: identical on every rank
+        mesh = mesh_latency_sharded(netMR2, calib2, dev, 512, 3)
 
     if rank == 0:
         print(json.dumps({

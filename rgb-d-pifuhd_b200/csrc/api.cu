@@ -629,62 +629,64 @@ int grow_cc(ChainPlan& P, long long cols) {
 int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const float* cl, const float* cg,
               const QueryOut& o, cudaStream_t s);
 
-// A sorted list of lattice ids (an octree frontier) through the chain kernel's run-list form.  The
-// list is cut into chunks of `chunk` rows; the runs of one chunk are its segments.  A chunk whose
-// runs are too short to pay for their constants (fewer than 4 rows per run) takes the per-layer path.
-constexpr int CHAIN_MIN_RUN = 4;
+// A sorted list of lattice ids (an octree frontier) through the chain kernel's run-list form.  Segments
+// never cross a 1024-row block (runs.cu), so the list is cut greedily into launches of whole blocks: at
+// most `chunk_tiles` tiles of rows and at most CHAIN_MAX_SEGS segments (the size of the constants buffer).
+// Every list takes this path whatever its run lengths, so a point's value does not depend on how a caller
+// (e.g. the multi-GPU octree, pifu_b200.dist) cuts the list into calls.
+constexpr long long CHAIN_MAX_SEGS = 64 * 1024;          // 557 MiB of per-segment constants
 int run_chain_ids(pifu_ctx* c, int R0, int R1, int R2, const long long* ids, long long n, const float* calib,
                   const double* calib_inv, float* out, cudaStream_t s) {
     using namespace chain;
     ChainPlan& P = c->cplan;
-    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M / RUN_BLOCK_ROWS * RUN_BLOCK_ROWS;
+    const long long ws_rows = static_cast<long long>(c->chunk_tiles) * TILE_M;       // rows the gather workspace holds
+    const long long max_blocks = ws_rows / RUN_BLOCK_ROWS;
+    const long long max_segs = CHAIN_MAX_SEGS < ws_rows ? CHAIN_MAX_SEGS : ws_rows;
     const long long nblocks = (n + RUN_BLOCK_ROWS - 1) / RUN_BLOCK_ROWS;
-    const int bpc = static_cast<int>(chunk / RUN_BLOCK_ROWS);
     if (P.cap_blocks < nblocks) {
         if (P.block_heads) { cudaFree(P.block_heads); P.block_heads = nullptr; P.cap_blocks = 0; }
         PIFU_CUDA(cudaMalloc(&P.block_heads, static_cast<size_t>(nblocks) * sizeof(uint32_t)));
         P.cap_blocks = nblocks;
     }
-    if (P.cap_rows < chunk) {
+    if (P.cap_rows < ws_rows) {
         if (P.rowseg) { cudaFree(P.rowseg); P.rowseg = nullptr; }
         if (P.seg_ids) { cudaFree(P.seg_ids); P.seg_ids = nullptr; }
         P.cap_rows = 0;
-        PIFU_CUDA(cudaMalloc(&P.rowseg, static_cast<size_t>(chunk) * sizeof(int)));
-        PIFU_CUDA(cudaMalloc(&P.seg_ids, static_cast<size_t>(chunk) * sizeof(long long)));
-        P.cap_rows = chunk;
+        PIFU_CUDA(cudaMalloc(&P.rowseg, static_cast<size_t>(ws_rows) * sizeof(int)));
+        PIFU_CUDA(cudaMalloc(&P.seg_ids, static_cast<size_t>(ws_rows) * sizeof(long long)));
+        P.cap_rows = ws_rows;
     }
     c->launches += 1;
-    if (launch_run_heads(ids, n, R2, chunk, P.block_heads, s)) return -1;
+    if (launch_run_heads(ids, n, R2, P.block_heads, s)) return -1;
     P.heads_host.resize(static_cast<size_t>(nblocks));
     PIFU_CUDA(cudaMemcpyAsync(P.heads_host.data(), P.block_heads, static_cast<size_t>(nblocks) * sizeof(uint32_t),
                               cudaMemcpyDeviceToHost, s));
     PIFU_CUDA(cudaStreamSynchronize(s));
-    // segments per chunk; the constants buffer holds the largest chunk that takes the chain
-    std::vector<long long> nseg;
+    // greedy cut into launches: (first block, blocks, segments)
+    struct Cut { long long b0, nb, segs; };
+    std::vector<Cut> cuts;
     long long cc_need = 0;
-    for (long long b = 0; b < nblocks; b += bpc) {
-        long long t = 0;
-        for (long long k = b; k < nblocks && k < b + bpc; ++k) t += P.heads_host[static_cast<size_t>(k)];
-        const long long rows = (n - b * RUN_BLOCK_ROWS) < chunk ? (n - b * RUN_BLOCK_ROWS) : chunk;
-        nseg.push_back(t);
-        if (t * CHAIN_MIN_RUN <= rows && t > cc_need) cc_need = t;
+    for (long long b = 0; b < nblocks;) {
+        Cut ct{b, 0, 0};
+        while (b < nblocks && ct.nb < max_blocks && ct.segs + P.heads_host[static_cast<size_t>(b)] <= max_segs) {
+            ct.segs += P.heads_host[static_cast<size_t>(b)];
+            ++ct.nb;
+            ++b;
+        }
+        if (ct.nb == 0) { set_error("chain: workspace smaller than one block of rows"); return -1; }
+        if (ct.segs > cc_need) cc_need = ct.segs;
+        cuts.push_back(ct);
     }
     if (grow_cc(P, cc_need)) return -1;
     PointSource src;
     lattice_source(src, R0, R1, R2, calib_inv);
-    for (size_t ci = 0; ci < nseg.size(); ++ci) {
-        const long long row0 = static_cast<long long>(ci) * chunk;
-        const int m = static_cast<int>(n - row0 < chunk ? n - row0 : chunk);
-        if (nseg[ci] * CHAIN_MIN_RUN > m) {
-            src.ids = ids + row0;
-            QueryOut o;
-            o.pred = out + row0;
-            if (run_chunk(c, 2, src, m, calib, calib, o, s)) return -1;
-            continue;
-        }
-        const int ns = static_cast<int>(nseg[ci]);
+    for (const Cut& ct : cuts) {
+        const long long row0 = ct.b0 * RUN_BLOCK_ROWS;
+        const long long rows = ct.nb * RUN_BLOCK_ROWS;
+        const int m = static_cast<int>(n - row0 < rows ? n - row0 : rows);
+        const int ns = static_cast<int>(ct.segs);
         c->launches += 1;
-        if (launch_run_assign(ids, row0, m, R2, chunk, P.block_heads + ci * bpc, P.rowseg, P.seg_ids, s)) return -1;
+        if (launch_run_assign(ids, row0, m, R2, P.block_heads + ct.b0, P.rowseg, P.seg_ids, s)) return -1;
         src.ids = P.seg_ids;
         if (chain_constants(c, src, ns, calib, s)) return -1;
         ChainArgs ca;
@@ -767,7 +769,7 @@ namespace pifu {
 // used by octree.cu: evaluate `n` lattice ids (device list) into out (device fp32 [n])
 int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
              const float* calib, const double* calib_inv, float* out, cudaStream_t s) {
-    if (c->cplan.rows_enabled && n >= TILE_M && c->chunk_tiles * TILE_M >= RUN_BLOCK_ROWS &&
+    if (c->cplan.rows_enabled && n > 0 && c->chunk_tiles * TILE_M >= RUN_BLOCK_ROWS &&
         chain_eligible(c, levels, TILE_M, calib, calib_inv))
         return run_chain_ids(c, R0, R1, R2, ids, n, calib, calib_inv, out, s);
     PointSource src;

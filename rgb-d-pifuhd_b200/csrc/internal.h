@@ -23,8 +23,8 @@ int launch_head(const ASeg* segs, int nseg, const float* w, float b, const uint8
 
 // runs.cu: segmentation of a sorted lattice-id list into runs of rows that share a lattice column
 constexpr int RUN_BLOCK_ROWS = 1024;
-int launch_run_heads(const long long* ids, long long n, int R2, long long chunk, uint32_t* block_heads, cudaStream_t s);
-int launch_run_assign(const long long* ids, long long row0, int m, int R2, long long chunk, const uint32_t* block_heads,
+int launch_run_heads(const long long* ids, long long n, int R2, uint32_t* block_heads, cudaStream_t s);
+int launch_run_assign(const long long* ids, long long row0, int m, int R2, const uint32_t* block_heads,
                       int* rowseg, long long* seg_ids, cudaStream_t s);
 
 // api.cu services used by the octree driver
