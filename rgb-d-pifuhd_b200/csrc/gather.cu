@@ -100,10 +100,13 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
 #pragma unroll
     for (int i = 0; i < MAX_CHUNKS_PER_LANE; ++i) ccache[i] = make_uint4(0, 0, 0, 0);
 
-    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-        const int row = warp * ROWS_PER_WARP + rr;
+    // gridDim.y splits a warp's 16 rows over several blocks: short launches (the per-run samples of an octree
+    // frontier, calc_normal's points) would otherwise leave most SMs idle behind 16 sequential rows per warp
+    const int rpw = ROWS_PER_WARP / static_cast<int>(gridDim.y);
+    for (int rr = 0; rr < rpw; ++rr) {
+        const int row = warp * ROWS_PER_WARP + static_cast<int>(blockIdx.y) * rpw + rr;
         const int p = mt * TILE_M + row;
-        if (p >= a.n) break;
+        if (p >= a.n) break;          // rows ascend within a warp: nothing valid follows
         float px, py, pz;
         if (S.mode == 0) {
             px = __ldg(S.pts + p);
@@ -187,7 +190,9 @@ int launch_gather(const GatherArgs& a, cudaStream_t s) {
         set_error("gather: fine channels %d unsupported (multiple of 8, <= 256)", a.Cf); return -1;
     }
     const int m_tiles = (a.n + TILE_M - 1) / TILE_M;
-    gather_kernel<<<m_tiles, 256, 0, s>>>(a);
+    int split = 1;
+    while (split < 8 && m_tiles * split < 4 * 148) split *= 2;
+    gather_kernel<<<dim3(m_tiles, split), 256, 0, s>>>(a);
     PIFU_CUDA(cudaGetLastError());
     return 0;
 }

@@ -6,9 +6,12 @@
 //   cells    : per cell of the stride grid, min/max of its 8 corners in float64 and the skip
 //              test (max - min) < threshold & unprocessed[centre] (`:154-179`)
 //   fill     : the reference's sequential per-cell fill (`:181-184`, inclusive range, later
-//              cells overwrite earlier ones) restated per voxel: among the skip cells covering
-//              a voxel the lexicographically largest wrote last.  Candidates per axis: cell
-//              p/step if it exists, and cell p/step - 1 only when p % step == 0.
+//              cells overwrite earlier ones) restated without the order: among the skip cells
+//              covering a voxel the lexicographically largest wrote last.  Candidates per axis: cell
+//              p/step if it exists, and cell p/step - 1 only when p % step == 0.  Hence a skip cell
+//              keeps every voxel of its (step+1)^3 block except those on its high faces that a
+//              skip cell further along those axes also covers.  One warp per skip cell (the cells
+//              kernel compacts them): the work follows the cells that fill, not the volume.
 // The field is kept in float64 exactly like the reference's `sdf`, so given identical
 // evaluated values the result is bit-identical to the reference loop.
 #include <vector>
@@ -29,6 +32,9 @@ struct OctreeState {
     double* sdf = nullptr;           // [R0*R1*R2]
     uint8_t* todo = nullptr;         // `notprocessed`
     uint8_t* skip = nullptr;         // per cell of the current level
+    uint32_t* skip_list = nullptr;   // the level's skip cells, compacted (any order)
+    unsigned long long* skip_count = nullptr;
+    long long cap_list = 0;
     double* mid = nullptr;
     long long* ids = nullptr;        // compacted frontier
     uint32_t* block_sums = nullptr;
@@ -44,6 +50,7 @@ struct OctreeState {
 void octree_free(OctreeState* s) {
     if (!s) return;
     cudaFree(s->sdf); cudaFree(s->todo); cudaFree(s->skip); cudaFree(s->mid); cudaFree(s->ids);
+    cudaFree(s->skip_list); cudaFree(s->skip_count);
     cudaFree(s->block_sums); cudaFree(s->partials); cudaFree(s->total_dev); cudaFree(s->vals);
     delete s;
 }
@@ -175,10 +182,12 @@ __global__ void commit_kernel(const T* __restrict__ vals, const long long* __res
 
 __global__ void cells_kernel(const double* __restrict__ sdf, const uint8_t* __restrict__ todo, int step,
                              int c0, int c1, int c2, int R1, int R2, double threshold,
-                             uint8_t* __restrict__ skip, double* __restrict__ mid) {
+                             uint8_t* __restrict__ skip, double* __restrict__ mid, uint32_t* __restrict__ skip_list,
+                             unsigned long long* __restrict__ skip_count) {
     const long long nc = static_cast<long long>(c0) * c1 * c2;
     const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (c >= nc) return;
+    bool sk = false;
+    if (c < nc) {
     const int z = static_cast<int>(c % c2);
     const int y = static_cast<int>((c / c2) % c1);
     const int x = static_cast<int>(c / (static_cast<long long>(c2) * c1));
@@ -192,8 +201,84 @@ __global__ void cells_kernel(const double* __restrict__ sdf, const uint8_t* __re
     }
     const int h = step / 2;
     const long long vc = (static_cast<long long>(x * step + h) * R1 + (y * step + h)) * R2 + (z * step + h);
-    skip[c] = ((hi - lo) < threshold) && todo[vc];
+    sk = ((hi - lo) < threshold) && todo[vc];
+    skip[c] = sk;
     mid[c] = 0.5 * (lo + hi);
+    }
+    // warp-aggregated append of the skip cells (ballot + popc ranks, one atomic per warp)
+    const int lane = threadIdx.x & 31;
+    uint32_t wc;
+    const uint32_t r = warp_flag_rank(sk, lane, &wc);
+    unsigned long long base = 0;
+    if (lane == 0 && wc) base = atomicAdd(skip_count, static_cast<unsigned long long>(wc));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (sk) skip_list[base + r] = static_cast<uint32_t>(c);
+}
+
+// Neighbour cells of a skip cell c, offset o in {-1, 0, 1}^3, bit n = (ox+1)*9 + (oy+1)*3 + (oz+1).
+__host__ __device__ constexpr uint32_t nb_axis_mask(int axis, int o) {
+    uint32_t m = 0;
+    for (int n = 0; n < 27; ++n) {
+        const int v[3] = {n / 9 - 1, (n / 3) % 3 - 1, n % 3 - 1};
+        if (v[axis] == o) m |= 1u << n;
+    }
+    return m;
+}
+__host__ __device__ constexpr uint32_t nb_later_mask() {           // cells visited after c by the reference's C-order loop: first nonzero offset is +1
+    uint32_t m = 0;
+    for (int n = 0; n < 27; ++n) {
+        const int v[3] = {n / 9 - 1, (n / 3) % 3 - 1, n % 3 - 1};
+        const int first = v[0] != 0 ? v[0] : (v[1] != 0 ? v[1] : v[2]);
+        if (first > 0) m |= 1u << n;
+    }
+    return m;
+}
+
+// One warp per skip cell: its (step+1)^3 voxels (clipped to the volume, like the reference's slices) get the
+// cell's midpoint unless a skip cell visited LATER by the reference's loop covers them too (last writer wins).
+// A voxel at offset d of cell c is covered by the cells c + o with o_a = 0, o_a = +1 if d_a == step (high face)
+// or o_a = -1 if d_a == 0 (low face); "later" = lexicographically larger = first nonzero o_a is +1.
+__global__ void __launch_bounds__(256) fill_cells_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo,
+                                                         const uint8_t* __restrict__ skip, const double* __restrict__ mid,
+                                                         const uint32_t* __restrict__ skip_list,
+                                                         const unsigned long long* __restrict__ skip_count, int step,
+                                                         int c0, int c1, int c2, int R0, int R1, int R2) {
+    constexpr uint32_t LATER = nb_later_mask();
+    constexpr uint32_t AX[3][3] = {{nb_axis_mask(0, -1), nb_axis_mask(0, 0), nb_axis_mask(0, 1)},
+                                   {nb_axis_mask(1, -1), nb_axis_mask(1, 0), nb_axis_mask(1, 1)},
+                                   {nb_axis_mask(2, -1), nb_axis_mask(2, 0), nb_axis_mask(2, 1)}};
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    const long long n = static_cast<long long>(*skip_count);
+    const int e = step + 1, e2 = e * e, total = e2 * e;
+    for (long long w = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); w < n; w += nwarps) {
+        const uint32_t c = skip_list[w];
+        const int z = static_cast<int>(c % c2);
+        const int y = static_cast<int>((c / c2) % c1);
+        const int x = static_cast<int>(c / (static_cast<uint32_t>(c2) * c1));
+        bool nb = false;
+        if (lane < 27) {
+            const int nx = x + lane / 9 - 1, ny = y + (lane / 3) % 3 - 1, nz = z + lane % 3 - 1;
+            if (nx >= 0 && nx < c0 && ny >= 0 && ny < c1 && nz >= 0 && nz < c2)
+                nb = skip[(static_cast<long long>(nx) * c1 + ny) * c2 + nz] != 0;
+        }
+        const uint32_t later = __ballot_sync(0xffffffffu, nb) & LATER;      // skip cells around c that write after it
+        const double m = mid[c];
+        const int bx = x * step, by = y * step, bz = z * step;
+        for (int v = lane; v < total; v += 32) {
+            const int dx = v / e2, rem = v - dx * e2;
+            const int dy = rem / e, dz = rem - dy * e;
+            const int px = bx + dx, py = by + dy, pz = bz + dz;
+            if (px >= R0 || py >= R1 || pz >= R2) continue;
+            const uint32_t cover = (AX[0][1] | (dx == step ? AX[0][2] : 0u) | (dx == 0 ? AX[0][0] : 0u)) &
+                                   (AX[1][1] | (dy == step ? AX[1][2] : 0u) | (dy == 0 ? AX[1][0] : 0u)) &
+                                   (AX[2][1] | (dz == step ? AX[2][2] : 0u) | (dz == 0 ? AX[2][0] : 0u));
+            if (later & cover) continue;
+            const long long p = (static_cast<long long>(px) * R1 + py) * R2 + pz;
+            sdf[p] = m;
+            todo[p] = 0;
+        }
+    }
 }
 
 // One thread per 4 consecutive voxels of a lattice row (i, j, 4 qk .. 4 qk + 3), so a warp's stores cover
@@ -374,18 +459,30 @@ int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStre
             cap = st->cap_cells;
             if (grow(&st->mid, &cap, nc)) return -1;
             st->cap_cells = cap;
+            if (nc > 0xffffffffLL) { set_error("octree: more than 2^32 cells in a level"); return -1; }
+            if (grow(&st->skip_list, &st->cap_list, nc)) return -1;
+            if (!st->skip_count) PIFU_CUDA(cudaMalloc(&st->skip_count, sizeof(unsigned long long)));
+            PIFU_CUDA(cudaMemsetAsync(st->skip_count, 0, sizeof(unsigned long long), s));
             cells_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(st->sdf, st->todo, step, c0, c1, c2, st->R[1], st->R[2],
-                                                          st->threshold, st->skip, st->mid);
-            const int quads = ceil_div(st->R[2], 4);
-            int shift = -1;
-            for (int b = 0; b < 30; ++b) if (step == (1 << b)) shift = b;
-            int tx = 32;
-            while (tx < quads && tx < 256) tx *= 2;
-            const dim3 blk(tx, 256 / tx, 1);
-            if (st->R[0] > 65535 || st->R[1] > 65535) { set_error("octree: resolution above 65535"); return -1; }
-            const dim3 grd(ceil_div(quads, tx), ceil_div(st->R[1], blk.y), st->R[0]);
-            fill_kernel<<<grd, blk, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, step, shift, c0, c1, c2,
-                                           st->R[0], st->R[1], st->R[2], quads);
+                                                          st->threshold, st->skip, st->mid, st->skip_list, st->skip_count);
+            if (step >= 8 && st->R[0] <= 65535 && st->R[1] <= 65535) {
+                // coarse levels fill most of the volume: voxel-centric, whole rows of the field per warp
+                // (measured at 512^3, step 8: 0.38 ms against 0.61 ms cell by cell)
+                const int quads = ceil_div(st->R[2], 4);
+                int shift = -1;
+                for (int b = 0; b < 30; ++b) if (step == (1 << b)) shift = b;
+                int tx = 32;
+                while (tx < quads && tx < 256) tx *= 2;
+                const dim3 blk(tx, 256 / tx, 1);
+                const dim3 grd(ceil_div(quads, tx), ceil_div(st->R[1], blk.y), st->R[0]);
+                fill_kernel<<<grd, blk, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, step, shift, c0, c1, c2,
+                                               st->R[0], st->R[1], st->R[2], quads);
+            } else {
+                // fine levels fill a thin shell: persistent warps over the compacted skip cells; the count stays on
+                // the device (no host sync) (step 4 / 2: 0.12 / 0.25 ms against 0.34 / 0.52 ms voxel by voxel)
+                fill_cells_kernel<<<ctx_num_sms(c) * 8, 256, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, st->skip_list,
+                                                                    st->skip_count, step, c0, c1, c2, st->R[0], st->R[1], st->R[2]);
+            }
             ctx_count_launch(c, 2);
         }
     }
