@@ -121,6 +121,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK) classify_kernel(const float* __res
         // corners: 0 (i,j,k) 1 (i,j,k+1) 2 (i,j+1,k+1) 3 (i,j+1,k) 4 (i+1,j,k) 5 (i+1,j,k+1) 6 (i+1,j+1,k+1) 7 (i+1,j+1,k)
         uint32_t word = 0;
         const int zij = zero_mask(i + d.i0, j, 1);
+        // ~99 % of the threads see 20 values on one side of the level: cases 0 or 255 for all their cells
+        const uint32_t any_in = in[0] | in[1] | in[2] | in[3], all_in = in[0] & in[1] & in[2] & in[3];
+        const bool uniform = k0 + CPT < d.n2 && (any_in == 0u || all_in == (1u << (CPT + 1)) - 1u);
+        if (uniform) {
+            word = any_in ? 0xffffffffu : 0u;
+            if (k0 + CPT > d.c2) word &= 0xffffffffu >> (8 * (k0 + CPT - d.c2));      // padding cells of the row stay 0
+        } else
 #pragma unroll
         for (int m = 0; m < CPT; ++m) {
             if (k0 + m >= d.c2) break;
