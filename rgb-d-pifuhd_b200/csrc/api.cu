@@ -74,10 +74,11 @@ struct ChainPlan {
     bool coarse_ok = false, fine_ok = false;
     bool enabled = true;
     uint8_t* wstream = nullptr;      // chain::WSTREAM_BYTES, stages in consumption order
-    uint8_t* w_colA = nullptr;       // feature columns of coarse L0 and L2: N = 1280, F layout (5 k-blocks)
-    float* bias_colA = nullptr;      // [b0 ; b2]
-    uint8_t* w_colB = nullptr;       // fine-feature columns of fine L0, L1, L2: N = 896, FF layout (1 k-block)
-    float* bias_colB = nullptr;      // [bF0 ; bF1 ; bF2]
+    // "column constants" operand: N = 2176 rows [coarse L0 | coarse L2 | fine L0 | L1 | L2], K = 6 k-blocks
+    // [F (5) | FF (1)]: the coarse rows read the coarse-feature columns, the fine rows the fine-feature columns,
+    // everything else is zero - one GEMM per launch of the chain kernel instead of two
+    uint8_t* w_colA = nullptr;
+    float* bias_colA = nullptr;      // [b0 ; b2 ; bF0 ; bF1 ; bF2]
     float* wz0 = nullptr;            // z column of coarse L0
     float* wz2 = nullptr;            // z column of coarse L2
     float* b1 = nullptr;
@@ -98,6 +99,7 @@ struct ChainPlan {
     std::vector<uint32_t> heads_host;
 };
 constexpr int CHAIN_COLS_PER_CHUNK = 148 * 32;
+constexpr int CCW_KB = 6;            // K of the column-constants GEMM: F (5 k-blocks) + FF (1)
 
 }  // namespace
 
@@ -337,7 +339,7 @@ void free_chain(ChainPlan& P, bool coarse_too) {
         P.cap_blocks = P.cap_rows = 0;
         P.coarse_ok = false;
     }
-    fr(P.w_colB); fr(P.bias_colB); fr(P.w3);
+    fr(P.w3);
     P.fine_ok = false;
 }
 
@@ -394,11 +396,11 @@ int chain_pack_stages(ChainPlan& P, int first_stage, int nst, const float* W, in
 }
 
 // feature-column weights of one layer appended to a "column constants" GEMM operand:
-// packed column k < nfeat reads source column col0 + k, all other packed columns are zero
-int chain_pack_colw(ChainPlan& P, const float* W, int cin, int col0, int nfeat, int num_kb, int N, int BN,
+// packed column kfirst + k, k < nfeat, reads source column col0 + k, all other packed columns are zero
+int chain_pack_colw(ChainPlan& P, const float* W, int cin, int col0, int nfeat, int kfirst, int num_kb, int N, int BN,
                     uint8_t* dst, cudaStream_t s) {
     std::vector<int> m(static_cast<size_t>(num_kb) * KB, -1);
-    for (int k = 0; k < nfeat; ++k) m[k] = col0 + k;
+    for (int k = 0; k < nfeat; ++k) m[kfirst + k] = col0 + k;
     int* dm = P.colmaps + static_cast<size_t>(chain::STAGES) * KB;     // scratch behind the stage maps
     PIFU_CUDA(cudaMemcpyAsync(dm, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     PIFU_CUDA(cudaStreamSynchronize(s));
@@ -417,8 +419,9 @@ int build_chain_coarse(pifu_ctx* c, const float* const* weights, const float* co
     PIFU_CUDA(cudaMalloc(&P.wstream, WSTREAM_BYTES));
     chain_encode_tmaps(P);
     PIFU_CUDA(cudaMalloc(&P.colmaps, (static_cast<size_t>(STAGES) + 8 + 16) * KB * sizeof(int)));
-    PIFU_CUDA(cudaMalloc(&P.w_colA, static_cast<size_t>(C0 + C2) * 5 * ROW_BYTES));
-    PIFU_CUDA(cudaMalloc(&P.bias_colA, (C0 + C2) * sizeof(float)));
+    PIFU_CUDA(cudaMalloc(&P.w_colA, static_cast<size_t>(CC_FLOATS) * CCW_KB * ROW_BYTES));
+    PIFU_CUDA(cudaMemsetAsync(P.w_colA, 0, static_cast<size_t>(CC_FLOATS) * CCW_KB * ROW_BYTES, s));
+    PIFU_CUDA(cudaMalloc(&P.bias_colA, CC_FLOATS * sizeof(float)));
     PIFU_CUDA(cudaMalloc(&P.wz0, C0 * sizeof(float)));
     PIFU_CUDA(cudaMalloc(&P.wz2, C2 * sizeof(float)));
     PIFU_CUDA(cudaMalloc(&P.b1, C1 * sizeof(float)));
@@ -428,9 +431,9 @@ int build_chain_coarse(pifu_ctx* c, const float* const* weights, const float* co
     if (chain_pack_stages(P, 1, 16, weights[1], C0, 256, 0, 256, s, 2)) return -1;
     if (chain_pack_stages(P, 32, 8, weights[2], cin2, 0, 0, 256, s)) return -1;
     // per-column constants: coarse L0 feature columns [0, 256), coarse L2 feature columns [512, 768)
-    if (chain_pack_colw(P, weights[0], 257, 0, 256, 5, C0, 256, P.w_colA, s)) return -1;
-    if (chain_pack_colw(P, weights[2], cin2, C1, 256, 5, C2, 256,
-                        P.w_colA + static_cast<size_t>(C0) * 5 * ROW_BYTES, s)) return -1;
+    if (chain_pack_colw(P, weights[0], 257, 0, 256, 0, CCW_KB, C0, 128, P.w_colA, s)) return -1;
+    if (chain_pack_colw(P, weights[2], cin2, C1, 256, 0, CCW_KB, C2, 128,
+                        P.w_colA + static_cast<size_t>(C0) * CCW_KB * ROW_BYTES, s)) return -1;
     PIFU_CUDA(cudaMemcpyAsync(P.bias_colA, biases[0], C0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     PIFU_CUDA(cudaMemcpyAsync(P.bias_colA + C0, biases[2], C2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     PIFU_CUDA(cudaMemcpyAsync(P.b1, biases[1], C1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -453,8 +456,8 @@ int build_chain_fine(pifu_ctx* c, const float* const* weights, const float* cons
     if (!P.coarse_ok) return 0;
     if (!(L.n_layers == 4 && L.dims[0] == 16 + C2 && L.dims[1] == F0 && L.dims[2] == F1 && L.dims[3] == F2 &&
           L.is_res(1) && L.is_res(2) && !L.is_res(3) && c->bufs[c->buf_FF].nkb == 1)) return 0;
-    PIFU_CUDA(cudaMalloc(&P.w_colB, static_cast<size_t>(F0 + F1 + F2) * ROW_BYTES));
-    PIFU_CUDA(cudaMalloc(&P.bias_colB, (F0 + F1 + F2) * sizeof(float)));
+    uint8_t* w_colB = P.w_colA + static_cast<size_t>(C0 + C2) * CCW_KB * ROW_BYTES;      // the fine rows of the operand
+    float* bias_colB = P.bias_colA + C0 + C2;
     PIFU_CUDA(cudaMalloc(&P.w3, F2 * sizeof(float)));
     const int cin0 = 16 + C2, cin1 = F0 + cin0, cin2 = F1 + cin0;
     // input order [fine feat ; phi] (`PIFuMRNet.py:170-171`), skip concat [y ; input] (`MLP.py:61-64`)
@@ -464,13 +467,13 @@ int build_chain_fine(pifu_ctx* c, const float* const* weights, const float* cons
     if (chain_pack_stages(P, 52, 8, weights[1], cin1, 0, 0, 256, s)) return -1;             //     y part
     if (chain_pack_stages(P, 60, 4, weights[2], cin2, 0, F1 + 16, 128, s)) return -1;       // J6: phi part
     if (chain_pack_stages(P, 64, 4, weights[2], cin2, 0, 0, 128, s)) return -1;             //     y part
-    if (chain_pack_colw(P, weights[0], cin0, 0, 16, 1, F0, 128, P.w_colB, s)) return -1;
-    if (chain_pack_colw(P, weights[1], cin1, F0, 16, 1, F1, 128, P.w_colB + static_cast<size_t>(F0) * ROW_BYTES, s)) return -1;
-    if (chain_pack_colw(P, weights[2], cin2, F1, 16, 1, F2, 128,
-                        P.w_colB + static_cast<size_t>(F0 + F1) * ROW_BYTES, s)) return -1;
-    PIFU_CUDA(cudaMemcpyAsync(P.bias_colB, biases[0], F0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    PIFU_CUDA(cudaMemcpyAsync(P.bias_colB + F0, biases[1], F1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    PIFU_CUDA(cudaMemcpyAsync(P.bias_colB + F0 + F1, biases[2], F2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (chain_pack_colw(P, weights[0], cin0, 0, 16, 5 * KB, CCW_KB, F0, 128, w_colB, s)) return -1;
+    if (chain_pack_colw(P, weights[1], cin1, F0, 16, 5 * KB, CCW_KB, F1, 128, w_colB + static_cast<size_t>(F0) * CCW_KB * ROW_BYTES, s)) return -1;
+    if (chain_pack_colw(P, weights[2], cin2, F1, 16, 5 * KB, CCW_KB, F2, 128,
+                        w_colB + static_cast<size_t>(F0 + F1) * CCW_KB * ROW_BYTES, s)) return -1;
+    PIFU_CUDA(cudaMemcpyAsync(bias_colB, biases[0], F0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(bias_colB + F0, biases[1], F1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    PIFU_CUDA(cudaMemcpyAsync(bias_colB + F0 + F1, biases[2], F2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     PIFU_CUDA(cudaMemcpyAsync(P.w3, weights[3], F2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     PIFU_CUDA(cudaStreamSynchronize(s));
     P.b3 = L.head_b;
@@ -605,17 +608,13 @@ int chain_constants(pifu_ctx* c, const PointSource& src, int ncol, const float* 
     if (launch_gather(ga, s)) return -1;
     GemmArgs g;
     memset(&g, 0, sizeof(g));
-    g.nseg = 1;
+    g.nseg = 2;
     g.seg[0].base = ga.F; g.seg[0].kb_stride = ga.kbF; g.seg[0].kb_off = 0; g.seg[0].nkb = ga.kbF;
-    g.num_kb = ga.kbF;
-    g.w = P.w_colA; g.bias = P.bias_colA; g.N = C0 + C2; g.m_tiles = m_tiles; g.n_valid = ncol;
+    g.seg[1].base = ga.FF; g.seg[1].kb_stride = ga.kbFF; g.seg[1].kb_off = 0; g.seg[1].nkb = ga.kbFF;
+    g.num_kb = ga.kbF + ga.kbFF;
+    g.w = P.w_colA; g.bias = P.bias_colA; g.N = CC_FLOATS; g.m_tiles = m_tiles; g.n_valid = ncol;
     g.out_f32 = P.cc; g.f32_ld = CC_FLOATS; g.f32_col0 = 0;
-    if (run_gemm(c, g, 2.0 * ncol * 256.0 * (C0 + C2), s)) return -1;
-    g.seg[0].base = ga.FF; g.seg[0].kb_stride = ga.kbFF; g.seg[0].nkb = ga.kbFF;
-    g.num_kb = ga.kbFF;
-    g.w = P.w_colB; g.bias = P.bias_colB; g.N = F0 + F1 + F2;
-    g.f32_col0 = C0 + C2;
-    return run_gemm(c, g, 2.0 * ncol * 16.0 * (F0 + F1 + F2), s);
+    return run_gemm(c, g, 2.0 * ncol * (256.0 * (C0 + C2) + 16.0 * (F0 + F1 + F2)), s);
 }
 
 int grow_cc(ChainPlan& P, long long cols) {

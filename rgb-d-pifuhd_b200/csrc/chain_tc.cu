@@ -499,8 +499,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
         // issued before k-block kb is converted, so only the first k-block of a range exposes their latency.
         auto gen_load = [&](int kb, float4 (&ca)[4], float4 (&cb)[4]) {
             if constexpr (ROWS) {
+                if (crow[0] == crow[3]) {
+                    // the four rows (12 apart at most, segments ascend) share one segment: one pair of loads; the L1 /
+                    // shared-memory data path is what the coarse-L1 GEMM's operand fetch already keeps 75 % busy
+                    ca[0] = ldg128(crow[0] + kb * KB + gchunk * 8); cb[0] = ldg128(crow[0] + kb * KB + gchunk * 8 + 4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { ca[i] = ldg128(crow[i] + kb * KB + gchunk * 8); cb[i] = ldg128(crow[i] + kb * KB + gchunk * 8 + 4); }
+                    for (int i = 1; i < 4; ++i) { ca[i] = ca[0]; cb[i] = cb[0]; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ca[i] = ldg128(crow[i] + kb * KB + gchunk * 8); cb[i] = ldg128(crow[i] + kb * KB + gchunk * 8 + 4); }
+                }
             } else {
                 const uint32_t n0 = static_cast<uint32_t>(kb * KB + gchunk * 8) * 4u;
                 ca[0] = lds128(c0_a + n0); cb[0] = lds128(c0_a + n0 + 16);
