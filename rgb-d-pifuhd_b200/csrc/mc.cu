@@ -54,6 +54,7 @@ void mc_free(McState* s) {
 namespace {
 
 constexpr int CPT = 4;                 // cells per thread, consecutive along axis 2
+constexpr int EMIT_LIST = 3072;        // vertices / triangles of one block redistributed over its threads
 
 // n*: planes of the local volume; c*: cell layers processed; cs2: padded cells per row, nq = cs2 / CPT;
 // i0 / g0: global index of local plane 0 and global plane count (slab mode); ghost: leading cell
@@ -230,29 +231,57 @@ __global__ void __launch_bounds__(SCAN_BLOCK) emit_vertices_kernel(const float* 
         }
     }
     uint32_t bt;
-    uint32_t base = voffs[blk] + block_exclusive_scan(nv, &bt);
-    if (word == 0u || word == 0xffffffffu) return;
-    for (int m = 0; m < CPT; ++m) {
-        const int cs = static_cast<int>((word >> (8 * m)) & 255u);
-        if (cs == 0 || cs == 255) continue;
-        const int k = k0 + m;
-        const int zm = zero_mask(i + d.i0, j, k);
-        vbase[row * d.cs2 + k] = base;
-        uint32_t r = 0;
-        const int nvc = MC_NVERT[cs];
-        for (int q = 0; q < nvc; ++q) {
-            const int e = MC_VERTS[cs][q];
-            if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
-            double pos[3];
-            float nrm[3], val;
-            edge_vertex(f, d, level, i, j, k, e, pos, nrm, &val);
-            const size_t o = static_cast<size_t>(base + r);
-            verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
-            if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
-            if (values) values[o] = val;
-            ++r;
+    const uint32_t rel = block_exclusive_scan(nv, &bt);      // rank of this thread's first vertex inside the block
+    // The surface crosses a handful of the block's 1024 cells, so a few threads own all of its vertices (up to 12
+    // each, ~500 dependent cycles apiece).  They only list them - (thread, cell, edge) at the vertex's rank - and
+    // the whole block then computes one vertex per thread.
+    __shared__ uint32_t todo[EMIT_LIST];
+    const bool listed = bt <= EMIT_LIST;
+    uint32_t base = voffs[blk] + rel;
+    if (word != 0u && word != 0xffffffffu) {
+        uint32_t lr = rel;
+        for (int m = 0; m < CPT; ++m) {
+            const int cs = static_cast<int>((word >> (8 * m)) & 255u);
+            if (cs == 0 || cs == 255) continue;
+            const int k = k0 + m;
+            const int zm = zero_mask(i + d.i0, j, k);
+            vbase[row * d.cs2 + k] = base;
+            uint32_t r = 0;
+            const int nvc = MC_NVERT[cs];
+            for (int q = 0; q < nvc; ++q) {
+                const int e = MC_VERTS[cs][q];
+                if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
+                if (listed) {
+                    todo[lr + r] = (threadIdx.x << 8) | (static_cast<uint32_t>(m) << 4) | static_cast<uint32_t>(e);
+                } else {                                     // more vertices than the list holds: in place
+                    double pos[3];
+                    float nrm[3], val;
+                    edge_vertex(f, d, level, i, j, k, e, pos, nrm, &val);
+                    const size_t o = static_cast<size_t>(base + r);
+                    verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
+                    if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
+                    if (values) values[o] = val;
+                }
+                ++r;
+            }
+            base += cnt[m];
+            lr += cnt[m];
         }
-        base += cnt[m];
+    }
+    if (!listed) return;
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < bt; v += SCAN_BLOCK) {
+        const uint32_t t = todo[v];
+        int ti, tj, tk0;
+        long long trow;
+        thread_cells(d, blk * SCAN_BLOCK + (t >> 8), ti, tj, tk0, trow);
+        double pos[3];
+        float nrm[3], val;
+        edge_vertex(f, d, level, ti, tj, tk0 + static_cast<int>((t >> 4) & 15u), static_cast<int>(t & 15u), pos, nrm, &val);
+        const size_t o = static_cast<size_t>(voffs[blk]) + v;
+        verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
+        if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
+        if (values) values[o] = val;
     }
 }
 
@@ -293,17 +322,39 @@ __global__ void __launch_bounds__(SCAN_BLOCK) emit_faces_kernel(Dims d, const ui
         for (int m = 0; m < CPT; ++m) nt += MC_NTRI[(word >> (8 * m)) & 255u];
     }
     uint32_t bt;
-    uint32_t base = toffs[blk] + block_exclusive_scan(nt, &bt);
-    if (nt == 0) return;
-    for (int m = 0; m < CPT; ++m) {
-        const int cs = static_cast<int>((word >> (8 * m)) & 255u);
-        const uint32_t n = MC_NTRI[cs];
-        for (uint32_t t = 0; t < n; ++t) {
-            const size_t o = static_cast<size_t>(base + t) * 3;
+    const uint32_t rel = block_exclusive_scan(nt, &bt);
+    // same redistribution as the vertices: list (thread, cell, triangle) at the triangle's rank, then one per thread
+    __shared__ uint32_t todo[EMIT_LIST];
+    const bool listed = bt <= EMIT_LIST;
+    if (nt != 0) {
+        uint32_t lr = rel;
+        for (int m = 0; m < CPT; ++m) {
+            const int cs = static_cast<int>((word >> (8 * m)) & 255u);
+            const uint32_t n = MC_NTRI[cs];
+            for (uint32_t t = 0; t < n; ++t) {
+                if (listed) {
+                    todo[lr + t] = (threadIdx.x << 8) | (static_cast<uint32_t>(m) << 4) | t;
+                } else {
+                    const size_t o = static_cast<size_t>(toffs[blk] + lr + t) * 3;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cases, vbase, i, j, k0 + m, MC_TRIS[cs][3 * t + q]);
+                    for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cases, vbase, i, j, k0 + m, MC_TRIS[cs][3 * t + q]);
+                }
+            }
+            lr += n;
         }
-        base += n;
+    }
+    if (!listed) return;
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < bt; v += SCAN_BLOCK) {
+        const uint32_t e = todo[v];
+        int ti, tj, tk0;
+        long long trow;
+        thread_cells(d, blk * SCAN_BLOCK + (e >> 8), ti, tj, tk0, trow);
+        const int m = static_cast<int>((e >> 4) & 15u), t = static_cast<int>(e & 15u);
+        const int cs = cases[trow * d.cs2 + tk0 + m];
+        const size_t o = (static_cast<size_t>(toffs[blk]) + v) * 3;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cases, vbase, ti, tj, tk0 + m, MC_TRIS[cs][3 * t + q]);
     }
 }
 
