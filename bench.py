@@ -262,6 +262,82 @@ def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3):
     return out
 
 
+def encoder_leg(dev, frames=8):
+    """SURVEY §8(f) row 3 / BASELINE configs[3]: the per-image PyTorch encoders (coarse 4-stack hourglass on
+    512^2 + fine 1-stack on 1024^2, 6-channel RGB-D input) timed per execution mode, and the whole per-frame
+    flow - images H2D from pinned memory, filter_global, filter_local, 256^3 octree reconstruction, mesh on
+    the host - in frames/s on this GPU (frames shard by frame across GPUs with no communication)."""
+    from pifu_b200 import PIFuMRNet, PIFuNetwNML, config, mesh_util, synthetic as syn
+    og = config.coarse_opt(use_front_normal=True)               # norm 'batch' (options.py:78), eval mode
+    netG = PIFuNetwNML(og, "orthogonal")
+    netG.netF = None                                            # RGB-D: depth rides in the normal channels (SURVEY §8(c))
+    netMR = PIFuMRNet(config.fine_opt(), netG, "orthogonal")
+    prob = syn.make_problem(bias_std=0.0)
+    netG.mlp.load_state_dict(prob["coarse"])
+    netMR.mlp.load_state_dict(prob["fine"])
+    syn.fill_state(netG.image_filter, 3)
+    syn.fill_state(netMR.image_filter, 4)
+    netMR.to(dev).eval()
+    img512 = [syn.encoder_input((1, 6, 512, 512), 100 + f).pin_memory() for f in range(2)]
+    img1024 = [syn.encoder_input((1, 1, 6, 1024, 1024), 200 + f).pin_memory() for f in range(2)]
+    calib = syn.default_calib().to(dev)
+    out = {"input": "6-channel 512^2 + 1024^2 per frame", "modes": {}}
+
+    def time_filters(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        a, b = img512[0].to(dev), img1024[0].to(dev)
+        for _ in range(2):
+            netMR.filter_global(a); netMR.filter_local(b)
+        ev[0].record()
+        for _ in range(reps):
+            netMR.filter_global(a); netMR.filter_local(b)
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        return ev[0].elapsed_time(ev[1]) / reps
+
+    for name, opts in (("eager_fp32_nchw", dict(channels_last=False, precision="fp32", graph=False, autotune=False)),
+                       ("eager_tf32_nchw (stock PyTorch defaults)", dict(channels_last=False, precision="tf32", graph=False, autotune=False)),
+                       ("fp32_nchw_graph", dict(channels_last=False, precision="fp32", graph=True)),
+                       ("tf32_nchw_graph (default)", dict(channels_last=False, precision="tf32", graph=True)),
+                       ("bf16_nchw_graph", dict(channels_last=False, precision="bf16", graph=True)),
+                       ("tf32_channels_last_graph", dict(channels_last=True, precision="tf32", graph=True)),
+                       ("bf16_channels_last_graph", dict(channels_last=True, precision="bf16", graph=True))):
+        for net in (netG, netMR):
+            net.reset_encoder_runners()
+            net.encoder_opts = opts
+        out["modes"][name] = {"filter_global_plus_local_ms": time_filters(5)}
+    # per-frame flow with the default (tf32, NCHW, graph) encoders; field calibrated on the first frame
+    for net in (netG, netMR):
+        net.reset_encoder_runners()
+        net.encoder_opts = None
+        net.image_filter.to(memory_format=torch.contiguous_format)
+    netMR.filter_global(img512[0].to(dev)); netMR.filter_local(img1024[0].to(dev))
+    pilot = syn.random_points(20000, syn.SEED_PILOT, -1.0, 1.0)
+    netMR.query(pilot.to(dev), calib)
+    syn.calibrate_last_layer(prob["fine"], 3, netMR.get_preds().float().cpu().numpy())
+    syn.saturate(prob["fine"], 3)
+    netMR.mlp.load_state_dict(prob["fine"])
+    netMR.to(dev).eval()
+
+    def frame(f):
+        netMR.filter_global(img512[f % 2].to(dev, non_blocking=True))
+        netMR.filter_local(img1024[f % 2].to(dev, non_blocking=True))
+        return mesh_util.reconstruction(netMR, dev, calib, 256, None, None, thresh=0.5, use_octree=True, num_samples=5000)
+
+    for f in range(2):
+        mesh = frame(f)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for f in range(frames):
+        mesh = frame(f)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    out["frames_256_octree"] = {"frames": frames, "frames_per_s": frames / dt, "ms_per_frame": dt / frames * 1e3,
+                                "mesh": None if mesh == -1 else [len(mesh[0]), len(mesh[1])],
+                                "h2d_bytes_per_frame": (6 * 512 * 512 + 6 * 1024 * 1024) * 4}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this metric (oracle port: the
     reference cannot travel to the GPU box and its query path is library torch ops)."""
@@ -436,12 +512,15 @@ def main():
             cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d-point strided sub-lattice of the %d^3 lattice, chunks of 100000, %.1f s" % (npts, res, sec)}
 
-    mesh = None
+    mesh = enc = None
     if rank == 0 and world == 1 and not args.no_mesh:
         del flush
         torch.cuda.empty_cache()
         _, netMR2, eng2, calib2 = build_mesh_problem(dev)
         mesh = mesh_latency(netMR2, eng2, calib2, dev, 512, 3)
+        del netMR2, eng2
+        torch.cuda.empty_cache()
+        enc = encoder_leg(dev)
 
     if world > 1 and not args.no_mesh:
         del flush, slab, gathered
@@ -461,7 +540,7 @@ def main():
                        "path": "chain" if eng.chain_ready() else "per-layer"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "mesh_512": mesh,
+            "mesh_512": mesh, "encoders": enc,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -1,25 +1,32 @@
 """Fine (multi-level) pixel-aligned implicit function, drop-in for the reference's `PIFuMRNet.py`.
 
-`filter_global` / `filter_local` stay PyTorch and only orchestrate the caller's encoders;
+`filter_global` / `filter_local` stay PyTorch (hourglass encoders executed by encoders.EncoderRunner);
 `query` / `get_preds` / `calc_normal` run coarse trunk + fine MLP in libpifu_b200.so."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import encoders
 from .BasePIFuNet import BasePIFuNet, _not_hot_path
 from .MLP import MLP
+from .PIFuNetwNML import EncoderHost
 from .engine import get_engine
 
 
-class PIFuMRNet(BasePIFuNet):
+class PIFuMRNet(BasePIFuNet, EncoderHost):
     """Constructor of the reference (`PIFuMRNet.py:19-57`), including its default projection
     string 'otthogonal' (which selects perspective, `BasePIFuNet.py:79`; callers pass the mode
-    explicitly, `reconstruction.py:285-286`), plus ``image_filter`` for the fine encoder."""
+    explicitly, `reconstruction.py:285-286`), plus ``image_filter`` for the fine encoder ('auto': the
+    'no_down' hourglass of `PIFuMRNet.py:38-39`; a module; or None, see PIFuNetwNML)."""
 
-    def __init__(self, opt, netG, projection_mode="otthogonal", criteria=None, image_filter=None):
+    def __init__(self, opt, netG, projection_mode="otthogonal", criteria=None, image_filter="auto"):
         super().__init__(projection_mode=projection_mode, criteria=criteria)
         self.name = "hg_pifu"
         self.opt = opt
+        if isinstance(image_filter, str):
+            if image_filter != "auto":
+                raise ValueError("image_filter must be 'auto', None or a module")
+            image_filter = encoders.build_encoder(opt, encoders.input_channels(getattr(netG, "opt", None)), "no_down")
         self.image_filter = image_filter
         self.mlp = MLP(filter_channels=opt.mlp_dim, merge_layer=-1, res_layers=opt.mlp_res_layers,
                        norm=opt.mlp_norm, last_op=nn.Sigmoid())
@@ -75,9 +82,8 @@ class PIFuMRNet(BasePIFuNet):
                 crops = [torch.stack([nm[i, :, r[1]:r[3], r[0]:r[2]] for r in rect[i]], 0)
                          for i in range(rect.size(0))]
                 images = torch.cat([images, torch.stack(crops, 0)], 2)
-        self.im_feat_list, self.normx = self.image_filter(images.reshape(-1, *images.shape[2:]))
-        if not self.training:
-            self.im_feat_list = [self.im_feat_list[-1]]
+        self.im_feat_list, self.normx = self._run_encoder("image_filter", self.image_filter,
+                                                          images.reshape(-1, *images.shape[2:]), not self.training)
 
     # ------------------------------------------------------------------ fused query
     def _engine_for(self, points):

@@ -1,25 +1,82 @@
 """Coarse pixel-aligned implicit function, drop-in for the reference's `PIFuNetwNML.py`.
 
-`filter` stays PyTorch (it runs once per image and only orchestrates the caller's encoder);
-`query` / `get_preds` / `calc_normal` run in libpifu_b200.so."""
+`filter` stays PyTorch (it runs once per image: hourglass `Filter` + optional normal nets, executed
+by encoders.EncoderRunner); `query` / `get_preds` / `calc_normal` run in libpifu_b200.so."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import encoders
 from .BasePIFuNet import BasePIFuNet, _not_hot_path
 from .MLP import MLP
 from .engine import get_engine
 
 
-class PIFuNetwNML(BasePIFuNet):
-    """Same constructor as the reference (`PIFuNetwNML.py:19-71`) plus ``image_filter``: the
-    hourglass encoder (reference `Filter`, or any module returning ``(feature_list, normx)``)
-    is supplied by the caller - it is not part of the replaced path."""
+class _AsEncoder(nn.Module):
+    """A tensor -> tensor module (the normal nets) behind the encoder calling convention."""
 
-    def __init__(self, opt, projection_mode="orthogonal", criteria=None, image_filter=None):
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x):
+        return [self.net(x)], None
+
+
+class EncoderHost:
+    """Shared by the coarse and the fine net: how their PyTorch encoders are executed.
+    `encoder_opts` (channels_last / precision / graph, see encoders.EncoderRunner) may be changed
+    before the first `filter*` call or followed by `reset_encoder_runners()`.  The default (TF32
+    convolutions, NCHW, graph replay) is the arithmetic stock PyTorch gives the reference on this GPU
+    (`torch.backends.cudnn.allow_tf32` defaults to True); `precision='fp32'` is IEEE fp32 (3x slower),
+    `'bf16'` autocast trades ~1e-2 relative feature error for less element-wise traffic."""
+
+    encoder_opts = None
+
+    def _runner(self, key, module):
+        if self.encoder_opts is None:
+            self.encoder_opts = dict(channels_last=False, precision="tf32", graph=True)
+        runners = self.__dict__.setdefault("_enc_runners", {})
+        r = runners.get(key)
+        if r is None or r.module is not module:
+            r = encoders.EncoderRunner(module, **self.encoder_opts)
+            runners[key] = r
+        return r
+
+    def reset_encoder_runners(self):
+        self.__dict__.pop("_enc_runners", None)
+
+    def _run_normal_net(self, key, net, images):
+        wraps = self.__dict__.setdefault("_enc_wrap", {})
+        w = wraps.get(key)
+        if w is None or w.net is not net:
+            w = _AsEncoder(net)
+            wraps[key] = w
+        w.train(net.training)
+        return self._run_encoder(key, w, images, True)[0][0].detach()
+
+    def _run_encoder(self, key, module, images, last_only):
+        """(feature_list, normx) of `module(images)`; tuned execution only for inference on a CUDA device."""
+        if images.is_cuda and not torch.is_grad_enabled() and not module.training:
+            return self._runner(key, module)(images, last_only=last_only)
+        feats, normx = module(images)
+        return ([feats[-1]] if last_only else feats), normx
+
+
+class PIFuNetwNML(BasePIFuNet, EncoderHost):
+    """Same constructor as the reference (`PIFuNetwNML.py:19-71`) plus ``image_filter``: 'auto' builds
+    the hourglass `Filter` the reference builds (`:40-41`; None when `opt` has no encoder fields); a
+    module returning ``(feature_list, normx)`` - e.g. the reference's own `Filter` - is used as given;
+    None leaves the net without encoder (feature maps are then assigned to `im_feat_list` directly)."""
+
+    def __init__(self, opt, projection_mode="orthogonal", criteria=None, image_filter="auto"):
         super().__init__(projection_mode=projection_mode, criteria=criteria)
         self.name = "hg_pifu"
         self.opt = opt
+        if isinstance(image_filter, str):
+            if image_filter != "auto":
+                raise ValueError("image_filter must be 'auto', None or a module")
+            image_filter = encoders.build_encoder(opt, encoders.input_channels(opt), getattr(opt, "hg_down", "ave_pool"))
         self.image_filter = image_filter
         self.mlp = MLP(filter_channels=opt.mlp_dim, merge_layer=opt.merge_layer,
                        res_layers=opt.mlp_res_layers, norm=opt.mlp_norm, last_op=nn.Sigmoid())
@@ -33,6 +90,12 @@ class PIFuNetwNML(BasePIFuNet):
         self.intermediate_preds_list = []
         self.netF = None
         self.netB = None
+        if self.image_filter is not None:                           # `PIFuNetwNML.py:63-69`
+            from .networks import define_G
+            if getattr(opt, "use_front_normal", False):
+                self.netF = define_G(3, 3, 64, "global", 4, 9, 1, 3, "instance")
+            if getattr(opt, "use_back_normal", False):
+                self.netB = define_G(3, 3, 64, "global", 4, 9, 1, 3, "instance")
         self.nmlF = None
         self.nmlB = None
 
@@ -45,19 +108,17 @@ class PIFuNetwNML(BasePIFuNet):
         extra = []
         with torch.no_grad():
             if self.netF is not None:
-                self.nmlF = self.netF.forward(images).detach()
+                self.nmlF = self._run_normal_net("netF", self.netF, images)
                 extra.append(self.nmlF)
             if self.netB is not None:
-                self.nmlB = self.netB.forward(images).detach()
+                self.nmlB = self._run_normal_net("netB", self.netB, images)
                 extra.append(self.nmlB)
         if extra:
             nmls = torch.cat(extra, 1)
             if nmls.shape[2:] != images.shape[2:]:
                 nmls = F.interpolate(nmls, size=images.shape[2:], mode="bilinear", align_corners=True)
             images = torch.cat([images, nmls], 1)
-        self.im_feat_list, self.normx = self.image_filter(images)
-        if not self.training:
-            self.im_feat_list = [self.im_feat_list[-1]]
+        self.im_feat_list, self.normx = self._run_encoder("image_filter", self.image_filter, images, not self.training)
 
     # ------------------------------------------------------------------ fused query
     def _engine_for(self, points):

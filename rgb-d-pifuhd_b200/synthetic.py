@@ -135,3 +135,53 @@ def make_problem(seed=SEED_WEIGHTS, bias_std=0.0, depth_gain=100.0, feat_scale=1
     feat_f = band_limited_features(fine_dims[0] - coarse_dims[3], 512, 512, SEED_FEAT_FINE,
                                    scale=feat_scale)
     return dict(coarse=coarse, fine=fine, feat_coarse=feat_c, feat_fine=feat_f)
+
+
+# ----------------------------------------------------------------------------- encoder parity fixtures
+ENCODER_CASES = {
+    # name: (kind, constructor arguments, input shape)
+    "filter_group_avepool": ("filter", (2, 2, 6, 16, "group", "ave_pool", False), (1, 6, 64, 64)),
+    "filter_batch_nodown": ("filter", (1, 1, 3, 8, "batch", "no_down", True), (2, 3, 32, 32)),
+    "global_generator": ("define_G", (3, 3, 8, "global", 2, 2, 1, 3, "instance"), (1, 3, 32, 32)),
+}
+
+
+def fill_state(module, seed):
+    """Deterministic, key-addressed parameters and buffers for an encoder module: the same call on the
+    reference's module and on this package's gives identical tensors as long as the state_dict keys and
+    shapes agree (which is what checkpoint compatibility means).  Convolutions get fan-in scaled normal
+    weights so activations stay O(1) through a deep hourglass; norm layers get non-trivial affine
+    parameters and running statistics."""
+    import zlib
+    sd = module.state_dict()
+    out = {}
+    for key in sorted(sd.keys()):
+        t = sd[key]
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+        if key.endswith("num_batches_tracked"):
+            out[key] = t.clone()
+        elif key.endswith("running_var"):
+            out[key] = torch.rand(t.shape, generator=g) + 0.5
+        elif key.endswith("running_mean"):
+            out[key] = 0.1 * torch.randn(t.shape, generator=g)
+        elif t.dim() == 1 and key.endswith("weight"):
+            out[key] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        elif t.dim() == 1:
+            out[key] = 0.1 * torch.randn(t.shape, generator=g)
+        else:
+            fan_in = float(np.prod(t.shape[1:]))
+            out[key] = torch.randn(t.shape, generator=g) / np.sqrt(fan_in)
+    module.load_state_dict(out)
+    return out
+
+
+def encoder_input(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g)
+
+
+def state_signature(module):
+    """sha256 over 'key:shape' lines of the state_dict, sorted - equal signatures = checkpoints interchange."""
+    import hashlib
+    lines = ["%s:%s" % (k, tuple(v.shape)) for k, v in sorted(module.state_dict().items())]
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()
