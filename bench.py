@@ -262,7 +262,7 @@ def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3):
     return out
 
 
-def encoder_leg(dev, frames=8):
+def encoder_leg(dev, frames=8, time_modes=True, world=1):
     """SURVEY §8(f) row 3 / BASELINE configs[3]: the per-image PyTorch encoders (coarse 4-stack hourglass on
     512^2 + fine 1-stack on 1024^2, 6-channel RGB-D input) timed per execution mode, and the whole per-frame
     flow - images H2D from pinned memory, filter_global, filter_local, 256^3 octree reconstruction, mesh on
@@ -295,7 +295,7 @@ def encoder_leg(dev, frames=8):
         torch.cuda.synchronize(dev)
         return ev[0].elapsed_time(ev[1]) / reps
 
-    for name, opts in (("eager_fp32_nchw", dict(channels_last=False, precision="fp32", graph=False, autotune=False)),
+    for name, opts in () if not time_modes else (("eager_fp32_nchw", dict(channels_last=False, precision="fp32", graph=False, autotune=False)),
                        ("eager_tf32_nchw (stock PyTorch defaults)", dict(channels_last=False, precision="tf32", graph=False, autotune=False)),
                        ("fp32_nchw_graph", dict(channels_last=False, precision="fp32", graph=True)),
                        ("tf32_nchw_graph (default)", dict(channels_last=False, precision="tf32", graph=True)),
@@ -319,20 +319,36 @@ def encoder_leg(dev, frames=8):
     netMR.mlp.load_state_dict(prob["fine"])
     netMR.to(dev).eval()
 
+    solo = None                                     # N > 1: every rank reconstructs its own frames (a one-rank group)
+    if world > 1:
+        import torch.distributed as dist
+        for r in range(world):
+            g = dist.new_group([r])
+            if r == dist.get_rank():
+                solo = g
+
     def frame(f):
         netMR.filter_global(img512[f % 2].to(dev, non_blocking=True))
         netMR.filter_local(img1024[f % 2].to(dev, non_blocking=True))
-        return mesh_util.reconstruction(netMR, dev, calib, 256, None, None, thresh=0.5, use_octree=True, num_samples=5000)
+        return mesh_util.reconstruction(netMR, dev, calib, 256, None, None, thresh=0.5, use_octree=True, num_samples=5000,
+                                        group=solo)
 
     for f in range(2):
         mesh = frame(f)
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for f in range(frames):
         mesh = frame(f)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
-    out["frames_256_octree"] = {"frames": frames, "frames_per_s": frames / dt, "ms_per_frame": dt / frames * 1e3,
+    if world > 1:                                   # frames shard by frame, no communication: the box's rate is set by the slowest rank
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out["frames_256_octree"] = {"frames": frames * world, "frames_per_s": frames * world / dt, "ms_per_frame": dt / frames * 1e3,
+                                "ranks": world,
                                 "mesh": None if mesh == -1 else [len(mesh[0]), len(mesh[1])],
                                 "h2d_bytes_per_frame": (6 * 512 * 512 + 6 * 1024 * 1024) * 4}
     return out
@@ -527,6 +543,9 @@ def main():
         torch.cuda.empty_cache()
         _, netMR2, eng2, calib2 = build_mesh_problem(dev)        # seeded: identical on every rank
         mesh = mesh_latency_sharded(netMR2, calib2, dev, 512, 3)
+        del netMR2, eng2
+        torch.cuda.empty_cache()
+        enc = encoder_leg(dev, frames=8, time_modes=False, world=world)
 
     if rank == 0:
         print(json.dumps({

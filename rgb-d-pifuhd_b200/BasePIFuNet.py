@@ -7,6 +7,15 @@ def _not_hot_path(what):
     raise NotImplementedError("%s is outside the reconstruction hot path this package replaces" % what)
 
 
+def index(feat, uv):
+    """`BasePIFuNet.py:11-23`: bilinear samples [B, C, N] of `feat` [B, C, H, W] at `uv` [B, 2, N] in [-1, 1]
+    (align_corners=True, zeros outside).  On the query path this is fused into gather.cu; the function stays
+    for callers that sample an *image*, e.g. the vertex colours of `gen_mesh_imgColor`
+    (`reconstruction.py:110-116`)."""
+    grid = uv.transpose(1, 2).unsqueeze(2)
+    return torch.nn.functional.grid_sample(feat, grid, mode="bilinear", padding_mode="zeros", align_corners=True)[:, :, :, 0]
+
+
 def orthogonal(points, calib, transform=None):
     """`BasePIFuNet.py:25-43` - kept for callers that project by hand (`reconstruction.py:113`)."""
     if transform is not None:

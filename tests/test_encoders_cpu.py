@@ -89,3 +89,14 @@ def test_runner_on_cpu_is_the_plain_module():
     a, na = net(x)
     b, nb = encoders.EncoderRunner(net, precision="bf16", graph=True)(x)       # CPU: no autocast, no graph
     assert torch.equal(a[0], b[0]) and torch.equal(na, nb)
+
+
+def test_index_matches_oracle_closed_form():
+    """`BasePIFuNet.index` (vertex colours of gen_mesh_imgColor, `reconstruction.py:110-116`) against the oracle's
+    closed form of aten's bilinear grid_sample (align_corners=True, zeros padding)."""
+    from oracle import pifu_oracle as orc
+    from pifu_b200.BasePIFuNet import index
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn(1, 3, 37, 53, generator=g)
+    uv = torch.rand(1, 2, 500, generator=g) * 2.4 - 1.2          # some samples outside the image
+    assert (index(feat, uv) - orc.index_closed_form(feat, uv)).abs().max() < 1e-5
