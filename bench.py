@@ -220,22 +220,28 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
             # colours, 4 finite-difference queries per vertex in chunks of 50 000, then the OBJ text file
             import tempfile
             mv, mf = mesh[0], mesh[1]
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            verts_tensor = torch.from_numpy(mv.T).unsqueeze(0).to(device=dev).float()
-            color = np.zeros(mv.shape)
-            interval = 50000
-            for i in range(len(color) // interval + 1):
-                left = i * interval
-                right = -1 if i == len(color) // interval else (i + 1) * interval
-                netMR.calc_normal(verts_tensor[:, None, :, left:right], cal[:, None], cal)
-                color[left:right] = (netMR.nmls.detach().cpu().numpy()[0] * 0.5 + 0.5).T
-            t1 = time.perf_counter()
-            with tempfile.TemporaryDirectory() as tmp:
-                path = os.path.join(tmp, "mesh.obj")
-                mesh_util.save_obj_mesh_with_color(path, mv, mf, color)
-                t2 = time.perf_counter()
-                nbytes = os.path.getsize(path)
+
+            def tail():
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                verts_tensor = torch.from_numpy(mv.T).unsqueeze(0).to(device=dev).float()
+                color = np.zeros(mv.shape)
+                interval = 50000
+                for i in range(len(color) // interval + 1):
+                    left = i * interval
+                    right = -1 if i == len(color) // interval else (i + 1) * interval
+                    netMR.calc_normal(verts_tensor[:, None, :, left:right], cal[:, None], cal)
+                    color[left:right] = (netMR.nmls.detach().cpu().numpy()[0] * 0.5 + 0.5).T
+                t1 = time.perf_counter()
+                with tempfile.TemporaryDirectory() as tmp:
+                    path = os.path.join(tmp, "mesh.obj")
+                    mesh_util.save_obj_mesh_with_color(path, mv, mf, color)
+                    t2 = time.perf_counter()
+                    nbytes = os.path.getsize(path)
+                return t0, t1, t2, nbytes
+
+            tail()                                       # first call: lazy initialisations of the general-points path
+            t0, t1, t2, nbytes = tail()
             d["gen_mesh_tail"] = {"vertex_normals_ms": (t1 - t0) * 1e3, "queries": 4 * len(mv), "obj_write_ms": (t2 - t1) * 1e3,
                                   "obj_bytes": nbytes, "gen_mesh_total_ms": best + (t2 - t0) * 1e3}
         if mode == "octree":

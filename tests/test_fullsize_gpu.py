@@ -1,0 +1,104 @@
+"""BASELINE.json's full sizes through size-independent properties (the oracle cannot run 512^3 in a test):
+
+* dense 512^3 field: a 1/64 sub-lattice re-evaluated as explicit points through the per-layer kernels agrees
+  within the occupancy tolerance; the lattice is the reference's [-1, 1 - 2/R] grid (first / last voxel);
+* 512^3 octree field vs the dense field: the reference's octree is lossy by design (skip threshold 0.05), but on
+  this smooth field the signs at 0.5 must agree on >= 99.9 % of the voxels it covers, the last plane of each
+  axis stays 0.0 (`mesh_util.py:135`), and it evaluates a small fraction of the lattice;
+* marching cubes of either field: closed 2-manifold away from the volume border (every undirected edge is used
+  by exactly two triangles, with opposite orientations), faces index valid vertices, vertices sit inside the
+  index box, vertex count = the number of lattice edges the surface crosses (recounted with torch);
+* the mesh of `reconstruction()` is that mesh mapped through inv(calib) . mat with flipped faces
+  (`mesh_util.py:87-92`)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import calibrated_problem, syn
+from test_query_gpu import build_nets, sign_agreement
+
+pytestmark = pytest.mark.gpu
+R = 512
+
+
+@pytest.fixture(scope="module")
+def fields():
+    torch.set_grad_enabled(False)
+    prob, _ = calibrated_problem(saturated=True)
+    netG, netMR = build_nets(prob)
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    calib = syn.default_calib()
+    netMR.query(syn.random_points(256).cuda(), calib.cuda())
+    dense = eng.eval_grid(2, R, calib[0]).view(R, R, R)
+    _, octree, ev = eng.eval_grid_octree(2, R, calib[0], want64=False, want32=True)
+    return netMR, eng, calib, dense, octree.view(R, R, R), ev
+
+
+def test_dense_sublattice_matches_explicit_points(fields):
+    netMR, eng, calib, dense, _, _ = fields
+    idx = torch.arange(3, R, 8, device="cuda")
+    i, j, k = torch.meshgrid(idx, idx, idx, indexing="ij")
+    pts = torch.stack([-1 + 2.0 * i / R, -(-1 + 2.0 * j / R), -1 + 2.0 * k / R]).reshape(3, -1).float()   # calib = diag(1,-1,1,1)
+    netMR.query(pts[None], calib.cuda())
+    sub = netMR.get_preds().view(len(idx), len(idx), len(idx))
+    ref = dense[3::8, 3::8, 3::8]
+    assert float((sub - ref).abs().max()) < 8e-3            # saturated field: the logit error reads larger at the surface
+    assert sign_agreement(sub.cpu().numpy(), ref.cpu().numpy()) >= 0.9999
+    assert float(dense.min()) >= 0.0 and float(dense.max()) <= 1.0
+
+
+def test_octree_field_properties(fields):
+    _, _, _, dense, octree, ev = fields
+    assert len(ev) == 4 and ev[0] == 64 ** 3 and sum(ev) < 0.1 * R ** 3      # strides 8, 4, 2, 1; a thin shell is evaluated
+    assert float(octree[-1].abs().max()) == 0.0 and float(octree[:, -1].abs().max()) == 0.0 and float(octree[:, :, -1].abs().max()) == 0.0
+    a, b = octree[:-1, :-1, :-1], dense[:-1, :-1, :-1]
+    assert float(((a > 0.5) == (b > 0.5)).float().mean()) >= 0.999
+
+
+def _check_mesh(eng, field):
+    verts, faces, normals, values = eng.marching_cubes(field, 0.5)
+    V, F = verts.shape[0], faces.shape[0]
+    assert V > 100000 and F > 200000
+    f = faces.long()
+    assert int(f.min()) == 0 and int(f.max()) == V - 1 and len(torch.unique(f)) == V          # every vertex is used
+    assert float(verts.min()) >= 0.0 and float(verts.max()) <= R - 1 + 1e-9      # (the weighted average may overshoot by an ulp)
+    # vertices = lattice edges whose end points straddle the level (strict > as in the classify pass)
+    ins = field > 0.5
+    crossings = sum(int((ins.narrow(a, 0, R - 1) != ins.narrow(a, 1, R - 1)).sum()) for a in range(3))
+    assert V == crossings
+    # directed edges: each appears once, and its reverse appears once unless the edge lies on the volume border
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0)
+    key = e[:, 0] * V + e[:, 1]
+    rkey = e[:, 1] * V + e[:, 0]
+    assert len(torch.unique(key)) == len(key)
+    has_twin = torch.isin(rkey, key)
+    v = verts
+    on_border = ((v < 1e-9) | (v > R - 1 - 1e-9)).any(1)
+    lonely = e[~has_twin]
+    assert bool(on_border[lonely[:, 0]].all()) and bool(on_border[lonely[:, 1]].all())
+    assert float(has_twin.float().mean()) > 0.99
+    assert bool(torch.isfinite(normals).all()) and float((values - 0.5).min()) >= 0.0
+    return verts, faces
+
+
+def test_marching_cubes_manifold_dense_and_octree(fields):
+    _, eng, _, dense, octree, _ = fields
+    _check_mesh(eng, dense.contiguous())
+    _check_mesh(eng, octree.contiguous())
+
+
+def test_reconstruction_is_the_transformed_mesh(fields):
+    from pifu_b200 import mesh_util
+    netMR, eng, calib, _, octree, _ = fields
+    verts, faces, _, _ = eng.marching_cubes(octree.contiguous(), 0.5)
+    out = mesh_util.reconstruction(netMR, "cuda", calib.cuda(), R, None, None, use_octree=True, num_samples=5000)
+    assert out != -1
+    mat = np.eye(4)
+    mat[0, 0] = mat[1, 1] = mat[2, 2] = 2.0 / R
+    mat[:3, 3] = -1.0
+    trans = np.linalg.inv(calib[0].numpy()) @ mat
+    want = (trans[:3, :3] @ verts.cpu().numpy().T + trans[:3, 3:4]).T
+    assert out[0].dtype == np.float64 and np.abs(out[0] - want).max() < 1e-12
+    assert np.array_equal(out[1], faces.cpu().numpy()[:, ::-1])        # det < 0 for the readData calibration
