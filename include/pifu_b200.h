@@ -94,7 +94,8 @@ int pifu_eval_grid(pifu_ctx* ctx, int levels, int R0, int R1, int R2, long long 
                    long long id_end, const float* calib, const double* calib_inv, float* out,
                    void* stream);
 
-/* Same, for an explicit list of lattice ids (device int64 [n]); out[p] = occupancy of ids[p]. */
+/* Same, for an explicit list of lattice ids (device int64 [n]); out[p] = occupancy of ids[p].  Sorted
+ * lists (octree frontiers) are the fast case: see the chain kernel's run-list form below. */
 int pifu_eval_lattice_ids(pifu_ctx* ctx, int levels, int R0, int R1, int R2, const long long* ids,
                           long long n, const float* calib, const double* calib_inv, float* out,
                           void* stream);
@@ -164,17 +165,24 @@ long long pifu_launch_count(pifu_ctx* ctx);
 int pifu_profile_enable(pifu_ctx* ctx, int on);
 int pifu_profile_read(pifu_ctx* ctx, long long* launches, double* total_ms, double* total_flops);
 
-/* Same, restricted to one kernel kind (0 = per-layer tcgen05 kernel, 1 = lattice chain kernel);
+/* Same, restricted to one kernel kind (0 = per-layer tcgen05 kernel, 1 = chain kernel, lattice form, 2 = chain kernel, run-list form);
  * does not clear the records. */
 int pifu_profile_read_kind(pifu_ctx* ctx, int kind, long long* launches, double* total_ms, double* total_flops);
 
-/* Lattice chain kernel (whole MLP stack of a 128-point lattice-column tile in one kernel,
- * activations resident in shared/tensor memory).  pifu_eval_grid uses it automatically when
- * both MLPs have the reference configuration (options.py:86-87,92-93), the projection is
- * orthogonal, R2 is a multiple of 128 and the calibration does not mix z into x/y; anything
- * else takes the per-layer kernels.  pifu_set_chain(ctx, 0) forces the per-layer kernels (A/B
- * measurements, parity tests between the two paths); pifu_chain_ready reports 1 when the
- * chain operands are built and enabled. */
+/* Chain kernel (whole MLP stack of a 128-point tile in one kernel, activations resident in
+ * shared/tensor memory).  Two forms, both taken automatically when both MLPs have the reference
+ * configuration (options.py:86-87,92-93), the projection is orthogonal and the calibration does not
+ * mix z into x/y:
+ *   lattice form   pifu_eval_grid, R2 a multiple of 128: a tile is 128 consecutive points of one
+ *                  lattice column;
+ *   run-list form  pifu_eval_lattice_ids / pifu_eval_grid_octree: a tile is 128 consecutive entries of
+ *                  the id list; consecutive ids of one lattice column (an octree frontier is compacted
+ *                  in C order) share one set of per-column constants.  Every list takes this form
+ *                  whatever its run lengths, so a point's value does not depend on how a caller cuts
+ *                  a list into calls.
+ * Anything else takes the per-layer kernels.  pifu_set_chain(ctx, 0) forces the per-layer kernels
+ * everywhere, 2 keeps only the lattice form (A/B measurements, parity tests between the paths), 1
+ * (default) enables both; pifu_chain_ready reports 1 when the chain operands are built and enabled. */
 int pifu_set_chain(pifu_ctx* ctx, int enabled);
 int pifu_chain_ready(pifu_ctx* ctx);
 

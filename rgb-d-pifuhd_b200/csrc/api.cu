@@ -625,9 +625,6 @@ int grow_cc(ChainPlan& P, long long cols) {
     return 0;
 }
 
-int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const float* cl, const float* cg,
-              const QueryOut& o, cudaStream_t s);
-
 // A sorted list of lattice ids (an octree frontier) through the chain kernel's run-list form.  Segments
 // never cross a 1024-row block (runs.cu), so the list is cut greedily into launches of whole blocks: at
 // most `chunk_tiles` tiles of rows and at most CHAIN_MAX_SEGS segments (the size of the constants buffer).
