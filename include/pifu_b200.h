@@ -156,6 +156,13 @@ int pifu_mc_count_slab(pifu_ctx* ctx, const float* field, int n0, int n1, int n2
 int pifu_write_obj(const char* path, const double* verts, const double* colors, long long nverts,
                    const int* faces, long long nfaces);
 
+/* Element-wise helper of the PyTorch image encoders (no context): y = relu?((x - mean) / sqrt(var + eps) * weight
+ * + bias) per channel, the eval-mode BatchNorm2d + ReLU pairs of Filter.py:23-69 in one pass.  x, y: device fp32
+ * [N][C][HW] contiguous (y may alias x); statistics / affine parameters: device fp32 [C] (weight / bias may be null).
+ * Launches on the CURRENT device. */
+int pifu_bn_relu_f32(const float* x, const float* running_mean, const float* running_var, const float* weight,
+                     const float* bias, double eps, int relu, float* y, long long N, int C, long long HW, void* stream);
+
 /* Number of kernels launched by this context since creation (bench accounting). */
 long long pifu_launch_count(pifu_ctx* ctx);
 

@@ -16,9 +16,37 @@ Structure (reference file:line):
                                    hourglasses with intermediate supervision taps `l{i}` and the
                                    `bl{i}` / `al{i}` re-injection between stacks
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+def _fused_ok(norm, x):
+    """Eval-mode BatchNorm2d + ReLU on a contiguous fp32 CUDA tensor, no autograd: one pass in libpifu_b200.so
+    (csrc/encoder_ops.cu) instead of two kernels and four passes.  PIFU_FUSED_BN_RELU=0 switches it off."""
+    return (isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats and x.is_cuda
+            and x.dtype == torch.float32 and x.is_contiguous() and not torch.is_grad_enabled()
+            and not torch.is_autocast_enabled() and os.environ.get("PIFU_FUSED_BN_RELU", "1") != "0")
+
+
+def norm_relu(norm, x):
+    """relu(norm(x)) - the pre-activation of every convolution of the hourglass (`Filter.py:61-63,187,211`)."""
+    if not _fused_ok(norm, x):
+        return F.relu(norm(x))
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(n * c, 1)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None      # noqa: E731
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pifu_bn_relu_f32(ptr(x), ptr(norm.running_mean), ptr(norm.running_var), ptr(norm.weight), ptr(norm.bias),
+                                        float(norm.eps), 1, ptr(y), n, c, hw,
+                                        ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return y
 
 
 def _norm(kind, channels):
@@ -48,10 +76,11 @@ class ConvBlock(nn.Module):
                                             nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, bias=False))
 
     def forward(self, x):
-        shortcut = x if self.downsample is None else self.downsample(x)
+        # (downsample = [bn4, ReLU, 1x1 conv]; spelled out so the norm + ReLU pair can take the fused kernel)
+        shortcut = x if self.downsample is None else self.downsample[2](norm_relu(self.bn4, x))
         parts, y = [], x
         for n in (1, 2, 3):
-            y = getattr(self, "conv%d" % n)(F.relu(getattr(self, "bn%d" % n)(y)))
+            y = getattr(self, "conv%d" % n)(norm_relu(getattr(self, "bn%d" % n), y))
             parts.append(y)
         return torch.cat(parts, 1) + shortcut
 
@@ -119,7 +148,7 @@ class Filter(nn.Module):
                 self.add_module("al%d" % i, nn.Conv2d(last_channels, 256, kernel_size=1, stride=1, padding=0))
 
     def forward(self, x):
-        x = F.relu(self.bn1(self.conv1(x)))
+        x = norm_relu(self.bn1, self.conv1(x))
         if self.down_type == "ave_pool":
             x = F.avg_pool2d(self.conv2(x), 2, stride=2)
         elif self.down_type == "no_down":
@@ -132,7 +161,7 @@ class Filter(nn.Module):
         for i in range(self.n_stack):
             m = self._modules
             ll = m["top_m_%d" % i](m["m%d" % i](carry))
-            ll = F.relu(m["bn_end%d" % i](m["conv_last%d" % i](ll)))
+            ll = norm_relu(m["bn_end%d" % i], m["conv_last%d" % i](ll))
             tap = m["l%d" % i](ll)
             outputs.append(torch.tanh(tap) if self.use_sigmoid else tap)
             if i < self.n_stack - 1:

@@ -72,3 +72,24 @@ def test_filter_calls_use_the_runner_and_feed_the_query_path():
     netMR.query(pts, syn.default_calib().cuda())
     p = netMR.get_preds()
     assert p.shape == (1, 1, 1000) and bool(torch.isfinite(p).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 33, 37), (1, 256, 64, 64), (3, 5, 1, 8)])
+def test_fused_bn_relu_matches_torch(shape):
+    """csrc/encoder_ops.cu against F.relu(BatchNorm2d.eval()(x)): same formula, one pass."""
+    from pifu_b200.Filter import norm_relu, _fused_ok
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(1)
+    bn = torch.nn.BatchNorm2d(shape[1])
+    bn.running_mean.copy_(torch.randn(shape[1], generator=g))
+    bn.running_var.copy_(torch.rand(shape[1], generator=g) + 0.3)
+    bn.weight.copy_(1 + 0.2 * torch.randn(shape[1], generator=g))
+    bn.bias.copy_(0.3 * torch.randn(shape[1], generator=g))
+    bn = bn.cuda().eval()
+    x = (2 * torch.randn(shape, generator=g)).cuda()
+    assert _fused_ok(bn, x)
+    y = norm_relu(bn, x)
+    ref = torch.nn.functional.relu(bn(x))
+    assert y.shape == ref.shape and float((y - ref).abs().max()) < 1e-5          # a few ulps: cuDNN folds the affine map differently
+    assert not _fused_ok(bn.train(), x) and not _fused_ok(bn.eval(), x.half())
+    assert not _fused_ok(torch.nn.GroupNorm(1, shape[1]).cuda(), x)
