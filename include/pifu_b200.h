@@ -163,6 +163,12 @@ int pifu_write_obj(const char* path, const double* verts, const double* colors, 
 int pifu_bn_relu_f32(const float* x, const float* running_mean, const float* running_var, const float* weight,
                      const float* bias, double eps, int relu, float* y, long long N, int C, long long HW, void* stream);
 
+/* out[n] = concatenate(a[n], b[n], c[n]) + s[n]: the tail of a hourglass block (Filter.py:65-67) in one pass.  Device
+ * fp32, contiguous, 16-byte aligned; la / lb / lc = floats of ONE image in a / b / c (multiples of 4); s and out hold
+ * la + lb + lc floats per image.  Launches on the CURRENT device. */
+int pifu_cat3_add_f32(const float* a, const float* b, const float* c, const float* s, float* out, long long N,
+                      long long la, long long lb, long long lc, void* stream);
+
 /* Number of kernels launched by this context since creation (bench accounting). */
 long long pifu_launch_count(pifu_ctx* ctx);
 

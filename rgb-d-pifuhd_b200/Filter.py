@@ -49,6 +49,28 @@ def norm_relu(norm, x):
     return y
 
 
+def cat3_add(parts, shortcut):
+    """cat(parts, 1) + shortcut - the tail of a block (`Filter.py:65-67`); one pass in libpifu_b200.so when the four
+    tensors are contiguous fp32 CUDA tensors outside autograd / autocast, else the two PyTorch operators."""
+    ok = (shortcut.is_cuda and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+          and os.environ.get("PIFU_FUSED_BN_RELU", "1") != "0"
+          and all(t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in (*parts, shortcut))
+          and all((t.numel() // max(t.shape[0], 1)) % 4 == 0 for t in parts) and shortcut.shape[0] <= 65535)
+    if not ok:
+        return torch.cat(parts, 1) + shortcut
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    out = torch.empty_like(shortcut)
+    n = shortcut.shape[0]
+    sizes = [t.numel() // max(n, 1) for t in parts]
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())      # noqa: E731
+    with torch.cuda.device(shortcut.device):
+        _lib.check(lib.pifu_cat3_add_f32(ptr(parts[0]), ptr(parts[1]), ptr(parts[2]), ptr(shortcut), ptr(out), n, *sizes,
+                                         ctypes.c_void_p(torch.cuda.current_stream(shortcut.device).cuda_stream)))
+    return out
+
+
 def _norm(kind, channels):
     if kind == "batch":
         return nn.BatchNorm2d(channels)
@@ -82,7 +104,7 @@ class ConvBlock(nn.Module):
         for n in (1, 2, 3):
             y = getattr(self, "conv%d" % n)(norm_relu(getattr(self, "bn%d" % n), y))
             parts.append(y)
-        return torch.cat(parts, 1) + shortcut
+        return cat3_add(parts, shortcut)
 
 
 class HourGlass(nn.Module):

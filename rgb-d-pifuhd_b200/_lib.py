@@ -50,6 +50,8 @@ SIGNATURES = {
     "pifu_write_obj": (ctypes.c_int, [ctypes.c_char_p, VP, VP, ctypes.c_longlong, VP, ctypes.c_longlong]),
     "pifu_bn_relu_f32": (ctypes.c_int, [VP, VP, VP, VP, VP, ctypes.c_double, ctypes.c_int, VP, ctypes.c_longlong,
                                         ctypes.c_int, ctypes.c_longlong, VP]),
+    "pifu_cat3_add_f32": (ctypes.c_int, [VP, VP, VP, VP, VP, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                                         ctypes.c_longlong, VP]),
     "pifu_launch_count": (ctypes.c_longlong, [VP]),
     "pifu_profile_enable": (ctypes.c_int, [VP, ctypes.c_int]),
     "pifu_profile_read": (ctypes.c_int, [VP, c_ll_p, c_double_p, c_double_p]),

@@ -43,10 +43,48 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const float* __restrict__ 
     }
 }
 
+// out[n] = cat(a[n], b[n], c[n]) + s[n] over the channel axis (the tail of a hourglass block, `Filter.py:65-67`):
+// stock PyTorch materialises the concatenation and then adds = 5 passes over the block's output, here 3.
+// One block row per image; `la / lb / lc` = floats of one image in a / b / c.
+__global__ void __launch_bounds__(256) cat3_add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       const float* __restrict__ c, const float* __restrict__ s,
+                                                       float* __restrict__ out, long long la, long long lb, long long lc) {
+    const long long n = blockIdx.y, per = la + lb + lc;
+    const float4* a4 = reinterpret_cast<const float4*>(a + n * la);
+    const float4* b4 = reinterpret_cast<const float4*>(b + n * lb);
+    const float4* c4 = reinterpret_cast<const float4*>(c + n * lc);
+    const float4* s4 = reinterpret_cast<const float4*>(s + n * per);
+    float4* o4 = reinterpret_cast<float4*>(out + n * per);
+    const long long qa = la >> 2, qb = lb >> 2, q = per >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < q; i += stride) {
+        const float4 v = i < qa ? a4[i] : (i < qa + qb ? b4[i - qa] : c4[i - qa - qb]);
+        const float4 r = s4[i];
+        o4[i] = make_float4(v.x + r.x, v.y + r.y, v.z + r.z, v.w + r.w);
+    }
+}
+
 }  // namespace
 }  // namespace pifu
 
 using namespace pifu;
+
+extern "C" int pifu_cat3_add_f32(const float* a, const float* b, const float* c, const float* s, float* out, long long N,
+                                 long long la, long long lb, long long lc, void* stream) {
+    if (!a || !b || !c || !s || !out || N < 0 || la < 0 || lb < 0 || lc < 0) { set_error("bad arguments to pifu_cat3_add_f32"); return -1; }
+    if ((la | lb | lc) & 3) { set_error("pifu_cat3_add_f32: per-image sizes must be multiples of 4 floats"); return -1; }
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                         reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(out);
+    if (al & 15) { set_error("pifu_cat3_add_f32: pointers must be 16-byte aligned"); return -1; }
+    if (N == 0 || la + lb + lc == 0) return 0;
+    if (N > 65535) { set_error("pifu_cat3_add_f32: batch above 65535"); return -1; }
+    long long bx = ((la + lb + lc) / 4 + 256 * 4 - 1) / (256 * 4);
+    if (bx > 4096) bx = 4096;
+    cat3_add_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(N)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        a, b, c, s, out, la, lb, lc);
+    PIFU_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int pifu_bn_relu_f32(const float* x, const float* running_mean, const float* running_var, const float* weight,
                                 const float* bias, double eps, int relu, float* y, long long N, int C, long long HW,

@@ -93,3 +93,16 @@ def test_fused_bn_relu_matches_torch(shape):
     assert y.shape == ref.shape and float((y - ref).abs().max()) < 1e-5          # a few ulps: cuDNN folds the affine map differently
     assert not _fused_ok(bn.train(), x) and not _fused_ok(bn.eval(), x.half())
     assert not _fused_ok(torch.nn.GroupNorm(1, shape[1]).cuda(), x)
+
+
+def test_fused_cat3_add_matches_torch():
+    from pifu_b200.Filter import cat3_add
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(2)
+    for n, c, h, w in ((1, 256, 32, 32), (3, 64, 6, 10)):
+        parts = [torch.randn(n, c // d, h, w, generator=g).cuda() for d in (2, 4, 4)]
+        sc = torch.randn(n, c, h, w, generator=g).cuda()
+        assert torch.equal(cat3_add(parts, sc), torch.cat(parts, 1) + sc)
+    odd = [torch.randn(1, k, 3, 3, generator=g).cuda() for k in (2, 1, 1)]          # 9 floats per channel: falls back
+    sc = torch.randn(1, 4, 3, 3, generator=g).cuda()
+    assert torch.equal(cat3_add(odd, sc), torch.cat(odd, 1) + sc)
