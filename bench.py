@@ -534,7 +534,8 @@ def main():
             achieved = chain_flops / (chain_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "chain_kernel (tcgen05 CTA-pair MLP chain, activations on-chip)",
                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                        "traffic": ncu_traffic("chain_kernel"), "peak_source": peaks["source"], "launches_per_step": n_c,
+                        "traffic": (ncu_traffic("chain_kernel") or {}).get("bytes_per_launch"),
+                        "traffic_detail": ncu_traffic("chain_kernel"), "peak_source": peaks["source"], "launches_per_step": n_c,
                         "avg_launch_us": chain_ms * 1e3 / n_c, "share_of_step": chain_ms / ms_per_step,
                         "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
                         "executed_flop_per_query": 2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128),
@@ -580,10 +581,10 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "dtype": "f16", "data": "synthetic",
             "config": {"workload": "PIFuMRNet multi-level (coarse 257-1024-512-256 trunk + fine 272-512-256-128-1), dense "
                                    "%dx%dx%d lattice, %d^3 = %d queries per GPU (BASELINE configs[1])" % (R0, res, res, res, per_rank),
-                       "parallelism": "slab%d" % world, "mlp_norm": "none",
+                       "parallelism": "slab%d" % world, "mlp_norm": "none", "arithmetic": "f16 tensor-core operands, f32 accumulate and epilogues",
                        "l2": "256 MiB flush write between timed iterations",
                        "path": "chain" if eng.chain_ready() else "per-layer"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
