@@ -28,6 +28,15 @@
 //   J3 F0[:256] -> Hb   J4 F0[256:] -> Ha   J5 F1 -> Hb   J6 F2 -> Ha[0:128]
 // Shared memory: P = 4 k-block slots (y0 ring during J0/J1, then phi, which stays resident for
 // J3-J6), D = 4 k-block slots (ring for y1 / fine activations), W = weight ring.
+//
+// Two forms of the same pipeline (template parameter ROWS):
+//   lattice form   a tile = 128 consecutive points of ONE lattice column (pifu_eval_grid); its constants arrive by
+//                  TMA in shared memory and every row adds the same vectors;
+//   run-list form  a tile = 128 consecutive entries of a lattice-id list (octree frontiers, `mesh_util.py:142-149`,
+//                  compacted in C order so the points of a column are consecutive); runs.cu numbers the runs
+//                  ("segments"), api.cu computes one set of constants per segment, and every row reads its own
+//                  segment's constants from global memory.  What was tried to make those reads cheaper, and why it
+//                  did not help, is recorded in profiles/r01_chain_rows_ncu_summary.md.
 #include <cstdlib>
 
 #include "common.cuh"
