@@ -4,11 +4,11 @@ PIFuMRNet multi-level, dense 256^3 lattice, per GPU).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one 256^3 lattice (16 777 216 queries) per GPU:
-in-kernel lattice generation -> calib projection -> bilinear sampling of the coarse/fine feature
-maps -> coarse MLP trunk -> fine MLP -> occupancy field in HBM.  For N > 1 (torchrun, one rank
-per GPU) the lattice is (256*N) x 256 x 256, slab-sharded along axis 0, no data-path collective;
-the slabs are gathered to rank 0 with NCCL inside the timed step (weak scaling).
+One "step" = one pass of the hot path over one dense lattice: in-kernel lattice generation -> calib
+projection -> bilinear sampling of the coarse/fine feature maps -> coarse MLP trunk -> fine MLP ->
+occupancy field in HBM.  N = 1: the 256^3 lattice of configs[1] (16 777 216 queries).  N > 1 (torchrun, one
+rank per GPU): ONE 512^3 lattice (configs[2]'s volume, 134 217 728 queries) slab-sharded along axis 0, no
+data-path collective; the slabs are gathered to rank 0 with NCCL inside the timed step (strong scaling).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -56,6 +56,18 @@ def build_problem():
     from pifu_b200 import synthetic as syn
     prob = syn.make_problem(bias_std=0.0)
     return prob, syn.default_calib()
+
+
+def calibrate_from_pilot(prob, pilot_preds, saturated=False):
+    """the raw random-init field is a Gaussian of width 4.5e-4 around 0.5 (no surface, every sign a
+    coin flip).  Only the last fine conv is rescaled, from the un-calibrated net's predictions on seeded pilot
+    points, so that 2 % of the cube exceeds 0.5 with O(1) logits (the parity-gate field); `saturated` adds the x8
+    gain of the octree / marching-cubes field.  The same tensors then go to every implementation."""
+    from pifu_b200 import synthetic as syn
+    syn.calibrate_last_layer(prob["fine"], 3, pilot_preds)
+    if saturated:
+        syn.saturate(prob["fine"], 3)
+    return prob
 
 
 class ClockSampler:
@@ -122,36 +134,63 @@ class ClockSampler:
                 "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_queries_per_s(prob, calib, n_points, steps=1, warmup=0):
-    """Times the CPU oracle (torch-CPU port of PIFuMRNet.query, same library kernels the
-    reference runs) on a bounded sample of the same lattice: every (RES^3 // n_points)-th point."""
+def sample_ids(res, n_points):
+    """The bounded sample of the res^3 lattice the CPU legs evaluate: every (res^3 // n_points)-th lattice id."""
+    stride = max(1, res ** 3 // n_points)
+    return np.arange(0, res ** 3, stride)[:n_points]
+
+
+def oracle_fine_state(prob):
     from pifu_b200 import config
     from oracle import pifu_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
     oc, of = config.coarse_opt(), config.fine_opt()
     coarse = orc.CoarseState(prob["coarse"], prob["feat_coarse"], oc)
-    fine = orc.FineState(prob["fine"], prob["feat_fine"], of, coarse)
-    stride = max(1, RES ** 3 // n_points)
-    ids = np.arange(0, RES ** 3, stride)[:n_points]
-    k, j, i = ids % RES, (ids // RES) % RES, ids // (RES * RES)
-    pts = np.stack([-1 + 2.0 * i / RES, -(-1 + 2.0 * j / RES), -1 + 2.0 * k / RES]).astype(np.float32)
+    return orc.FineState(prob["fine"], prob["feat_fine"], of, coarse)
+
+
+def cpu_port_queries_per_s(prob, calib, n_points, steps=1, warmup=0, res=RES, keep=False):
+    """Times the CPU oracle (torch-CPU port of PIFuMRNet.query, same library kernels the
+    reference runs) on a bounded sample of the same lattice: every (res^3 // n_points)-th point.
+    With `keep` the occupancies of the sample are returned as well (the parity block compares the
+    GPU field with them)."""
+    from oracle import pifu_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    fine = oracle_fine_state(prob)
+    ids = sample_ids(res, n_points)
+    k, j, i = ids % res, (ids // res) % res, ids // (res * res)
+    pts = np.stack([-1 + 2.0 * i / res, -(-1 + 2.0 * j / res), -1 + 2.0 * k / res]).astype(np.float32)
     pts = torch.from_numpy(pts)[None]
     chunk = 100000                      # gen_mesh_imgColor's num_samples (reconstruction.py:108)
-    times = []
+    times, vals = [], None
     with torch.no_grad():
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            for s in range(0, pts.shape[2], chunk):
-                orc.query_fine(fine, pts[:, :, s:s + chunk], calib)
+            out = [orc.query_fine(fine, pts[:, :, s:s + chunk], calib)[0] for s in range(0, pts.shape[2], chunk)]
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
-    return pts.shape[2] / (sum(times) / len(times)), torch.get_num_threads(), pts.shape[2], sum(times) / len(times)
+            if keep:
+                vals = torch.cat(out, 2).numpy().ravel()
+    sec = sum(times) / len(times)
+    res_t = (pts.shape[2] / sec, torch.get_num_threads(), pts.shape[2], sec)
+    return res_t + (vals,) if keep else res_t
 
 
-def build_mesh_problem(dev):
+def parity_block(out, ref, what):
+    """GPU field vs the CPU oracle on the same lattice points (north_star: <= 1e-3 absolute, >= 99.99 % sign
+    agreement at the 0.5 iso-level, identical in-bounds masks)."""
+    out, ref = np.asarray(out, dtype=np.float32).ravel(), np.asarray(ref, dtype=np.float32).ravel()
+    return {"n": int(ref.size), "max_abs_err": float(np.abs(out - ref).max()),
+            "sign_agreement": float(((out > 0.5) == (ref > 0.5)).mean()),
+            "mask_equal": bool(np.array_equal(out == 0, ref == 0)),
+            "occupied_fraction": float((ref > 0.5).mean()), "what": what}
+
+
+def build_nets(dev, saturated, with_prob=False):
     """Two-level net whose random-init field has an iso-surface: only the last
-    fine conv is rescaled, from the un-calibrated net's own predictions on seeded pilot points,
-    so ~2 % of the cube is occupied and the sigmoid saturates away from the surface."""
+    fine conv is rescaled, from the un-calibrated net's own predictions on seeded pilot points
+    (fast arithmetic on the GPU; the raw logits are ~1e-3, so their fp16 noise is ~1e-6 of the
+    calibrated spread), so ~2 % of the cube is occupied; `saturated` adds the x8 gain that makes
+    the sigmoid saturate away from the surface (octree / marching-cubes field)."""
     from pifu_b200 import PIFuMRNet, PIFuNetwNML, config, synthetic as syn
     prob = syn.make_problem(bias_std=0.0)
     calib = syn.default_calib()
@@ -163,26 +202,84 @@ def build_mesh_problem(dev):
     netG.im_feat_list = [prob["feat_coarse"].to(dev)]
     netMR.im_feat_list = [prob["feat_fine"].to(dev)]
     pilot = syn.random_points(20000, syn.SEED_PILOT, -1.0, 1.0)
-    netMR.query(pilot.to(dev), calib.to(dev))
+    eng = netMR._engine_for(torch.zeros(1, device=dev))
+    eng.set_precision("split")                  # the pilot in fp32-level arithmetic: the calibration is then the same
+    netMR.query(pilot.to(dev), calib.to(dev))   # tensor the oracle would derive (a scale and a bias of one layer)
+    eng.set_precision("fast")
     p = netMR.get_preds().float().cpu().numpy()
-    syn.calibrate_last_layer(prob["fine"], 3, p)
-    syn.saturate(prob["fine"], 3)
+    calibrate_from_pilot(prob, p, saturated)
     netMR.mlp.load_state_dict(prob["fine"])
     netMR.to(dev).eval()
     eng = netMR._engine_for(torch.zeros(1, device=dev))
     eng.sync_features(0, netG.im_feat_list[-1])
     eng.sync_features(1, netMR.im_feat_list[-1])
+    if with_prob:
+        return netG, netMR, eng, calib, prob
     return netG, netMR, eng, calib
 
 
-def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
+def build_mesh_problem(dev):
+    return build_nets(dev, saturated=True)
+
+
+def mesh_cpu_baseline(prob, calib, res):
+    """BASELINE's second figure on the host: the reference's CPU reconstruction path (`mesh_util.py:40-96` with
+    use_octree=True) restated by the oracle - create_grid + calib pre-transform, eval_grid_octree with the
+    torch-CPU query as eval_func (num_samples = 100000), marching cubes (oracle/mc_ref.c; scikit-image is absent).
+    Returns the timings and the field / mesh sizes the GPU results are compared with."""
+    from oracle import mc_oracle
+    from oracle import pifu_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    fine = oracle_fine_state(prob)
+    t0 = time.perf_counter()
+    coords, _, _ = orc.lattice_coords(res, calib)
+    t1 = time.perf_counter()
+    stats = []
+    ef = orc.make_eval_func(lambda p, c: orc.query_fine(fine, p, c), calib)
+    with torch.no_grad():
+        sdf = orc.eval_grid_octree(coords, ef, num_samples=100000, stats=stats)
+    del coords
+    t2 = time.perf_counter()
+    verts, faces, _, _, _ = mc_oracle.marching_cubes(sdf, 0.5)
+    t3 = time.perf_counter()
+    return {"sdf": sdf, "evaluated_per_level": [n for _, n in stats], "verts": len(verts), "faces": len(faces),
+            "create_grid_ms": (t1 - t0) * 1e3, "octree_ms": (t2 - t1) * 1e3, "mc_ms": (t3 - t2) * 1e3,
+            "total_ms": (t3 - t0) * 1e3, "cores": torch.get_num_threads()}
+
+
+def mesh_latency(netMR, eng, calib, dev, res=512, reps=3, cpu=None):
     """BASELINE.json's second figure: end-to-end latency of mesh_util.reconstruction at res^3 on
     this GPU (features resident; field -> marching cubes -> mesh on the host), octree and dense,
-    with the phases timed by CUDA events and the marching-cubes HBM roofline."""
+    with the phases timed by CUDA events and the marching-cubes HBM roofline.  `cpu`: the host's
+    result of the same reconstruction (mesh_cpu_baseline) the octree fields are compared with."""
     from pifu_b200 import mesh_util
     peaks = load_peaks()
     cal = calib.to(dev)
     out = {"resolution": res}
+    # the same reconstruction in the hybrid arithmetic (parity gates met as stated on this saturated field)
+    eng.set_precision("hybrid")
+    try:
+        hy = {}
+        best = None
+        r0 = eng.refined_points()
+        for _ in range(reps + 1):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            mesh_h = mesh_util.reconstruction(netMR, dev, cal, res, None, None, thresh=0.5, use_octree=True, num_samples=5000)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+        hy["latency_ms"] = best
+        hy["refined_points_per_reconstruction"] = (eng.refined_points() - r0) // (reps + 1)
+        hy["verts"], hy["faces"] = (len(mesh_h[0]), len(mesh_h[1])) if mesh_h != -1 else (0, 0)
+        if cpu is not None:
+            st = []
+            f = mesh_util.eval_field_device(netMR, dev, cal, res, True, stats=st)
+            hy["vs_cpu"] = field_vs_cpu(f, st, cpu)
+            del f
+        out["octree_hybrid"] = hy
+    finally:
+        eng.set_precision("fast")
     for mode in ("octree", "dense"):
         best = None
         for _ in range(reps + 1):                      # first pass warms allocations
@@ -244,6 +341,8 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
             t0, t1, t2, nbytes = tail()
             d["gen_mesh_tail"] = {"vertex_normals_ms": (t1 - t0) * 1e3, "queries": 4 * len(mv), "obj_write_ms": (t2 - t1) * 1e3,
                                   "obj_bytes": nbytes, "gen_mesh_total_ms": best + (t2 - t0) * 1e3}
+        if mode == "octree" and cpu is not None:
+            d["vs_cpu"] = field_vs_cpu(field, stats, cpu)
         if mode == "octree":
             d["evaluated_per_level"] = stats
             d["evaluated_fraction"] = sum(stats) / float(res ** 3)
@@ -260,6 +359,20 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3):
         out[mode] = d
         del field, verts, faces, normals, values, host
     return out
+
+
+def field_vs_cpu(field, stats, cpu):
+    """GPU octree field (device float32 [R, R, R]) against the host's float64 field of the same reconstruction."""
+    ref = torch.from_numpy(cpu["sdf"]).to(field.device)
+    diff = (field.double() - ref).abs()
+    agree = ((field > 0.5) == (ref > 0.5)).double().mean().item()
+    over = (diff > 1e-3).double().mean().item()
+    r = {"evaluated_per_level_gpu": list(stats), "evaluated_per_level_cpu": cpu["evaluated_per_level"],
+         "evaluated_sets_equal_in_size": list(stats) == list(cpu["evaluated_per_level"]),
+         "sign_agreement_all_voxels": agree, "max_abs_err": diff.max().item(), "fraction_over_1e-3": over,
+         "voxels": int(ref.numel())}
+    del ref, diff
+    return r
 
 
 def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3):

@@ -68,6 +68,24 @@ int pifu_set_features(pifu_ctx* ctx, int level, const float* nchw, int C, int H,
 /* projection: 0 orthogonal / 1 perspective (BasePIFuNet.py:79); DepthNormalizer constants
  * z * z_mul / z_div (DepthNormalizer.py:23: loadSize // 2 and z_size). */
 int pifu_set_options(pifu_ctx* ctx, int perspective, float z_mul, float z_div);
+
+/* Arithmetic of the per-point MLP (MLP.py:55-73; the reference computes in fp32).
+ *   PIFU_PREC_FAST   (default) every tensor-core operand is one fp16 image, fp32 accumulate: logit error ~6e-4 of the
+ *                    logit spread;
+ *   PIFU_PREC_SPLIT  every operand (features, activations, weights) is carried as fp16 + fp16 residual and a layer
+ *                    computes x_hi W_hi + x_lo W_hi + x_hi W_lo (three tensor-core passes, fp32 accumulate): fp32-level
+ *                    error, per-layer kernels only; `terms` selects the residual products (bit 0: activations and
+ *                    features, bit 1: weights; 3 = both) so each rounding point's share of the error can be measured;
+ *   PIFU_PREC_HYBRID fast everywhere (chain kernels included), then the points whose occupancy falls inside
+ *                    (band_lo, band_hi) are evaluated again in split precision: outside the band the sigmoid's slope
+ *                    <= band_lo (1 - band_lo) scales the fast path's logit error below the parity gate and no sign at
+ *                    0.5 can differ.  One host synchronisation per 4 Mi outputs sizes the second pass. */
+#define PIFU_PREC_FAST 0
+#define PIFU_PREC_SPLIT 1
+#define PIFU_PREC_HYBRID 2
+int pifu_set_precision(pifu_ctx* ctx, int mode, int terms, float band_lo, float band_hi);
+/* points re-evaluated by the hybrid mode since the context was created */
+long long pifu_refined_points(pifu_ctx* ctx);
 int pifu_set_gemm_impl(pifu_ctx* ctx, int impl);
 int pifu_set_chunk_tiles(pifu_ctx* ctx, int tiles_of_128_points);
 
@@ -80,6 +98,7 @@ int pifu_set_chunk_tiles(pifu_ctx* ctx, int tiles_of_128_points);
  *   out_pred_low [n]      coarse prediction (netG.intermediate_preds_list[-1]); levels == 2 only
  *   out_phi      [C][n]   coarse merge-layer feature `netG.phi` (row stride n) */
 #define PIFU_QUERY_NO_MASK 1 /* raw sigmoid, no in-bounds mask: calc_normal (PIFuMRNet.py:232-237) */
+#define PIFU_QUERY_PRECISE 2 /* this call in split precision whatever pifu_set_precision says (finite differences) */
 int pifu_query(pifu_ctx* ctx, int levels, int flags, const float* points, long long pstride, long long n,
                const float* calib_local, const float* calib_global, float* out_pred,
                float* out_pred_low, float* out_phi, void* stream);

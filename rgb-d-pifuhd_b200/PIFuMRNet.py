@@ -44,6 +44,9 @@ class PIFuMRNet(BasePIFuNet, EncoderHost):
         # direct query() calls fill preds_low / netG.phi like the reference; the reconstruction
         # driver switches them off because nothing on that path reads them
         self.materialize_intermediates = True
+        # calc_normal differences occupancies `delta` = 0.001 apart: the fp16 rounding noise of the fast arithmetic,
+        # divided by delta, would swamp the gradient, so finite differences run in split precision (engine.set_precision)
+        self.precise_normals = True
 
     def train(self, mode=True):
         """`PIFuMRNet.py:59-69`: the coarse net stays in eval mode unless trained end to end."""
@@ -89,8 +92,8 @@ class PIFuMRNet(BasePIFuNet, EncoderHost):
     def _engine_for(self, points):
         eng = get_engine(points.device)
         eng.set_options(self.is_perspective, self.netG.opt.loadSize, self.netG.opt.z_size)
-        eng.sync_mlp(0, self.netG.mlp, id(self.netG))
-        eng.sync_mlp(1, self.mlp, id(self))
+        eng.sync_mlp(0, self.netG.mlp)
+        eng.sync_mlp(1, self.mlp)
         return eng
 
     def _features(self, b1, b2, B2):
@@ -161,7 +164,8 @@ class PIFuMRNet(BasePIFuNet, EncoderHost):
                 fc, ff = self._features(b1, b2, B2)
                 eng.sync_features(0, fc)
                 eng.sync_features(1, ff)
-                out.append(eng.query(2, pall[b1], calib_local[b1, b2], calib_global[b1], no_mask=True)[0])
+                out.append(eng.query(2, pall[b1], calib_local[b1, b2], calib_global[b1], no_mask=True,
+                                     precise=self.precise_normals)[0])
             pred = torch.stack(out, 0).view(B1, 1, N, 4)
             d = [pred[:, :, :, a + 1] - pred[:, :, :, 0] for a in range(3)]
             nmls.append(F.normalize(-torch.cat(d, 1), dim=1, eps=1e-8))

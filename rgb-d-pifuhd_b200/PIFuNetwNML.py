@@ -98,6 +98,7 @@ class PIFuNetwNML(BasePIFuNet, EncoderHost):
                 self.netB = define_G(3, 3, 64, "global", 4, 9, 1, 3, "instance")
         self.nmlF = None
         self.nmlB = None
+        self.precise_normals = True        # finite differences in split precision (see PIFuMRNet)
 
     # ------------------------------------------------------------------ encoder (PyTorch, once per image)
     def filter(self, images):
@@ -124,7 +125,7 @@ class PIFuNetwNML(BasePIFuNet, EncoderHost):
     def _engine_for(self, points):
         eng = get_engine(points.device)
         eng.set_options(self.is_perspective, self.opt.loadSize, self.opt.z_size)
-        eng.sync_mlp(0, self.mlp, id(self))
+        eng.sync_mlp(0, self.mlp)
         return eng
 
     def query(self, points, calibs, transforms=None, labels=None, update_pred=True, update_phi=True):
@@ -164,7 +165,8 @@ class PIFuNetwNML(BasePIFuNet, EncoderHost):
         preds = []
         for b in range(points.shape[0]):
             eng.sync_features(0, self.im_feat_list[-1][b:b + 1])
-            preds.append(eng.query(1, pall[b], calibs[b], calibs[b], no_mask=True)[0][None, None])
+            preds.append(eng.query(1, pall[b], calibs[b], calibs[b], no_mask=True,
+                                   precise=self.precise_normals)[0][None, None])
         pred = torch.cat(preds, 0).view(points.shape[0], 1, -1, 4)
         d = [pred[:, :, :, a + 1] - pred[:, :, :, 0] for a in range(3)]
         self.nml = F.normalize(-torch.cat(d, 1), dim=1, eps=1e-8)

@@ -26,6 +26,8 @@ SIGNATURES = {
     "pifu_set_features": (ctypes.c_int, [VP, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, VP]),
     "pifu_set_options": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
     "pifu_set_gemm_impl": (ctypes.c_int, [VP, ctypes.c_int]),
+    "pifu_set_precision": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
+    "pifu_refined_points": (ctypes.c_longlong, [VP]),
     "pifu_set_chunk_tiles": (ctypes.c_int, [VP, ctypes.c_int]),
     "pifu_set_mlp_norm": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_double, VP, VP, VP]),
     "pifu_query": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_longlong, ctypes.c_longlong,

@@ -38,7 +38,8 @@ struct Layer {
     int cout = 0, cin = 0;
     int BN = 0, num_kb = 0;
     std::vector<SegRef> segs;
-    uint8_t* w = nullptr;                      // packed fp16 blocks
+    uint8_t* w = nullptr;                      // packed fp16 blocks, [N/BN][2 * num_kb]: per n-tile the fp16 images of the
+                                               // k-blocks, then their residual images fp16(w - fp16(w)) (split precision)
     float* bias = nullptr;
     int out_buf = -1;
 };
@@ -50,7 +51,9 @@ struct Level {
     int merge = -1;                            // index of the layer whose output is the `phi` tap
     int n_layers = 0;
     std::vector<Layer> hidden;                 // layers 0 .. n_layers-2
-    float* head_w = nullptr;                   // last layer, packed order, fp32
+    float* head_w = nullptr;                   // last layer, packed order, fp32: [y | input segments]
+    float* head_w_split = nullptr;             // split precision, fused form: [y | input segments | input segments (residuals)]
+    float* head_w_split_norm = nullptr;        // ... un-fused form (norm.cu head): [y | y (residual) | segments | segments (residuals)]
     float head_b = 0.f;
     std::vector<SegRef> head_segs;
     std::vector<SegRef> in_segs;               // the level's input row as K segments
@@ -65,7 +68,7 @@ struct Level {
     bool is_res(int i) const { for (int r : res) if (r == i) return true; return false; }
 };
 
-struct Buffer { int nkb = 0; uint8_t* ptr = nullptr; };
+struct Buffer { int nkb = 0; uint8_t* ptr = nullptr; uint8_t* ptr_lo = nullptr; };   // ptr_lo: residual images (split precision)
 
 // Operands of the lattice chain kernel (chain_tc.cu), built when the two MLPs have the
 // reference configuration (`options.py:86-87,92-93`): coarse 257-1024-512-256-..., fine
@@ -110,6 +113,18 @@ struct pifu_ctx {
     int chunk_tiles = 296;
     int perspective = 0;
     float z_mul = 512.f, z_div = 200.f;
+    // arithmetic of the per-point MLP (pifu_set_precision): 0 fast = one fp16 image per operand; 1 split = every
+    // operand carried as fp16 hi + fp16 residual, products hi*hi + lo*hi + hi*lo (terms selectable for error-budget
+    // measurements); 2 hybrid = fast everywhere, then the points whose occupancy lies in (band_lo, band_hi) again in split
+    int prec_mode = 0;
+    int prec_terms = 3;                        // bit 0: activation/feature residuals, bit 1: weight residuals
+    float band_lo = 0.02f, band_hi = 0.98f;
+    bool want_lo = false;                      // residual buffers allocated with the workspace
+    long long refined_points = 0;
+    long long* sel_ids = nullptr;              // hybrid: compacted keys / output positions of one window
+    long long* sel_pos = nullptr;
+    unsigned long long* sel_count = nullptr;
+    long long sel_cap = 0;
     Level lv[2];
     std::vector<Buffer> bufs;                  // activation buffers, sized for chunk_tiles
     int buf_F = -1, buf_FF = -1;
@@ -141,7 +156,10 @@ int new_buffer(pifu_ctx* c, int nkb) {
 }
 
 void free_workspace(pifu_ctx* c) {
-    for (auto& b : c->bufs) if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; }
+    for (auto& b : c->bufs) {
+        if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; }
+        if (b.ptr_lo) { cudaFree(b.ptr_lo); b.ptr_lo = nullptr; }
+    }
     if (c->mask) { cudaFree(c->mask); c->mask = nullptr; }
     if (c->pred_chunk) { cudaFree(c->pred_chunk); c->pred_chunk = nullptr; }
     if (c->norm_stats) { cudaFree(c->norm_stats); c->norm_stats = nullptr; }
@@ -152,13 +170,15 @@ void free_workspace(pifu_ctx* c) {
 int ensure_workspace(pifu_ctx* c) {
     if (c->alloc_tiles == c->chunk_tiles) {
         bool ok = true;
-        for (auto& b : c->bufs) if (!b.ptr) ok = false;
+        for (auto& b : c->bufs) if (!b.ptr || (c->want_lo && !b.ptr_lo)) ok = false;
         if (ok) return 0;
     } else {
         free_workspace(c);
     }
-    for (auto& b : c->bufs)
+    for (auto& b : c->bufs) {
         if (!b.ptr) PIFU_CUDA(cudaMalloc(&b.ptr, static_cast<size_t>(c->chunk_tiles) * b.nkb * ABLOCK_BYTES));
+        if (c->want_lo && !b.ptr_lo) PIFU_CUDA(cudaMalloc(&b.ptr_lo, static_cast<size_t>(c->chunk_tiles) * b.nkb * ABLOCK_BYTES));
+    }
     if (!c->mask) PIFU_CUDA(cudaMalloc(&c->mask, static_cast<size_t>(c->chunk_tiles) * TILE_M));
     if (!c->pred_chunk) PIFU_CUDA(cudaMalloc(&c->pred_chunk, static_cast<size_t>(c->chunk_tiles) * TILE_M * sizeof(float)));
     if (!c->norm_stats) PIFU_CUDA(cudaMalloc(&c->norm_stats, 2 * sizeof(double) * 4096));
@@ -170,6 +190,8 @@ void free_level(Level& L) {
     for (auto& l : L.hidden) { if (l.w) cudaFree(l.w); if (l.bias) cudaFree(l.bias); }
     L.hidden.clear();
     if (L.head_w) { cudaFree(L.head_w); L.head_w = nullptr; }
+    if (L.head_w_split) { cudaFree(L.head_w_split); L.head_w_split = nullptr; }
+    if (L.head_w_split_norm) { cudaFree(L.head_w_split_norm); L.head_w_split_norm = nullptr; }
     for (float* g : L.gamma) if (g) cudaFree(g);
     for (float* b : L.beta) if (b) cudaFree(b);
     L.gamma.clear(); L.beta.clear();
@@ -183,9 +205,9 @@ int gemm_bn(int N, bool head) {
     return 0;
 }
 
-ASeg make_seg(const pifu_ctx* c, const SegRef& r) {
+ASeg make_seg(const pifu_ctx* c, const SegRef& r, bool lo = false) {
     ASeg s;
-    s.base = c->bufs[r.buf].ptr;
+    s.base = lo ? c->bufs[r.buf].ptr_lo : c->bufs[r.buf].ptr;
     s.kb_stride = c->bufs[r.buf].nkb;
     s.kb_off = 0;
     s.nkb = r.nkb;
@@ -217,15 +239,31 @@ int run_gemm(pifu_ctx* c, const GemmArgs& g, double flops, cudaStream_t s) {
 
 // hidden layers [first, last] of a level; the fused last layer rides on layer n_layers-2
 int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_tiles, int n_valid,
-               float* head_out, int mask_bit, cudaStream_t s) {
+               float* head_out, int mask_bit, int prec, cudaStream_t s) {
     // mask_bit < 0: the caller wants the raw sigmoid (calc_normal, `PIFuMRNet.py:232-237`)
+    // prec: split-precision terms (0 = one fp16 image per operand).  The extra products are extra K segments:
+    //   [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T, the residual images read the weight k-blocks of their term.
+    const bool xlo = (prec & 1) != 0, wlo = (prec & 2) != 0;
     for (int i = first; i <= last; ++i) {
         Layer& l = L.hidden[i];
         GemmArgs g;
         memset(&g, 0, sizeof(g));
-        g.nseg = static_cast<int>(l.segs.size());
-        for (int k = 0; k < g.nseg; ++k) g.seg[k] = make_seg(c, l.segs[k]);
-        g.num_kb = l.num_kb;
+        const int ns = static_cast<int>(l.segs.size());
+        g.w_nkb = 2 * l.num_kb;
+        g.explicit_wkb = 1;
+        g.nseg = 0;
+        g.num_kb = 0;
+        for (int term = 0; term < 3; ++term) {
+            if ((term == 1 && !xlo) || (term == 2 && !wlo)) continue;
+            int off = 0;
+            for (int k = 0; k < ns; ++k) {
+                g.seg[g.nseg] = make_seg(c, l.segs[k], term == 1);
+                g.seg_wkb[g.nseg] = off + (term == 2 ? l.num_kb : 0);
+                off += l.segs[k].nkb;
+                g.num_kb += l.segs[k].nkb;
+                ++g.nseg;
+            }
+        }
         g.w = l.w;
         g.bias = l.bias;
         g.N = l.cout;
@@ -245,34 +283,41 @@ int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_ti
         } else if (feeds_next || tap || !with_head) {
             g.out = c->bufs[l.out_buf].ptr;
             g.out_kb_stride = c->bufs[l.out_buf].nkb;
+            if (xlo) g.out_lo = c->bufs[l.out_buf].ptr_lo;
         }
         if (with_head) {
-            g.head_w = L.head_w;
+            g.head_w = xlo ? L.head_w_split : L.head_w;
             g.head_b = L.head_b;
-            g.head_nseg = static_cast<int>(L.head_segs.size());
-            for (int k = 0; k < g.head_nseg; ++k) g.head_seg[k] = make_seg(c, L.head_segs[k]);
+            g.head_nseg = 0;
+            for (int lo = 0; lo < (xlo ? 2 : 1); ++lo)
+                for (const SegRef& r : L.head_segs) g.head_seg[g.head_nseg++] = make_seg(c, r, lo == 1);
             g.head_out = head_out;
             g.mask = mask_bit >= 0 ? c->mask : nullptr;
             g.mask_bit = mask_bit >= 0 ? mask_bit : 0;
         }
         // algorithmic work of this launch: 2 * points * true Cin * Cout (+ the fused Conv1d -> 1)
-        double flops = 2.0 * n_valid * static_cast<double>(l.cin) * l.cout;
+        double flops = 2.0 * n_valid * static_cast<double>(l.cin) * l.cout * (1 + (xlo ? 1 : 0) + (wlo ? 1 : 0));
         if (with_head) flops += 2.0 * n_valid * (L.dims[L.n_layers - 1] + (L.is_res(L.n_layers - 1) ? L.dims[0] : 0));
         if (run_gemm(c, g, flops, s)) return -1;
         if (L.norm) {
             const int groups = L.norm_groups > 0 ? L.norm_groups : l.cout;
             if (groups > 4096) { set_error("normalisation: too many groups"); return -1; }
             c->launches += 2;
-            if (launch_group_norm(c->norm_x, c->bufs[l.out_buf].ptr, c->bufs[l.out_buf].nkb, l.cout, groups, m_tiles,
+            if (launch_group_norm(c->norm_x, c->bufs[l.out_buf].ptr, xlo ? c->bufs[l.out_buf].ptr_lo : nullptr,
+                                  c->bufs[l.out_buf].nkb, l.cout, groups, m_tiles,
                                   n_valid, L.gamma[i], L.beta[i], L.norm_eps, c->norm_stats, s)) return -1;
             if (wants_head) {
                 ASeg segs[MAX_SEGS + 1];
                 int ns = 0;
-                segs[ns].base = c->bufs[l.out_buf].ptr; segs[ns].kb_stride = c->bufs[l.out_buf].nkb;
-                segs[ns].kb_off = 0; segs[ns].nkb = l.cout / KB; ++ns;
-                for (const SegRef& r : L.head_segs) segs[ns++] = make_seg(c, r);
+                for (int lo = 0; lo < (xlo ? 2 : 1); ++lo) {
+                    segs[ns].base = lo ? c->bufs[l.out_buf].ptr_lo : c->bufs[l.out_buf].ptr;
+                    segs[ns].kb_stride = c->bufs[l.out_buf].nkb;
+                    segs[ns].kb_off = 0; segs[ns].nkb = l.cout / KB; ++ns;
+                }
+                for (int lo = 0; lo < (xlo ? 2 : 1); ++lo)
+                    for (const SegRef& r : L.head_segs) segs[ns++] = make_seg(c, r, lo == 1);
                 c->launches += 1;
-                if (launch_head(segs, ns, L.head_w, L.head_b, mask_bit >= 0 ? c->mask : nullptr, mask_bit >= 0 ? mask_bit : 0,
+                if (launch_head(segs, ns, xlo ? L.head_w_split_norm : L.head_w, L.head_b, mask_bit >= 0 ? c->mask : nullptr, mask_bit >= 0 ? mask_bit : 0,
                                 head_out, m_tiles, n_valid, s)) return -1;
             }
         }
@@ -289,7 +334,7 @@ struct QueryOut {
 };
 
 int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const float* cl, const float* cg,
-              const QueryOut& o, cudaStream_t s) {
+              const QueryOut& o, int prec, cudaStream_t s) {
     Level& LC = c->lv[0];
     Level& LF = c->lv[1];
     const int m_tiles = (n + TILE_M - 1) / TILE_M;
@@ -309,26 +354,94 @@ int run_chunk(pifu_ctx* c, int levels, const PointSource& src, int n, const floa
         ga.FF = c->bufs[c->buf_FF].ptr; ga.kbFF = c->bufs[c->buf_FF].nkb;
     }
     ga.mask = c->mask;
+    ga.num_sms = c->num_sms;
+    if (prec & 1) {
+        ga.F_lo = c->bufs[c->buf_F].ptr_lo;
+        if (levels == 2) ga.FF_lo = c->bufs[c->buf_FF].ptr_lo;
+    }
     c->launches += 1;
     if (launch_gather(ga, s)) return -1;
 
     if (levels == 1) {
-        if (run_layers(c, LC, true, 0, LC.n_layers - 2, m_tiles, n, o.pred, o.no_mask ? -1 : 0, s)) return -1;
+        if (run_layers(c, LC, true, 0, LC.n_layers - 2, m_tiles, n, o.pred, o.no_mask ? -1 : 0, prec, s)) return -1;
     } else {
         const bool want_low = o.pred_low != nullptr;
         if (run_layers(c, LC, true, 0, want_low ? LC.n_layers - 2 : LC.merge, m_tiles, n,
-                       want_low ? o.pred_low : nullptr, o.no_mask ? -1 : 0, s)) return -1;
-        if (run_layers(c, LF, false, 0, LF.n_layers - 2, m_tiles, n, o.pred, o.no_mask ? -1 : 1, s)) return -1;
+                       want_low ? o.pred_low : nullptr, o.no_mask ? -1 : 0, prec, s)) return -1;
+        if (run_layers(c, LF, false, 0, LF.n_layers - 2, m_tiles, n, o.pred, o.no_mask ? -1 : 1, prec, s)) return -1;
     }
     if (o.phi != nullptr) {
         const Layer& tap = LC.hidden[LC.merge];
         c->launches += 1;
-        if (launch_unblock(c->bufs[tap.out_buf].ptr, c->bufs[tap.out_buf].nkb, 0, tap.cout, n, o.phi,
-                           o.phi_ld, s)) return -1;
+        if (launch_unblock(c->bufs[tap.out_buf].ptr, (prec & 1) ? c->bufs[tap.out_buf].ptr_lo : nullptr,
+                           c->bufs[tap.out_buf].nkb, 0, tap.cout, n, o.phi, o.phi_ld, s)) return -1;
     }
     return 0;
 }
 
+
+// ----------------------------------------------------------------------------- precision modes
+// terms of the per-layer launches of a call: split precision when forced by the caller (PIFU_QUERY_PRECISE), in
+// mode 1, and in mode 2 for a normalised MLP (its statistics couple the points of a call, a subset cannot be
+// re-evaluated on its own)
+int call_prec(const pifu_ctx* c, int levels, bool force) {
+    const bool norm = c->lv[0].norm || (levels == 2 && c->lv[1].norm);
+    return (force || c->prec_mode == 1 || (c->prec_mode == 2 && norm)) ? c->prec_terms : 0;
+}
+bool call_refines(const pifu_ctx* c, int levels, bool force) {
+    return c->prec_mode == 2 && call_prec(c, levels, force) == 0;
+}
+int need_lo(pifu_ctx* c) {
+    if (c->want_lo) return 0;
+    c->want_lo = true;
+    return ensure_workspace(c);
+}
+
+constexpr long long REFINE_WINDOW = 4LL << 20;
+void lattice_source(PointSource& src, int R0, int R1, int R2, const double* calib_inv);
+
+// hybrid precision: out[0, n) holds fast occupancies; re-evaluate those inside the band in split precision
+int refine_band(pifu_ctx* c, int levels, float* out, long long n, const PointSource& base, const float* cl,
+                const float* cg, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (need_lo(c)) return -1;
+    const long long cap = n < REFINE_WINDOW ? n : REFINE_WINDOW;
+    if (c->sel_cap < cap) {
+        if (c->sel_ids) { cudaFree(c->sel_ids); c->sel_ids = nullptr; }
+        if (c->sel_pos) { cudaFree(c->sel_pos); c->sel_pos = nullptr; }
+        c->sel_cap = 0;
+        PIFU_CUDA(cudaMalloc(&c->sel_ids, static_cast<size_t>(cap) * sizeof(long long)));
+        PIFU_CUDA(cudaMalloc(&c->sel_pos, static_cast<size_t>(cap) * sizeof(long long)));
+        c->sel_cap = cap;
+    }
+    if (!c->sel_count) PIFU_CUDA(cudaMalloc(&c->sel_count, sizeof(unsigned long long)));
+    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
+    for (long long w0 = 0; w0 < n; w0 += REFINE_WINDOW) {
+        const long long m = n - w0 < REFINE_WINDOW ? n - w0 : REFINE_WINDOW;
+        PIFU_CUDA(cudaMemsetAsync(c->sel_count, 0, sizeof(unsigned long long), s));
+        const long long* ids = base.mode == 1 && base.ids ? base.ids + w0 : nullptr;
+        const long long key0 = base.mode == 1 ? base.id0 + w0 : w0;
+        c->launches += 1;
+        if (launch_select_band(out + w0, m, c->band_lo, c->band_hi, ids, key0, w0, c->sel_ids, c->sel_pos, c->sel_count,
+                               c->num_sms, s)) return -1;
+        unsigned long long cnt = 0;
+        PIFU_CUDA(cudaMemcpyAsync(&cnt, c->sel_count, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+        PIFU_CUDA(cudaStreamSynchronize(s));
+        c->refined_points += static_cast<long long>(cnt);
+        for (long long b = 0; b < static_cast<long long>(cnt); b += chunk) {
+            const int mm = static_cast<int>(static_cast<long long>(cnt) - b < chunk ? static_cast<long long>(cnt) - b : chunk);
+            PointSource src = base;
+            if (base.mode == 1) { src.ids = c->sel_ids + b; src.id0 = 0; src.id_stride = 0; }
+            else src.pidx = c->sel_ids + b;
+            QueryOut o;
+            o.pred = c->pred_chunk;
+            if (run_chunk(c, levels, src, mm, cl, cg, o, c->prec_terms, s)) return -1;
+            c->launches += 1;
+            if (launch_scatter(c->pred_chunk, c->sel_pos + b, mm, out, s)) return -1;
+        }
+    }
+    return 0;
+}
 
 // ----------------------------------------------------------------------------- chain plan
 void free_chain(ChainPlan& P, bool coarse_too) {
@@ -486,6 +599,7 @@ bool chain_eligible(const pifu_ctx* c, int levels, int R2, const float* calib, c
     const ChainPlan& P = c->cplan;
     // x and y of the projected point must not depend on the lattice index along axis 2
     if (c->lv[0].norm || c->lv[1].norm) return false;       // statistics couple the points of a call
+    if (c->prec_mode == 1) return false;                    // split precision runs layer by layer
     return levels == 2 && P.enabled && P.coarse_ok && P.fine_ok && c->gemm_impl == PIFU_GEMM_TCGEN05 &&
            !c->perspective && R2 % TILE_M == 0 && calib[2] == 0.f && calib[6] == 0.f &&
            calib_inv[2] == 0.0 && calib_inv[6] == 0.0;
@@ -604,6 +718,7 @@ int chain_constants(pifu_ctx* c, const PointSource& src, int ncol, const float* 
     ga.feat_f = LF.feat; ga.Hf = LF.H; ga.Wf = LF.W; ga.Cf = LF.C;
     ga.FF = c->bufs[c->buf_FF].ptr; ga.kbFF = c->bufs[c->buf_FF].nkb;
     ga.mask = c->mask;
+    ga.num_sms = c->num_sms;
     c->launches += 1;
     if (launch_gather(ga, s)) return -1;
     GemmArgs g;
@@ -765,18 +880,26 @@ namespace pifu {
 // used by octree.cu: evaluate `n` lattice ids (device list) into out (device fp32 [n])
 int eval_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const long long* ids, long long n,
              const float* calib, const double* calib_inv, float* out, cudaStream_t s) {
-    if (c->cplan.rows_enabled && n > 0 && c->chunk_tiles * TILE_M >= RUN_BLOCK_ROWS &&
-        chain_eligible(c, levels, TILE_M, calib, calib_inv))
-        return run_chain_ids(c, R0, R1, R2, ids, n, calib, calib_inv, out, s);
+    const int prec = call_prec(c, levels, false);
+    if (prec && need_lo(c)) return -1;
     PointSource src;
     lattice_source(src, R0, R1, R2, calib_inv);
-    const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
-    for (long long b = 0; b < n; b += chunk) {
-        const int m = static_cast<int>(n - b < chunk ? n - b : chunk);
-        src.ids = ids + b;
-        QueryOut o;
-        o.pred = out + b;
-        if (run_chunk(c, levels, src, m, calib, calib, o, s)) return -1;
+    if (c->cplan.rows_enabled && n > 0 && c->chunk_tiles * TILE_M >= RUN_BLOCK_ROWS &&
+        chain_eligible(c, levels, TILE_M, calib, calib_inv)) {
+        if (run_chain_ids(c, R0, R1, R2, ids, n, calib, calib_inv, out, s)) return -1;
+    } else {
+        const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
+        for (long long b = 0; b < n; b += chunk) {
+            const int m = static_cast<int>(n - b < chunk ? n - b : chunk);
+            src.ids = ids + b;
+            QueryOut o;
+            o.pred = out + b;
+            if (run_chunk(c, levels, src, m, calib, calib, o, prec, s)) return -1;
+        }
+    }
+    if (call_refines(c, levels, false)) {
+        src.ids = ids;
+        return refine_band(c, levels, out, n, src, calib, calib, s);
     }
     return 0;
 }
@@ -822,6 +945,9 @@ void pifu_destroy(pifu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     free_workspace(c);
+    if (c->sel_ids) cudaFree(c->sel_ids);
+    if (c->sel_pos) cudaFree(c->sel_pos);
+    if (c->sel_count) cudaFree(c->sel_count);
     for (int l = 0; l < 2; ++l) { free_level(c->lv[l]); if (c->lv[l].feat) cudaFree(c->lv[l].feat); }
     free_chain(c->cplan, true);
     if (c->cplan.cc) cudaFree(c->cplan.cc);
@@ -904,6 +1030,19 @@ int pifu_set_chain(pifu_ctx* c, int enabled) {
     c->cplan.rows_enabled = enabled == 1;
     return 0;
 }
+
+int pifu_set_precision(pifu_ctx* c, int mode, int terms, float band_lo, float band_hi) {
+    if (!c || mode < 0 || mode > 2 || terms < 0 || terms > 3 || !(band_lo >= 0.f) || !(band_hi <= 1.f) || !(band_lo < band_hi)) {
+        set_error("bad arguments to pifu_set_precision"); return -1;
+    }
+    c->prec_mode = mode;
+    c->prec_terms = terms;
+    c->band_lo = band_lo;
+    c->band_hi = band_hi;
+    return 0;
+}
+
+long long pifu_refined_points(pifu_ctx* c) { return c ? c->refined_points : 0; }
 
 int pifu_chain_ready(pifu_ctx* c) { return c && c->cplan.coarse_ok && c->cplan.fine_ok && c->cplan.enabled ? 1 : 0; }
 
@@ -1020,11 +1159,12 @@ int pifu_set_mlp(pifu_ctx* c, int level, int n_channels, const int* ch, int n_re
             int* dmap = nullptr;
             PIFU_CUDA(cudaMalloc(&dmap, colmap.size() * sizeof(int)));
             PIFU_CUDA(cudaMemcpyAsync(dmap, colmap.data(), colmap.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-            PIFU_CUDA(cudaMalloc(&l.w, static_cast<size_t>(l.cout) * num_kb * ROW_BYTES));
+            PIFU_CUDA(cudaMalloc(&l.w, static_cast<size_t>(l.cout) * 2 * num_kb * ROW_BYTES));
             PIFU_CUDA(cudaMalloc(&l.bias, l.cout * sizeof(float)));
             PIFU_CUDA(cudaMemcpyAsync(l.bias, biases[i], l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
-            c->launches += 1;
-            if (launch_pack_weights(weights[i], cin, dmap, num_kb, l.cout, l.BN, l.w, s)) return -1;
+            c->launches += 2;
+            if (launch_pack_weights_split(weights[i], cin, dmap, num_kb, 2 * num_kb, 0, l.cout, l.BN, 0, l.w, s)) return -1;
+            if (launch_pack_weights_split(weights[i], cin, dmap, num_kb, 2 * num_kb, num_kb, l.cout, l.BN, 1, l.w, s)) return -1;
             PIFU_CUDA(cudaStreamSynchronize(s));
             cudaFree(dmap);
             l.out_buf = new_buffer(c, l.cout / KB);
@@ -1039,6 +1179,15 @@ int pifu_set_mlp(pifu_ctx* c, int level, int n_channels, const int* ch, int n_re
             // z is carried as z_hi + z_lo: both columns take the z weight (already duplicated by colmap)
             PIFU_CUDA(cudaMalloc(&L.head_w, hw.size() * sizeof(float)));
             PIFU_CUDA(cudaMemcpyAsync(L.head_w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            // split precision: the residual images of the concatenated input meet the same fp32 weights
+            std::vector<float> hs(hw.begin(), hw.end()), hn(hw.begin(), hw.begin() + ycols);
+            hs.insert(hs.end(), hw.begin() + ycols, hw.end());
+            hn.insert(hn.end(), hw.begin(), hw.begin() + ycols);
+            for (int rpt = 0; rpt < 2; ++rpt) hn.insert(hn.end(), hw.begin() + ycols, hw.end());
+            PIFU_CUDA(cudaMalloc(&L.head_w_split, hs.size() * sizeof(float)));
+            PIFU_CUDA(cudaMalloc(&L.head_w_split_norm, hn.size() * sizeof(float)));
+            PIFU_CUDA(cudaMemcpyAsync(L.head_w_split, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            PIFU_CUDA(cudaMemcpyAsync(L.head_w_split_norm, hn.data(), hn.size() * sizeof(float), cudaMemcpyHostToDevice, s));
             PIFU_CUDA(cudaStreamSynchronize(s));
             L.head_segs.assign(segs.begin() + 1, segs.end());
         }
@@ -1085,6 +1234,9 @@ int pifu_query(pifu_ctx* c, int levels, int flags, const float* points, long lon
     PIFU_CUDA(cudaSetDevice(c->device));
     if (fit_call(c, levels, n)) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool force = (flags & PIFU_QUERY_PRECISE) != 0;
+    const int prec = call_prec(c, levels, force);
+    if (prec && need_lo(c)) return -1;
     PointSource src;
     memset(&src, 0, sizeof(src));
     src.mode = 0;
@@ -1099,7 +1251,13 @@ int pifu_query(pifu_ctx* c, int levels, int flags, const float* points, long lon
         o.phi = out_phi ? out_phi + b : nullptr;
         o.phi_ld = n;
         o.no_mask = (flags & PIFU_QUERY_NO_MASK) != 0;
-        if (run_chunk(c, levels, src, m, calib_local, calib_global, o, s)) return -1;
+        if (run_chunk(c, levels, src, m, calib_local, calib_global, o, prec, s)) return -1;
+    }
+    // hybrid: only the final occupancy is refined (pred_low / phi keep the fast arithmetic); a raw-sigmoid call
+    // (calc_normal) is refined the same way through its un-masked values
+    if (call_refines(c, levels, force) && out_pred != nullptr && !(flags & PIFU_QUERY_NO_MASK)) {
+        src.pts = points;
+        return refine_band(c, levels, out_pred, n, src, calib_local, calib_global, s);
     }
     return 0;
 }
@@ -1120,6 +1278,8 @@ int pifu_eval_grid(pifu_ctx* c, int levels, int R0, int R1, int R2, long long id
         cb = id_end / TILE_M * TILE_M;
         if (cb <= ca) ca = cb = id_begin;
     }
+    const int prec = call_prec(c, levels, false);
+    if (prec && need_lo(c)) return -1;
     PointSource src;
     lattice_source(src, R0, R1, R2, calib_inv);
     const long long chunk = static_cast<long long>(c->chunk_tiles) * TILE_M;
@@ -1130,10 +1290,14 @@ int pifu_eval_grid(pifu_ctx* c, int levels, int R0, int R1, int R2, long long id
             src.id0 = b;
             QueryOut o;
             o.pred = out + (b - id_begin);
-            if (run_chunk(c, levels, src, m, calib, calib, o, s)) return -1;
+            if (run_chunk(c, levels, src, m, calib, calib, o, prec, s)) return -1;
         }
     }
     if (cb > ca && run_chain(c, R0, R1, R2, ca, cb, calib, calib_inv, out + (ca - id_begin), s)) return -1;
+    if (call_refines(c, levels, false)) {
+        src.id0 = id_begin;
+        return refine_band(c, levels, out, id_end - id_begin, src, calib, calib, s);
+    }
     return 0;
 }
 
@@ -1178,7 +1342,7 @@ int pifu_debug_gemm(pifu_ctx* c, const float* X, const float* W, const float* b,
     g.out = yo; g.out_kb_stride = N / KB; g.leaky = leaky; g.n_valid = M;
     if (!rc) rc = run_gemm(c, g, 2.0 * M * static_cast<double>(K) * N, s);
     // Y comes back channel-major [N][M], the orientation of the reference's [C, N] tensors
-    if (!rc) rc = launch_unblock(yo, N / KB, 0, N, M, Y, M, s);
+    if (!rc) rc = launch_unblock(yo, nullptr, N / KB, 0, N, M, Y, M, s);
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(xa); cudaFree(wp); cudaFree(yo); cudaFree(dmap); cudaFree(bias);
     if (!rc && e != cudaSuccess) { set_error("debug gemm: %s", cudaGetErrorString(e)); rc = -1; }

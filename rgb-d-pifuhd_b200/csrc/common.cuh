@@ -34,19 +34,23 @@ struct ASeg {
     int nkb;                // number of k-blocks used
 };
 
-constexpr int MAX_SEGS = 3;
+constexpr int MAX_SEGS = 9;        // 3 activation buffers x 3 split-precision terms (api.cu, precise mode)
 
 struct GemmArgs {
     ASeg seg[MAX_SEGS];
     int nseg;
     int num_kb;             // sum of seg[].nkb
-    const uint8_t* w;       // packed weights: [N/BN][num_kb] blocks of BN x 64 fp16 (swizzled image)
+    const uint8_t* w;       // packed weights: [N/BN][w_nkb] blocks of BN x 64 fp16 (swizzled image)
+    int w_nkb;              // k-blocks per n-tile in `w` (0 is read as num_kb)
+    int explicit_wkb;       // 0: segment s starts at the running k-block count; 1: at seg_wkb[s] (split precision:
+    int seg_wkb[MAX_SEGS];  //    the hi and lo images of an activation buffer share one weight k-block range)
     const float* bias;      // [N]
     int N;                  // output channels
     int m_tiles;            // number of 128-point tiles
     uint8_t* out;           // activation buffer written (may be null when only the head is wanted)
     int out_kb_stride;      // k-blocks per m-tile in out
     int out_kb_off;
+    uint8_t* out_lo;        // split precision: fp16(x - fp16(x)) in the layout of `out` (null = single fp16 image)
     int leaky;              // apply leaky_relu(0.01)
     // fused last layer (Conv1d to 1 channel + sigmoid), only when N == BN:
     const float* head_w;    // [N + 64 * sum(head_seg nkb)] fp32; null = no head
@@ -82,9 +86,11 @@ int launch_gemm_tc(const GemmArgs& a, int num_sms, int pair, cudaStream_t s);   
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);                // CUDA-core cross-check
 
 struct PointSource {
-    // mode 0: explicit points, reference layout [3][n] with row stride `pstride`
+    // mode 0: explicit points, reference layout [3][n] with row stride `pstride`; point p of the chunk is column
+    // pidx[p] when an index list is given (hybrid precision: the near-surface subset of a call), else column p
     const float* pts;
     long long pstride;
+    const long long* pidx;
     // mode 1: lattice ids; id -> (i, j, k) of an R0 x R1 x R2 lattice; ids == null -> id0 + p.
     // World coordinates follow `mesh_util.py:12-38,59-65` in float64: c = step*idx + bmin,
     // then [c,1] . cinv^T, then the float32 cast of `mesh_util.py:70`.
@@ -112,6 +118,9 @@ struct GatherArgs {
     int kbF;
     uint8_t* FF;            // fine input tiles    [m_tiles][kbFF] = [fine feat | 0...]
     int kbFF;
+    int num_sms;            // SMs of the device (launch geometry)
+    uint8_t* F_lo;          // split precision: residual images fp16(x - fp16(x)) of F / FF (z column: the third term of z)
+    uint8_t* FF_lo;
     uint8_t* mask;          // [m_tiles*128] bit0 coarse in-bounds (x,y,z), bit1 fine in-bounds (x,y)
 };
 int launch_gather(const GatherArgs& a, cudaStream_t s);

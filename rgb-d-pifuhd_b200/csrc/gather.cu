@@ -40,7 +40,9 @@ __device__ __forceinline__ Taps make_taps(float u, float v, int H, int W, int C)
     return t;
 }
 
-__device__ __forceinline__ uint4 sample8(const float* __restrict__ feat, const Taps& t, int c0) {
+// 8 blended channels as fp16 (return value) and the residual of that rounding, fp16(x - fp16(x)) (`res`; the second
+// operand image of the split-precision mode)
+__device__ __forceinline__ uint4 sample8(const float* __restrict__ feat, const Taps& t, int c0, uint4& res) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -69,6 +71,11 @@ __device__ __forceinline__ uint4 sample8(const float* __restrict__ feat, const T
     uint4 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+    __half2 l0 = __floats2half2_rn(acc[0] - f0.x, acc[1] - f0.y), l1 = __floats2half2_rn(acc[2] - f1.x, acc[3] - f1.y);
+    __half2 l2 = __floats2half2_rn(acc[4] - f2.x, acc[5] - f2.y), l3 = __floats2half2_rn(acc[6] - f3.x, acc[7] - f3.y);
+    res.x = *reinterpret_cast<uint32_t*>(&l0); res.y = *reinterpret_cast<uint32_t*>(&l1);
+    res.z = *reinterpret_cast<uint32_t*>(&l2); res.w = *reinterpret_cast<uint32_t*>(&l3);
     return pk;
 }
 
@@ -92,13 +99,15 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
     const int fchunks = a.feat_f ? (a.Cf >> 3) : 0;
     uint8_t* Fblk = a.F + static_cast<size_t>(mt) * a.kbF * ABLOCK_BYTES;
     uint8_t* FFblk = a.FF ? a.FF + static_cast<size_t>(mt) * a.kbFF * ABLOCK_BYTES : nullptr;
+    uint8_t* Flo = a.F_lo ? a.F_lo + static_cast<size_t>(mt) * a.kbF * ABLOCK_BYTES : nullptr;
+    uint8_t* FFlo = (a.FF && a.FF_lo) ? a.FF_lo + static_cast<size_t>(mt) * a.kbFF * ABLOCK_BYTES : nullptr;
 
     uint32_t last_u = 0x7fc00001u, last_v = 0x7fc00001u;     // NaN payloads never match
     uint32_t last_ul = 0x7fc00001u, last_vl = 0x7fc00001u;
-    uint4 ccache[MAX_CHUNKS_PER_LANE];
-    uint4 fcache = make_uint4(0, 0, 0, 0);
+    uint4 ccache[MAX_CHUNKS_PER_LANE], ccache_lo[MAX_CHUNKS_PER_LANE];
+    uint4 fcache = make_uint4(0, 0, 0, 0), fcache_lo = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS_PER_LANE; ++i) ccache[i] = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < MAX_CHUNKS_PER_LANE; ++i) ccache[i] = ccache_lo[i] = make_uint4(0, 0, 0, 0);
 
     // gridDim.y splits a warp's 16 rows over several blocks: short launches (the per-run samples of an octree
     // frontier, calc_normal's points) would otherwise leave most SMs idle behind 16 sequential rows per warp
@@ -109,9 +118,10 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
         if (p >= a.n) break;          // rows ascend within a warp: nothing valid follows
         float px, py, pz;
         if (S.mode == 0) {
-            px = __ldg(S.pts + p);
-            py = __ldg(S.pts + S.pstride + p);
-            pz = __ldg(S.pts + 2 * S.pstride + p);
+            const long long pc = S.pidx ? __ldg(S.pidx + p) : p;
+            px = __ldg(S.pts + pc);
+            py = __ldg(S.pts + S.pstride + pc);
+            pz = __ldg(S.pts + 2 * S.pstride + pc);
         } else {
             const long long id = S.ids ? __ldg(S.ids + p) : S.id0 + p * (S.id_stride > 0 ? S.id_stride : 1);
             const int k = static_cast<int>(id % S.R2);
@@ -143,36 +153,43 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
         for (int q = 0; q < MAX_CHUNKS_PER_LANE + 1; ++q) {
             const int ch = lane + 32 * q;
             if (ch >= total_c) break;
-            uint4 pk;
+            uint4 pk, pl = make_uint4(0, 0, 0, 0);
             if (ch < cchunks && q < MAX_CHUNKS_PER_LANE) {
-                if (!same_c) ccache[q] = sample8(a.feat_c, tc, ch * 8);
+                if (!same_c) ccache[q] = sample8(a.feat_c, tc, ch * 8, ccache_lo[q]);
                 pk = ccache[q];
+                pl = ccache_lo[q];
             } else if (ch == cchunks) {
                 const __half hi = __float2half_rn(zf);
-                const __half lo = __float2half_rn(zf - __half2float(hi));
+                const float r1 = zf - __half2float(hi);
+                const __half lo = __float2half_rn(r1);
                 pk = make_uint4(static_cast<uint32_t>(__half_as_ushort(hi)) |
                                 (static_cast<uint32_t>(__half_as_ushort(lo)) << 16), 0, 0, 0);
+                // the z_hi column of the residual image carries the third term of z (it meets the z weight there)
+                pl.x = static_cast<uint32_t>(__half_as_ushort(__float2half_rn(r1 - __half2float(lo))));
             } else {
                 pk = make_uint4(0, 0, 0, 0);
             }
-            *reinterpret_cast<uint4*>(Fblk + static_cast<size_t>(ch >> 3) * ABLOCK_BYTES +
-                                      sw128_chunk_offset(row, ch & 7)) = pk;
+            const size_t off = static_cast<size_t>(ch >> 3) * ABLOCK_BYTES + sw128_chunk_offset(row, ch & 7);
+            *reinterpret_cast<uint4*>(Fblk + off) = pk;
+            if (Flo != nullptr) *reinterpret_cast<uint4*>(Flo + off) = pl;
         }
         // ---- fine row: [fine feat(Cf) | 0 ...]
         if (FFblk != nullptr) {
             const bool same_f = (__float_as_uint(xl) == last_ul) && (__float_as_uint(yl) == last_vl);
             const int total_f = a.kbFF * 8;
             if (lane < total_f) {
-                uint4 pk = make_uint4(0, 0, 0, 0);
+                uint4 pk = make_uint4(0, 0, 0, 0), pl = make_uint4(0, 0, 0, 0);
                 if (lane < fchunks) {
                     if (!same_f) {
                         const Taps tf = make_taps(xl, yl, a.Hf, a.Wf, a.Cf);
-                        fcache = sample8(a.feat_f, tf, lane * 8);
+                        fcache = sample8(a.feat_f, tf, lane * 8, fcache_lo);
                     }
                     pk = fcache;
+                    pl = fcache_lo;
                 }
-                *reinterpret_cast<uint4*>(FFblk + static_cast<size_t>(lane >> 3) * ABLOCK_BYTES +
-                                          sw128_chunk_offset(row, lane & 7)) = pk;
+                const size_t off = static_cast<size_t>(lane >> 3) * ABLOCK_BYTES + sw128_chunk_offset(row, lane & 7);
+                *reinterpret_cast<uint4*>(FFblk + off) = pk;
+                if (FFlo != nullptr) *reinterpret_cast<uint4*>(FFlo + off) = pl;
             }
             last_ul = __float_as_uint(xl); last_vl = __float_as_uint(yl);
         }
@@ -191,7 +208,7 @@ int launch_gather(const GatherArgs& a, cudaStream_t s) {
     }
     const int m_tiles = (a.n + TILE_M - 1) / TILE_M;
     int split = 1;
-    while (split < 8 && m_tiles * split < 4 * 148) split *= 2;
+    while (split < 8 && m_tiles * split < 4 * a.num_sms) split *= 2;
     gather_kernel<<<dim3(m_tiles, split), 256, 0, s>>>(a);
     PIFU_CUDA(cudaGetLastError());
     return 0;

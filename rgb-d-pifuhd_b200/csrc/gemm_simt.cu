@@ -24,9 +24,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a, int BN
     int kbg = 0;
     for (int sg = 0; sg < a.nseg; ++sg) {
         const ASeg& seg = a.seg[sg];
+        if (a.explicit_wkb) kbg = a.seg_wkb[sg];
         for (int kb = 0; kb < seg.nkb; ++kb, ++kbg) {
             const uint8_t* ga = seg.base + (static_cast<size_t>(mt) * seg.kb_stride + seg.kb_off + kb) * ABLOCK_BYTES;
-            const uint8_t* gw = a.w + (static_cast<size_t>(nt) * a.num_kb + kbg) * bblock +
+            const uint8_t* gw = a.w + (static_cast<size_t>(nt) * (a.w_nkb > 0 ? a.w_nkb : a.num_kb) + kbg) * bblock +
                                 static_cast<size_t>(n_in) * ROW_BYTES;
             __syncthreads();
             for (int i = threadIdx.x; i < ABLOCK_BYTES / 16; i += 256)
@@ -58,7 +59,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a, int BN
             if (a.head_w != nullptr) part = fmaf(x, a.head_w[n], part);
             if (a.out != nullptr) {
                 uint8_t* blk = a.out + (static_cast<size_t>(mt) * a.out_kb_stride + a.out_kb_off + (n >> 6)) * ABLOCK_BYTES;
-                *reinterpret_cast<__half*>(blk + sw128_elem_offset(row, n & 63)) = __float2half_rn(x);
+                const __half hx = __float2half_rn(x);
+                *reinterpret_cast<__half*>(blk + sw128_elem_offset(row, n & 63)) = hx;
+                if (a.out_lo != nullptr) {
+                    uint8_t* blo = a.out_lo + (static_cast<size_t>(mt) * a.out_kb_stride + a.out_kb_off + (n >> 6)) * ABLOCK_BYTES;
+                    *reinterpret_cast<__half*>(blo + sw128_elem_offset(row, n & 63)) = __float2half_rn(x - __half2float(hx));
+                }
             }
         }
         if (a.head_w != nullptr) atomicAdd(&logit_scratch[mt * TILE_M + row], part);

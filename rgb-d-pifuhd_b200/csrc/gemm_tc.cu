@@ -119,13 +119,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const int nt = t % n_tiles_n;
                 int mt = (t / n_tiles_n) * CL + static_cast<int>(cta_rank);
                 if (mt >= a.m_tiles) mt = a.m_tiles - 1;     // odd tail: stage a valid tile, results unused
-                const uint8_t* wt = a.w + static_cast<size_t>(nt) * a.num_kb * C::BBLOCK_BYTES +
+                const uint8_t* wt = a.w + static_cast<size_t>(nt) * (a.w_nkb > 0 ? a.w_nkb : a.num_kb) * C::BBLOCK_BYTES +
                                     static_cast<size_t>(cta_rank) * C::BLOAD_BYTES;
                 int kbg = 0;
                 for (int sg = 0; sg < a.nseg; ++sg) {
                     const ASeg& seg = a.seg[sg];
                     const uint8_t* ab = seg.base +
                         (static_cast<size_t>(mt) * seg.kb_stride + seg.kb_off) * ABLOCK_BYTES;
+                    if (a.explicit_wkb) kbg = a.seg_wkb[sg];      // split precision: hi and lo images share weight blocks
                     for (int kb = 0; kb < seg.nkb; ++kb, ++kbg) {
                         // leader of a pair: its loads land on pfull, the barrier the peer's forwarder also
                         // arrives on, so the MMA warp waits on ONE barrier per stage
@@ -219,8 +220,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
             uint8_t* otile = nullptr;
+            uint8_t* otile_lo = nullptr;
             if (a.out != nullptr && live)
                 otile = a.out + (static_cast<size_t>(mt) * a.out_kb_stride + a.out_kb_off + (nt * BN) / KB) * ABLOCK_BYTES;
+            if (a.out_lo != nullptr && otile != nullptr)
+                otile_lo = a.out_lo + (static_cast<size_t>(mt) * a.out_kb_stride + a.out_kb_off + (nt * BN) / KB) * ABLOCK_BYTES;
             float hacc = 0.f;
 #pragma unroll 1
             for (int r0 = 0; r0 < BN; r0 += 128) {
@@ -277,6 +281,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             pk.z = *reinterpret_cast<uint32_t*>(&h2);
                             pk.w = *reinterpret_cast<uint32_t*>(&h3);
                             sts128(s_out + sw128_chunk_offset(row, 4 * hh + q), pk);
+                            if (otile_lo != nullptr) {
+                                // split precision: the residual of the fp16 rounding, as a second operand image
+                                // (straight to global memory: 4 x 16 B of one 128-byte row per thread)
+                                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                                const float2 f2 = __half22float2(h2), f3 = __half22float2(h3);
+                                const __half2 l0 = __floats2half2_rn(x[8 * q + 0] - f0.x, x[8 * q + 1] - f0.y);
+                                const __half2 l1 = __floats2half2_rn(x[8 * q + 2] - f1.x, x[8 * q + 3] - f1.y);
+                                const __half2 l2 = __floats2half2_rn(x[8 * q + 4] - f2.x, x[8 * q + 5] - f2.y);
+                                const __half2 l3 = __floats2half2_rn(x[8 * q + 6] - f3.x, x[8 * q + 7] - f3.y);
+                                uint4 lk;
+                                lk.x = *reinterpret_cast<const uint32_t*>(&l0);
+                                lk.y = *reinterpret_cast<const uint32_t*>(&l1);
+                                lk.z = *reinterpret_cast<const uint32_t*>(&l2);
+                                lk.w = *reinterpret_cast<const uint32_t*>(&l3);
+                                *reinterpret_cast<uint4*>(otile_lo + static_cast<size_t>((r0 >> 6) + half) * ABLOCK_BYTES +
+                                                          sw128_chunk_offset(row, 4 * hh + q)) = lk;
+                            }
                         }
                     }
                 }

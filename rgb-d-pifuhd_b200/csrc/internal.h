@@ -9,17 +9,25 @@ namespace pifu {
 
 int launch_pack_weights(const float* W, int cin, const int* colmap, int num_kb, int N, int BN,
                         uint8_t* out, cudaStream_t s);
+int launch_pack_weights_split(const float* W, int cin, const int* colmap, int num_kb, int w_nkb, int kb0, int N, int BN,
+                              int lo, uint8_t* out, cudaStream_t s);
 int launch_pack_rows(const float* X, int M, int K, int num_kb, uint8_t* out, cudaStream_t s);
 int launch_nchw_to_nhwc(const float* in, float* out, int C, int HW, cudaStream_t s);
-int launch_unblock(const uint8_t* buf, int kb_stride, int kb_off, int C, int n, float* dst, long long ld,
+int launch_unblock(const uint8_t* buf, const uint8_t* buf_lo, int kb_stride, int kb_off, int C, int n, float* dst, long long ld,
                    cudaStream_t s);
 
 // norm.cu: normalised stacks (GroupNorm / batch statistics) and the un-fused last layer
 struct ASeg;
-int launch_group_norm(const float* x, uint8_t* buf, int nkb, int channels, int groups, int m_tiles, int n_valid,
+int launch_group_norm(const float* x, uint8_t* buf, uint8_t* buf_lo, int nkb, int channels, int groups, int m_tiles, int n_valid,
                       const float* gamma, const float* beta, double eps, double* stats, cudaStream_t s);
 int launch_head(const ASeg* segs, int nseg, const float* w, float b, const uint8_t* mask, int mask_bit, float* out,
                 int m_tiles, int n_valid, cudaStream_t s);
+
+// refine.cu: hybrid precision, compaction of the near-surface points of a call and scatter of their re-evaluation
+int launch_select_band(const float* out, long long n, float lo, float hi, const long long* ids, long long key0,
+                       long long pos0, long long* sel_key, long long* sel_pos, unsigned long long* count, int num_sms,
+                       cudaStream_t s);
+int launch_scatter(const float* vals, const long long* pos, int m, float* out, cudaStream_t s);
 
 // runs.cu: segmentation of a sorted lattice-id list into runs of rows that share a lattice column
 constexpr int RUN_BLOCK_ROWS = 1024;

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(const float* __r
 }
 
 __global__ void __launch_bounds__(NORM_THREADS) gn_apply_kernel(const float* __restrict__ x, uint8_t* __restrict__ buf,
-                                                                int nkb, int gsize, int n_valid,
+                                                                uint8_t* __restrict__ buf_lo, int nkb, int gsize, int n_valid,
                                                                 const double* __restrict__ stats,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, double eps) {
@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_apply_kernel(const float* __r
 #pragma unroll
     for (int q = 0; q < 8; ++q) { sc[q] = s_scale[chunk * 8 + q]; sh[q] = s_shift[chunk * 8 + q]; }
     const int ld = nkb * KB;
+    uint8_t* blk_lo = buf_lo ? buf_lo + static_cast<size_t>(blockIdx.x) * ABLOCK_BYTES : nullptr;
     for (int r = r0; r < TILE_M; r += NORM_THREADS / 8) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);                           // padding rows of the last tile: zeros
+        uint4 vl = make_uint4(0u, 0u, 0u, 0u);                          // split precision: residual of the fp16 rounding
         if (r < rows) {
             const float* px = x + static_cast<size_t>(mt * TILE_M + r) * ld + kb * KB + chunk * 8;
             const float4 a = *reinterpret_cast<const float4*>(px), b = *reinterpret_cast<const float4*>(px + 4);
@@ -97,8 +99,15 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_apply_kernel(const float* __r
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+            __half2* hl = reinterpret_cast<__half2*>(&vl);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 back = __half22float2(h[q]);
+                hl[q] = __floats2half2_rn(f[2 * q] - back.x, f[2 * q + 1] - back.y);
+            }
         }
         *reinterpret_cast<uint4*>(blk + sw128_chunk_offset(r, chunk)) = v;
+        if (blk_lo != nullptr) *reinterpret_cast<uint4*>(blk_lo + sw128_chunk_offset(r, chunk)) = vl;
     }
 }
 
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(TILE_M) head_kernel(const HeadArgs a) {
 
 }  // namespace
 
-int launch_group_norm(const float* x, uint8_t* buf, int nkb, int channels, int groups, int m_tiles, int n_valid,
+int launch_group_norm(const float* x, uint8_t* buf, uint8_t* buf_lo, int nkb, int channels, int groups, int m_tiles, int n_valid,
                       const float* gamma, const float* beta, double eps, double* stats, cudaStream_t s) {
     const int gsize = channels / groups;
     if (groups <= 0 || channels % groups || (gsize < KB ? KB % gsize : gsize % KB)) {
@@ -153,7 +162,7 @@ int launch_group_norm(const float* x, uint8_t* buf, int nkb, int channels, int g
     }
     PIFU_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double) * groups, s));
     gn_stats_kernel<<<m_tiles * nkb, NORM_THREADS, 0, s>>>(x, nkb, gsize, n_valid, stats);
-    gn_apply_kernel<<<m_tiles * nkb, NORM_THREADS, 0, s>>>(x, buf, nkb, gsize, n_valid, stats, gamma, beta, eps);
+    gn_apply_kernel<<<m_tiles * nkb, NORM_THREADS, 0, s>>>(x, buf, buf_lo, nkb, gsize, n_valid, stats, gamma, beta, eps);
     PIFU_CUDA(cudaGetLastError());
     return 0;
 }

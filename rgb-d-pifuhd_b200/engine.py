@@ -49,6 +49,8 @@ class Engine:
         self._opt_key = None
         self._normalised = [False, False]
         self._keep = {}
+        self._hold = {}
+        self.precision = 0
 
     def __del__(self):
         try:
@@ -61,9 +63,11 @@ class Engine:
     # ------------------------------------------------------------------ snapshots
     @staticmethod
     def _tensor_key(ts):
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+        """Identity of live tensors.  Only meaningful while the caller keeps `ts` referenced (see `_hold`): a freed
+        tensor's id(), address and version count can all be re-issued to a different tensor."""
+        return tuple((id(t), t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
 
-    def sync_mlp(self, level, mlp, owner_id):
+    def sync_mlp(self, level, mlp, owner_id=None):
         """mlp: object with .filters (Conv1d list), .norms, .res_layers, .merge_layer, .norm, .filter_channels.
 
         mlp_norm (`MLP.py:36-41`): 'group' -> GroupNorm(32) statistics over the points of each call;
@@ -79,9 +83,12 @@ class Engine:
             params += [nm.weight, nm.bias]
             if fold:
                 params += [nm.running_mean, nm.running_var]
-        key = (owner_id, norm, fold, self._tensor_key(params))
+        key = (norm, fold, self._tensor_key(params))
         if self._mlp_key[level] == key:
             return
+        # the keyed tensors stay referenced for as long as their key is cached, so no later net can be handed
+        # the same (id, address, version) triple
+        self._hold[("mlp", level)] = params
         if level == 0:
             self._mlp_key[1] = None
         ws, bs = [], []
@@ -131,6 +138,7 @@ class Engine:
         _lib.check(self.lib.pifu_set_features(self.h, level, ctypes.c_void_p(f.data_ptr()), f.shape[1],
                                               f.shape[2], f.shape[3], _stream(self.device_index)))
         self._keep[("feat", level)] = f        # keep alive until the copy on the stream is done
+        self._hold[("feat", level)] = feat     # the keyed tensor itself (f may be a converted copy)
         self._feat_key[level] = key
 
     def set_options(self, perspective, load_size, z_size):
@@ -141,6 +149,19 @@ class Engine:
 
     def set_gemm_impl(self, impl):
         _lib.check(self.lib.pifu_set_gemm_impl(self.h, int(impl)))
+
+    PRECISION = {"fast": 0, "split": 1, "hybrid": 2}
+
+    def set_precision(self, mode="fast", terms=3, band=(0.02, 0.98)):
+        """Arithmetic of the per-point MLP (`pifu_set_precision`): 'fast' (one fp16 image per tensor-core operand),
+        'split' (fp16 + fp16 residual for features, activations and weights: fp32-level error, 3 tensor-core passes),
+        'hybrid' (fast everywhere, points whose occupancy lies inside `band` again in split precision)."""
+        m = self.PRECISION[mode] if isinstance(mode, str) else int(mode)
+        _lib.check(self.lib.pifu_set_precision(self.h, m, int(terms), float(band[0]), float(band[1])))
+        self.precision = m
+
+    def refined_points(self):
+        return int(self.lib.pifu_refined_points(self.h))
 
     def set_chunk_tiles(self, tiles):
         _lib.check(self.lib.pifu_set_chunk_tiles(self.h, int(tiles)))
@@ -173,7 +194,7 @@ class Engine:
         return int(self.lib.pifu_launch_count(self.h))
 
     # ------------------------------------------------------------------ compute
-    def query(self, levels, points, calib_local, calib_global, want_low=False, want_phi=0, no_mask=False):
+    def query(self, levels, points, calib_local, calib_global, want_low=False, want_phi=0, no_mask=False, precise=False):
         """points [3, n] fp32 on this device.  Returns (pred [n], low [n] | None, phi [C, n] | None)."""
         assert points.dim() == 2 and points.shape[0] == 3
         pts = points.detach().to(self.device, torch.float32)
@@ -188,7 +209,7 @@ class Engine:
         cl, _ = _calib16(calib_local)
         cg, _ = _calib16(calib_global)
         _lib.check(self.lib.pifu_query(
-            self.h, levels, 1 if no_mask else 0, ctypes.c_void_p(pts.data_ptr()), pts.stride(0), n, cl, cg,
+            self.h, levels, (1 if no_mask else 0) | (2 if precise else 0), ctypes.c_void_p(pts.data_ptr()), pts.stride(0), n, cl, cg,
             ctypes.c_void_p(pred.data_ptr()),
             ctypes.c_void_p(low.data_ptr()) if low is not None else None,
             ctypes.c_void_p(phi.data_ptr()) if phi is not None else None,

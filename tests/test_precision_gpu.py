@@ -1,0 +1,214 @@
+"""Parity at north_star's own gates on the field every mesh figure is taken on.
+
+The fast arithmetic (one fp16 image per tensor-core operand, fp32 accumulate) carries a logit error of ~6e-4 of
+the logit spread; on the saturated octree / marching-cubes field (last layer x8) that reads as up to ~6e-3 of
+occupancy at the surface.  The split-precision mode (fp16 + fp16 residual for features, activations and weights,
+three tensor-core products per layer) and the hybrid mode (fast everywhere, split inside the occupancy band where
+the sigmoid is steep) must meet the gates as stated: <= 1e-3 absolute, >= 99.99 % sign agreement at 0.5 - on the
+saturated field, at BASELINE's lattice sizes, and for the reference's finite-difference normals (delta = 0.001,
+`PIFuMRNet.py:188`)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import calibrated_problem, oracle_states, orc, syn
+from test_chain_gpu import lattice_points
+from test_query_gpu import OCC_TOL, build_nets, sign_agreement
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sat():
+    torch.set_grad_enabled(False)
+    prob, _ = calibrated_problem(saturated=True)
+    _, fine = oracle_states(prob)
+    netG, netMR = build_nets(prob)
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    yield prob, fine, netG, netMR, eng
+    eng.set_precision("fast")
+
+
+@pytest.fixture(scope="module")
+def sat_points(sat):
+    prob, fine, *_ = sat
+    pts = syn.random_points(200000, 9)
+    calib = syn.default_calib()
+    ref, ref_low, ref_phi = orc.query_fine(fine, pts, calib)
+    return pts, calib, ref, ref_low, ref_phi
+
+
+def test_split_precision_saturated_field(sat, sat_points):
+    """Every operand as fp16 + residual: fp32-level agreement with the fp32 reference, also for the
+    intermediate outputs (`preds_low`, `netG.phi`)."""
+    _, _, netG, netMR, eng = sat
+    pts, calib, ref, ref_low, ref_phi = sat_points
+    eng.set_precision("split")
+    try:
+        netMR.query(pts.cuda(), calib.cuda())
+        out = netMR.get_preds().cpu()
+        err = (out - ref).abs().max().item()
+        print("split precision, saturated field: max |err| %.3e" % err)
+        assert err < 1e-4
+        assert sign_agreement(out.numpy(), ref.numpy()) >= 0.9999
+        assert torch.equal(out == 0, ref == 0)
+        assert (netMR.preds_low.cpu() - ref_low).abs().max().item() < 1e-4
+        assert (netG.phi.cpu() - ref_phi).abs().max().item() < 1e-4 * max(1.0, ref_phi.abs().max().item())
+    finally:
+        eng.set_precision("fast")
+
+
+def test_error_budget_by_rounding_point(sat, sat_points):
+    """terms: 0 = fast, 1 = + activation/feature residuals, 2 = + weight residuals, 3 = both.  Each residual
+    product removes its rounding point's share; only both together reach the fp32 level."""
+    _, _, _, netMR, eng = sat
+    pts, calib, ref, _, _ = sat_points
+    sub = pts[:, :, :50000]
+    errs = {}
+    try:
+        for terms in (0, 1, 2, 3):
+            eng.set_precision("split" if terms else "fast", terms=terms or 3)
+            netMR.query(sub.cuda(), calib.cuda())
+            errs[terms] = (netMR.get_preds().cpu() - ref[:, :, :50000]).abs().max().item()
+    finally:
+        eng.set_precision("fast")
+    print("max |occupancy err| by residual terms:", errs)
+    assert errs[3] < 0.1 * min(errs[1], errs[2])
+    assert errs[1] < errs[0] and errs[2] < errs[0]
+
+
+def test_hybrid_points_saturated_field(sat, sat_points):
+    """test_saturated_field at the gate as stated (OCC_TOL, not 8e-3), explicit points."""
+    _, _, _, netMR, eng = sat
+    pts, calib, ref, _, _ = sat_points
+    eng.set_precision("hybrid")
+    try:
+        r0 = eng.refined_points()
+        netMR.query(pts.cuda(), calib.cuda())
+        out = netMR.get_preds().cpu()
+        refined = eng.refined_points() - r0
+        print("hybrid: %d of %d points re-evaluated, max |err| %.3e" % (refined, pts.shape[2], (out - ref).abs().max().item()))
+        assert 0 < refined < pts.shape[2] // 2
+        assert (out - ref).abs().max().item() < OCC_TOL
+        assert sign_agreement(out.numpy(), ref.numpy()) >= 0.9999
+        assert torch.equal(out == 0, ref == 0)
+    finally:
+        eng.set_precision("fast")
+
+
+def test_hybrid_chain_saturated_field(sat):
+    """test_chain_saturated_field at OCC_TOL: lattice columns through the chain kernel, band points again in
+    split precision; also the run-list form (a sorted id list)."""
+    _, fine, _, netMR, eng = sat
+    calib = syn.default_calib()
+    netMR.query(syn.random_points(256).cuda(), calib.cuda())
+    R = (40, 40, 128)
+    ids = np.arange(R[0] * R[1] * R[2])
+    ref = orc.query_fine(fine, lattice_points(R, calib, ids), calib)[0].numpy().ravel()
+    eng.set_precision("hybrid")
+    try:
+        assert eng.chain_ready()
+        out = eng.eval_grid(2, R, calib[0]).cpu().numpy()
+        assert np.abs(out - ref).max() < OCC_TOL
+        assert sign_agreement(out, ref) >= 0.9999
+        sub = np.flatnonzero((ids // 128 + ids) % 5 < 2).astype(np.int64)        # ragged runs per column
+        out2 = eng.eval_lattice_ids(2, R, torch.from_numpy(sub), calib[0]).cpu().numpy()
+        assert np.abs(out2 - ref[sub]).max() < OCC_TOL
+        assert sign_agreement(out2, ref[sub]) >= 0.9999
+    finally:
+        eng.set_precision("fast")
+
+
+@pytest.mark.parametrize("field", ["gate", "saturated"])
+def test_dense_256_strided_vs_oracle(field):
+    """BASELINE configs[1] at full size: the 256^3 lattice through pifu_eval_grid (chain kernel), compared with the
+    oracle on every 7th lattice point (2.4 M points, all depth residues of every column).  Gate field: fast
+    arithmetic; saturated field: hybrid."""
+    torch.set_grad_enabled(False)
+    prob, _ = calibrated_problem(saturated=(field == "saturated"))
+    _, fine = oracle_states(prob)
+    netG, netMR = build_nets(prob)
+    eng = netMR._engine_for(torch.zeros(1, device="cuda"))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    calib = syn.default_calib()
+    R = (256, 256, 256)
+    ids = np.arange(0, 256 ** 3, 7)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = np.concatenate([orc.query_fine(fine, lattice_points(R, calib, ids[b:b + 200000]), calib)[0].numpy().ravel()
+                          for b in range(0, len(ids), 200000)])
+    eng.set_precision("hybrid" if field == "saturated" else "fast")
+    try:
+        out = eng.eval_grid(2, 256, calib[0]).cpu().numpy()[ids]
+    finally:
+        eng.set_precision("fast")
+    err = np.abs(out - ref).max()
+    agree = sign_agreement(out, ref)
+    print("256^3 %s field: %d points, max |err| %.3e, sign agreement %.6f, occupied %.4f" % (field, len(ids), err, agree, (ref > 0.5).mean()))
+    assert err < OCC_TOL
+    assert agree >= 0.9999
+    assert np.array_equal(out == 0, ref == 0)
+
+
+def _near_surface_points(fine, calib, n, seed):
+    """Random points whose reference occupancy lies in (0.1, 0.9): where gen_mesh's vertices are."""
+    pts = syn.random_points(40 * n, seed, -0.95, 0.95)
+    p = orc.query_fine(fine, pts, calib)[0].numpy().ravel()
+    keep = np.flatnonzero((p > 0.1) & (p < 0.9))[:n]
+    assert len(keep) >= n // 2
+    return pts[:, :, keep].contiguous()
+
+
+def test_calc_normal_reference_delta(sat):
+    """`PIFuMRNet.calc_normal` at the reference's own delta = 0.001 (`PIFuMRNet.py:188`, what gen_mesh uses,
+    `reconstruction.py:58-70`) on near-surface points of the saturated field.  Finite differences amplify any
+    occupancy noise by 1/delta, so they run in split precision (net.precise_normals); the oracle's own fp32 noise
+    (~1e-6 of occupancy against differences of ~1e-3) bounds what can be asked: angular deviation < 1 degree
+    wherever the raw difference vector is longer than 2e-4."""
+    _, fine, _, netMR, _ = sat
+    calib = syn.default_calib()
+    pts = _near_surface_points(fine, calib, 2000, 31)
+    ref, raw = orc.calc_normal_fine(fine, pts, calib, calib, delta=0.001, return_raw=True)
+    netMR.calc_normal(pts[:, None].cuda(), calib[:, None].cuda(), calib.cuda())          # default delta = 0.001
+    n = netMR.nmls.cpu().numpy()
+    assert n.shape == ref.shape
+    ok = np.linalg.norm(raw.numpy(), axis=1) > 2e-4
+    cos = (n * ref.numpy()).sum(1)[ok]
+    print("calc_normal delta=0.001: %d of %d points compared, min cos %.6f, median angle %.4f deg"
+          % (ok.sum(), ok.size, cos.min(), np.degrees(np.arccos(np.clip(np.median(cos), -1, 1)))))
+    assert ok.mean() > 0.5
+    assert cos.min() > np.cos(np.radians(1.0))      # measured on B200: 0.57 degrees worst, 0.02 median
+    # the fast arithmetic cannot meet this: recorded, not asserted as a gate
+    netMR.precise_normals = False
+    try:
+        netMR.calc_normal(pts[:, None].cuda(), calib[:, None].cuda(), calib.cuda())
+        cos_fast = (netMR.nmls.cpu().numpy() * ref.numpy()).sum(1)[ok]
+        print("   fast arithmetic at the same delta: min cos %.4f" % cos_fast.min())
+    finally:
+        netMR.precise_normals = True
+
+
+def test_hybrid_octree_with_net(sat):
+    """test_octree_with_net against the reference's own field (golden `mr_octree64_init16`, made by the unmodified
+    reference) with the hybrid arithmetic: evaluated values agree within OCC_TOL; a filled voxel differs by more
+    only where a skip decision (`mesh_util.py:179`, span < 0.05) sits within the arithmetic error of its threshold
+    and flips a whole cell - counted, and bounded by half the skip threshold."""
+    from helpers import golden
+    _, _, _, netMR, eng = sat
+    calib = syn.default_calib()
+    res = 64
+    gold = golden("query_none.npz")["mr_octree64_init16"]
+    eng.set_precision("hybrid")
+    try:
+        sdf64, _, ev = eng.eval_grid_octree(2, res, calib, init_resolution=16, want64=True)
+    finally:
+        eng.set_precision("fast")
+    out = sdf64.cpu().numpy()
+    err = np.abs(out - gold)
+    print("hybrid octree 64^3 vs reference field: max |err| %.3e, voxels over 1e-3: %d of %d, sign agreement %.6f"
+          % (err.max(), int((err > OCC_TOL).sum()), err.size, sign_agreement(out, gold)))
+    assert sign_agreement(out, gold) >= 0.9999
+    assert (err > OCC_TOL).mean() < 1e-3
+    assert err.max() < 0.03
