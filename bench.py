@@ -222,6 +222,44 @@ def build_mesh_problem(dev):
     return build_nets(dev, saturated=True)
 
 
+def group_norm_leg(dev, res, chunks=32, num_samples=100000):
+    """The reference's DEFAULT mlp_norm ('group', options.py:95): GroupNorm(32) between every Conv1d and its
+    leaky_relu, statistics over the points of one query() call - so the lattice is cut into the reference's own
+    calls (num_samples = 100000, reconstruction.py:108,160), each one statistics domain through the per-layer
+    kernels + norm.cu.  Reported beside the headline, which is quoted on mlp_norm 'none'."""
+    from pifu_b200 import PIFuMRNet, PIFuNetwNML, config, synthetic as syn
+    prob = syn.make_problem(bias_std=0.0)
+    netG = PIFuNetwNML(config.coarse_opt(mlp_norm="group"), "orthogonal")
+    netMR = PIFuMRNet(config.fine_opt(mlp_norm="group"), netG, "orthogonal")
+    netG.mlp.load_state_dict(prob["coarse"], strict=False)          # GroupNorm affine stays at its init (1, 0)
+    netMR.mlp.load_state_dict(prob["fine"], strict=False)
+    netMR.to(dev).eval()
+    netG.im_feat_list = [prob["feat_coarse"].to(dev)]
+    netMR.im_feat_list = [prob["feat_fine"].to(dev)]
+    eng = netMR._engine_for(torch.zeros(1, device=dev))
+    eng.sync_features(0, netG.im_feat_list[-1])
+    eng.sync_features(1, netMR.im_feat_list[-1])
+    calib = syn.default_calib()
+    out = torch.empty(num_samples, device=dev, dtype=torch.float32)
+    first = (res ** 3) // 3                     # a run of calls in the middle of the lattice
+
+    def run():
+        for c in range(chunks):
+            b = first + c * num_samples
+            eng.eval_grid(2, res, calib[0], id_begin=b, id_end=b + num_samples, out=out)
+
+    run()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    run()
+    ev[1].record()
+    torch.cuda.synchronize(dev)
+    ms = ev[0].elapsed_time(ev[1])
+    return {"mlp_norm": "group", "queries_per_s": chunks * num_samples / (ms * 1e-3), "calls": chunks,
+            "points_per_call": num_samples, "ms": ms,
+            "note": "per-layer tcgen05 kernels + call-wide GroupNorm statistics (norm.cu); not shardable, not chained"}
+
+
 def mesh_cpu_baseline(prob, calib, res):
     """BASELINE's second figure on the host: the reference's CPU reconstruction path (`mesh_util.py:40-96` with
     use_octree=True) restated by the oracle - create_grid + calib pre-transform, eval_grid_octree with the
@@ -375,7 +413,7 @@ def field_vs_cpu(field, stats, cpu):
     return r
 
 
-def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3):
+def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3, modes=("octree", "dense")):
     """The same figure at N > 1 (one rank per GPU): dense lattices are cut into slabs along axis 0, an octree
     level's frontier into equal shares; every rank extracts the iso-surface of its own slab after one halo
     exchange and the fragments are gathered on rank 0 (pifu_b200.dist).  Wall clock between barriers, best of
@@ -384,7 +422,7 @@ def mesh_latency_sharded(netMR, calib, dev, res=512, reps=3):
     from pifu_b200 import mesh_util
     cal = calib.to(dev)
     out = {"resolution": res, "ranks": dist.get_world_size()}
-    for mode in ("octree", "dense"):
+    for mode in modes:
         best, shape = None, None
         for _ in range(reps + 1):
             dist.barrier()
@@ -496,25 +534,54 @@ def encoder_leg(dev, frames=8, time_modes=True, world=1):
     return out
 
 
+def workload(world):
+    """(lattice resolution, description) of the timed step: configs[1] on one GPU, one configs[2]-sized volume
+    slab-sharded over N > 1 GPUs."""
+    if world == 1:
+        return RES, ("PIFuMRNet multi-level (coarse 257-1024-512-256 trunk + fine 272-512-256-128-1), dense %d^3 lattice = "
+                     "%d queries on 1 GPU (BASELINE configs[1])" % (RES, RES ** 3))
+    return 512, ("PIFuMRNet multi-level (coarse 257-1024-512-256 trunk + fine 272-512-256-128-1), ONE dense 512^3 lattice = "
+                 "%d queries slab-sharded along axis 0 over %d GPUs (BASELINE configs[2]'s volume, dense)" % (512 ** 3, world))
+
+
+def config_dict(world, res, what):
+    """The `config` object, identical in both arms (--impl ours / reference)."""
+    return {"workload": what, "queries_per_step": res ** 3, "mlp_norm": "none",
+            "field": "random-init weights, band-limited synthetic feature maps, last fine conv calibrated to logit sigma 0.75 / "
+                     "2 % occupied (SURVEY 7.3-2)",
+            "l2": "GPU arm: 256 MiB flush write between timed iterations; CPU arm: not applicable"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this metric (oracle port: the
     reference cannot travel to the GPU box and its query path is library torch ops)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    res, what = workload(world)
     prob, calib = build_problem()
+    # the same calibration rule as the GPU arm, from the oracle's own pilot predictions
+    from oracle import pifu_oracle as orc
+    from pifu_b200 import synthetic as syn
+    with torch.no_grad():
+        pilot = orc.query_fine(oracle_fine_state(prob), syn.random_points(20000, syn.SEED_PILOT, -1.0, 1.0), calib)[0].numpy()
+    calibrate_from_pilot(prob, pilot)
     n = 200000
-    qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, n, steps=args.steps, warmup=min(args.warmup, 1))
-    sample = "%d-point strided sub-lattice of the %d^3 lattice per step, chunks of 100000 (PIFuMRNet.query port, torch CPU fp32)" % (npts, RES)
+    qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, n, steps=args.steps, warmup=args.warmup, res=res)
+    sample = "%d-point strided sub-lattice of the %d^3 lattice per step, chunks of 100000 (PIFuMRNet.query port, torch CPU fp32)" % (npts, res)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PIFuMRNet multi-level occupancy query, dense %d^3 lattice (configs[1]); bounded sample" % RES},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(world, res, what),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+EXEC_FLOP = 2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128)      # chain kernel, per query
 
 
 def main():
@@ -525,13 +592,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mesh", action="store_true", help="skip the 512^3 mesh-latency leg")
-    ap.add_argument("--res", type=int, default=RES, help=argparse.SUPPRESS)
+    ap.add_argument("--no-encoders", action="store_true", help="skip the per-frame encoder leg")
+    ap.add_argument("--res", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
-    from pifu_b200 import PIFuMRNet, PIFuNetwNML, config, dist as pdist
+    from pifu_b200 import config
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -543,33 +611,28 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
-    res = args.res
+    res, what = workload(world)
+    if args.res:
+        res = args.res
+    if res % world:
+        raise SystemExit("the %d^3 lattice does not cut into %d slabs" % (res, world))
 
     torch.set_grad_enabled(False)
-    prob, calib = build_problem()
-    netG = PIFuNetwNML(config.coarse_opt(), "orthogonal")
-    netMR = PIFuMRNet(config.fine_opt(), netG, "orthogonal")
-    netG.mlp.load_state_dict(prob["coarse"])
-    netMR.mlp.load_state_dict(prob["fine"])
-    netMR.to(dev).eval()
+    # gate field (sigma 0.75, 2 % occupied): the parity gates of north_star are stated on this arithmetic
+    netG, netMR, eng, calib, prob = build_nets(dev, saturated=False, with_prob=True)
     # host copies of the hot path's inputs (what filter_* leaves behind), pinned for the e2e leg
     feat_c_host = prob["feat_coarse"].pin_memory()
     feat_f_host = prob["feat_fine"].pin_memory()
-    netG.im_feat_list = [feat_c_host.to(dev)]
-    netMR.im_feat_list = [feat_f_host.to(dev)]
-    eng = netMR._engine_for(torch.zeros(1, device=dev))
-    eng.sync_features(0, netG.im_feat_list[-1])
-    eng.sync_features(1, netMR.im_feat_list[-1])
 
-    R0 = res * world
-    per_rank = res ** 3
+    total = res ** 3
+    per_rank = total // world
     id_b, id_e = rank * per_rank, (rank + 1) * per_rank
     slab = torch.empty(per_rank, device=dev, dtype=torch.float32)
     gathered = [torch.empty(per_rank, device=dev, dtype=torch.float32) for _ in range(world)] if (world > 1 and rank == 0) else None
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
 
     def step():
-        eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
+        eng.eval_grid(2, res, calib[0], id_begin=id_b, id_end=id_e, out=slab)
         if world > 1:
             dist.gather(slab, gathered, dst=0)
 
@@ -603,7 +666,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * per_rank / (ms_per_step * 1e-3)
+    value = total / (ms_per_step * 1e-3)
 
     # ---- end to end through the reference-shaped API with HOST buffers: features H2D from pinned
     # memory + re-layout, the fused query, and the occupancy field back to pinned host memory
@@ -616,7 +679,7 @@ def main():
         netMR.im_feat_list = [feat_f_host.to(dev, non_blocking=True)]
         eng.sync_features(0, netG.im_feat_list[-1])
         eng.sync_features(1, netMR.im_feat_list[-1])
-        eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
+        eng.eval_grid(2, res, calib[0], id_begin=id_b, id_end=id_e, out=slab)
         field_host.copy_(slab, non_blocking=True)
 
     e2e_step()
@@ -630,79 +693,137 @@ def main():
     t2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * per_rank / (float(t2.item()) / args.steps * 1e-3)
+    e2e_value = total / (float(t2.item()) / args.steps * 1e-3)
 
-    # ---- roofline of the dominant kernel (tcgen05 layer kernel): per-launch CUDA events
-    roofline = cpu = None
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream
+    roofline = cpu = parity = precision = None
     if rank == 0:
         peaks = load_peaks()
         eng.profile(True)
-        eng.eval_grid(2, (R0, res, res), calib[0], id_begin=id_b, id_end=id_e, out=slab)
+        eng.eval_grid(2, res, calib[0], id_begin=id_b, id_end=id_e, out=slab)
         n_c, chain_ms, chain_flops = eng.profile_read_kind(1)
         n_l, gemm_ms, gemm_flops = eng.profile_read_kind(0)
         eng.profile(False)
+        alg_flop = config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385)
         if n_c > 0:
             # dominant kernel = the lattice chain kernel (one launch per column chunk); the per-layer
-            # kernel only computes the per-column constants
-            achieved = chain_flops / (chain_ms * 1e-3) / 1e12
+            # kernel only computes the per-column constants.  `achieved` / `frac` count the FLOPs the tensor
+            # cores EXECUTE (after the per-column constant folding); the reference's layer stack per query is
+            # kept beside them as algorithmic_*.
+            algorithmic = chain_flops / (chain_ms * 1e-3) / 1e12
+            executed = algorithmic * EXEC_FLOP / alg_flop
             roofline = {"bound": "tensor", "kernel": "chain_kernel (tcgen05 CTA-pair MLP chain, activations on-chip)",
-                        "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                        "achieved": executed, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": executed / peaks["tflops"],
                         "traffic": (ncu_traffic("chain_kernel") or {}).get("bytes_per_launch"),
                         "traffic_detail": ncu_traffic("chain_kernel"), "peak_source": peaks["source"], "launches_per_step": n_c,
                         "avg_launch_us": chain_ms * 1e3 / n_c, "share_of_step": chain_ms / ms_per_step,
-                        "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
-                        "executed_flop_per_query": 2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128),
-                        "executed_tflops": achieved * (2 * (1024 * 512 + 512 * 256 + 256 * 512 + 768 * 256 + 512 * 128 + 128)) /
-                                           (config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385)),
+                        "executed_flop_per_query": EXEC_FLOP, "algorithmic_flop_per_query": alg_flop,
+                        "algorithmic_tflops": algorithmic, "algorithmic_frac": algorithmic / peaks["tflops"],
                         "column_constants": {"kernel": "gemm_tc_kernel", "launches_per_step": n_l, "ms_per_step": gemm_ms},
-                        "note": "algorithmic = the reference's get_preds() layer stack per query (coarse L0-L2, fine L0-L3; "
-                                "coarse L3/L4 only feed preds_low); executed = what the tensor cores run after the "
-                                "per-column constant folding (SURVEY 7.3-4)"}
+                        "note": "executed = what the tensor cores run after the per-column constant folding (SURVEY 7.3-4); "
+                                "algorithmic = the reference's get_preds() layer stack per query (coarse L0-L2, fine L0-L3; "
+                                "coarse L3/L4 only feed preds_low)"}
         else:
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
             roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 MLP layer)", "achieved": achieved,
                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                         "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_l,
                         "avg_launch_us": gemm_ms * 1e3 / max(n_l, 1), "share_of_step": gemm_ms / ms_per_step,
-                        "algorithmic_flop_per_query": config.FLOP_PER_QUERY_MR - 2 * (513 * 128 + 385),
+                        "algorithmic_flop_per_query": alg_flop,
                         "note": "coarse L3/L4 (preds_low) are not on the get_preds() path and are skipped"}
         if not args.no_cpu_baseline:
-            qps, cores, npts, sec = cpu_port_queries_per_s(prob, calib, 128 ** 3)
+            # the CPU port on a bounded sample of the SAME lattice; its values are the parity reference for the
+            # field the timed step produced (this rank's slab)
+            n_s = 128 ** 3
+            qps, cores, npts, sec, ref_vals = cpu_port_queries_per_s(prob, calib, n_s, res=res, keep=True)
             cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d-point strided sub-lattice of the %d^3 lattice, chunks of 100000, %.1f s" % (npts, res, sec)}
+            ids = sample_ids(res, n_s)
+            mine = (ids >= id_b) & (ids < id_e)
+            step()
+            got = slab[torch.from_numpy(ids[mine] - id_b).to(dev)].cpu().numpy()
+            parity = parity_block(got, ref_vals[mine], "timed step's field (fast arithmetic, gate field sigma 0.75) vs the CPU "
+                                  "port on the strided sample%s" % ("" if world == 1 else ", rank 0's slab"))
 
-    mesh = enc = None
+    mesh = enc = stress = group = None
+    del flush
+    torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_mesh:
-        del flush
+        del netMR, netG, eng
+        # saturated field (x8 last-layer gain): what the octree prunes on and every mesh figure is taken on
+        netG2, netMR2, eng2, calib2, prob2 = build_nets(dev, saturated=True, with_prob=True)
+        # the three arithmetics on the dense 256^3 lattice of this field, each against the CPU port
+        precision = {}
+        ref_sat = None
+        if not args.no_cpu_baseline:
+            ref_sat = cpu_port_queries_per_s(prob2, calib2, 128 ** 3, res=res, keep=True)[4]
+        ids_dev = torch.from_numpy(sample_ids(res, 128 ** 3)).to(dev)
+        for mode, reps in (("fast", 5), ("hybrid", 5), ("split", 2)):
+            eng2.set_precision(mode)
+            eng2.eval_grid(2, res, calib2[0], out=slab)
+            r0 = eng2.refined_points()
+            evp = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            evp[0].record()
+            for _ in range(reps):
+                eng2.eval_grid(2, res, calib2[0], out=slab)
+            evp[1].record()
+            torch.cuda.synchronize(dev)
+            d = {"queries_per_s": total / (evp[0].elapsed_time(evp[1]) / reps * 1e-3),
+                 "ms_per_step": evp[0].elapsed_time(evp[1]) / reps}
+            if mode == "hybrid":
+                d["refined_fraction"] = (eng2.refined_points() - r0) / float(reps * total)
+            if ref_sat is not None:
+                d["parity"] = parity_block(slab[ids_dev].cpu().numpy(), ref_sat, "saturated field, %s arithmetic vs the CPU port" % mode)
+            precision[mode] = d
+        eng2.set_precision("fast")
+        precision["note"] = ("dense %d^3 lattice of the saturated field (last layer x8); fast = one fp16 image per tensor-core operand; "
+                             "split = fp16 + fp16 residual for features, activations and weights (3 products per layer, per-layer "
+                             "kernels); hybrid = fast (chain kernel), then occupancies inside (0.02, 0.98) again in split" % res)
+        group = group_norm_leg(dev, res)
+        cpu_mesh = None
+        if not args.no_cpu_baseline:
+            cpu_mesh = mesh_cpu_baseline(prob2, calib2, 512)
+        mesh = mesh_latency(netMR2, eng2, calib2, dev, 512, 3, cpu=cpu_mesh)
+        if cpu_mesh is not None:
+            mesh["cpu_baseline"] = {k: v for k, v in cpu_mesh.items() if k != "sdf"}
+            mesh["cpu_baseline"]["kind"] = "port"
+            mesh["cpu_baseline"]["what"] = ("create_grid + calib pre-transform, eval_grid_octree (numpy bookkeeping + torch-CPU query, "
+                                            "num_samples 100000), marching cubes (oracle/mc_ref.c, single thread)")
+            mesh["cpu_baseline_ms"] = cpu_mesh["total_ms"]
+            mesh["octree"]["vs_cpu"]["mesh_cpu"] = [cpu_mesh["verts"], cpu_mesh["faces"]]
+            mesh["octree"]["vs_cpu"]["mesh_gpu"] = [mesh["octree"]["verts"], mesh["octree"]["faces"]]
+            mesh["octree_hybrid"]["vs_cpu"]["mesh_cpu"] = [cpu_mesh["verts"], cpu_mesh["faces"]]
+            mesh["octree_hybrid"]["vs_cpu"]["mesh_gpu"] = [mesh["octree_hybrid"]["verts"], mesh["octree_hybrid"]["faces"]]
+        del cpu_mesh
+        del netMR2, eng2, netG2
         torch.cuda.empty_cache()
-        _, netMR2, eng2, calib2 = build_mesh_problem(dev)
-        mesh = mesh_latency(netMR2, eng2, calib2, dev, 512, 3)
-        del netMR2, eng2
-        torch.cuda.empty_cache()
-        enc = encoder_leg(dev)
+        if not args.no_encoders:
+            enc = encoder_leg(dev)
 
     if world > 1 and not args.no_mesh:
-        del flush, slab, gathered
+        del slab, gathered, netMR, netG, eng
         torch.cuda.empty_cache()
         _, netMR2, eng2, calib2 = build_mesh_problem(dev)        # seeded: identical on every rank
         mesh = mesh_latency_sharded(netMR2, calib2, dev, 512, 3)
+        if world == 8:
+            # BASELINE configs[4]: 1024^3 dense query + marching cubes on 8 GPUs (~1e9 points)
+            stress = mesh_latency_sharded(netMR2, calib2, dev, 1024, 1, modes=("dense",))
         del netMR2, eng2
         torch.cuda.empty_cache()
-        enc = encoder_leg(dev, frames=8, time_modes=False, world=world)
+        if not args.no_encoders:
+            enc = encoder_leg(dev, frames=8, time_modes=False, world=world)
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "PIFuMRNet multi-level (coarse 257-1024-512-256 trunk + fine 272-512-256-128-1), dense "
-                                   "%dx%dx%d lattice, %d^3 = %d queries per GPU (BASELINE configs[1])" % (R0, res, res, res, per_rank),
-                       "parallelism": "slab%d" % world, "mlp_norm": "none", "arithmetic": "f16 tensor-core operands, f32 accumulate and epilogues",
-                       "l2": "256 MiB flush write between timed iterations",
-                       "path": "chain" if eng.chain_ready() else "per-layer"},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": config_dict(world, res, what),
+            "execution": {"parallelism": "slab%d" % world, "arithmetic": "f16 tensor-core operands, f32 accumulate and epilogues",
+                          "path": "chain"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "mesh_512": mesh, "encoders": enc,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "precision": precision, "group_norm": group, "mesh_512": mesh, "stress_1024": stress, "encoders": enc,
         }))
     if world > 1:
         dist.destroy_process_group()

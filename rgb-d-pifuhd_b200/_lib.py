@@ -65,6 +65,9 @@ SIGNATURES = {
 }
 
 
+ABI_VERSION = 2          # pifu_abi_version() of the library these signatures describe
+
+
 class PifuError(RuntimeError):
     pass
 
@@ -78,15 +81,23 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        from . import build as _build
+    from . import build as _build
+    stale = not os.path.exists(_LIB_PATH) or not _build.up_to_date()
+    if stale:
+        # missing, or built from other sources than the ones in the tree (csrc / header digest in the stamp)
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001
-            raise PifuError("libpifu_b200.so is missing and could not be built (%s). "
-                            "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root; "
-                            "there is no CPU fallback." % (e,))
+            if not os.path.exists(_LIB_PATH):
+                raise PifuError("libpifu_b200.so is missing and could not be built (%s). "
+                                "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root; "
+                                "there is no CPU fallback." % (e,))
+            raise PifuError("libpifu_b200.so does not match the sources in the tree and could not be rebuilt (%s)" % (e,))
     lib = ctypes.CDLL(_LIB_PATH)
+    lib.pifu_abi_version.restype = ctypes.c_int
+    if lib.pifu_abi_version() != ABI_VERSION:
+        raise PifuError("libpifu_b200.so has ABI version %d, this binding expects %d: rebuild it"
+                        % (lib.pifu_abi_version(), ABI_VERSION))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

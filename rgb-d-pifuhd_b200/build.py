@@ -32,6 +32,15 @@ def _digest():
     return h.hexdigest()
 
 
+def up_to_date():
+    """True when the library on disk was built from exactly the sources in the tree."""
+    stamp = LIB + ".stamp"
+    try:
+        return os.path.exists(LIB) and open(stamp).read() == _digest()
+    except OSError:
+        return False
+
+
 def build(force=False, verbose=False):
     """Compile every .cu into objects (parallel) and link the shared library."""
     stamp = LIB + ".stamp"

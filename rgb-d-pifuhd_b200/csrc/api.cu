@@ -101,14 +101,14 @@ struct ChainPlan {
     long long cap_rows = 0;
     std::vector<uint32_t> heads_host;
 };
-constexpr int CHAIN_COLS_PER_CHUNK = 148 * 32;
+constexpr int CHAIN_COLS_PER_SM = 32;   // lattice columns per chain launch = 32 x the device's SM count
 constexpr int CCW_KB = 6;            // K of the column-constants GEMM: F (5 k-blocks) + FF (1)
 
 }  // namespace
 
 struct pifu_ctx {
     int device = 0;
-    int num_sms = 148;
+    int num_sms = 0;                           // cudaDevAttrMultiProcessorCount, set by pifu_create
     int gemm_impl = PIFU_GEMM_TCGEN05;
     int chunk_tiles = 296;
     int perspective = 0;
@@ -650,7 +650,7 @@ int run_chain(pifu_ctx* c, int R0, int R1, int R2, long long id_a, long long id_
     const long long tpc = R2 / TILE_M;
     const long long ta = id_a / TILE_M, tb = id_b / TILE_M;
     const long long col_a = ta / tpc, col_b = (tb + tpc - 1) / tpc;
-    long long per_chunk = CHAIN_COLS_PER_CHUNK;
+    long long per_chunk = static_cast<long long>(CHAIN_COLS_PER_SM) * c->num_sms;
     const long long ws_cols = static_cast<long long>(c->chunk_tiles) * TILE_M;
     if (per_chunk > ws_cols) per_chunk = ws_cols;
     if (grow_cc(P, per_chunk)) return -1;
@@ -915,7 +915,7 @@ McState*& ctx_mc(pifu_ctx* c) { return c->mc; }
 extern "C" {
 
 const char* pifu_last_error(void) { return g_error.c_str(); }
-int pifu_abi_version(void) { return 1; }
+int pifu_abi_version(void) { return 2; }
 
 int pifu_create(int device, pifu_ctx** out) {
     if (!out) { set_error("null out pointer"); return -1; }

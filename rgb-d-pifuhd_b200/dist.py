@@ -75,7 +75,7 @@ def exchange_halo(local, group=None):
     W, r = world_size(group), rank(group)
     if W == 1:
         return None, None
-    if local.shape[0] < 2:
+    if local.shape[0] < 2:        # rank-local: callers validate the cut on every rank before any collective (sharded_mesh)
         raise ValueError("slab marching cubes needs at least two planes per rank")
     edge = torch.stack([local[0], local[1], local[-1]], 0).contiguous()
     buf = torch.empty((W * 3,) + tuple(edge.shape[1:]), dtype=edge.dtype, device=edge.device)
@@ -174,6 +174,14 @@ def sharded_mesh(eng, levels, res, calib, use_octree, level=0.5, init_resolution
     plane = res * res
     b, e = shard_bounds(res * plane, W, r, align=plane)
     pb, pe = b // plane, e // plane
+    if W > 1 and not use_octree:
+        # every rank checks every rank's share (shard_bounds is deterministic), so all of them raise together and
+        # none is left waiting in the halo exchange
+        for q in range(W):
+            bq, eq = shard_bounds(res * plane, W, q, align=plane)
+            if (eq - bq) // plane < 2:
+                raise ValueError("a %d^3 lattice cut over %d ranks leaves rank %d fewer than the two planes slab marching "
+                                 "cubes needs" % (res, W, q))
     if use_octree:
         field = sharded_eval_grid_octree(eng, levels, res, calib, init_resolution, threshold, group=group,
                                          dst=None, stats=stats)

@@ -207,8 +207,8 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5
         if np.linalg.det(trans[:3, :3]) < 0.0:
             faces = faces[:, ::-1]
         return verts, faces, normals, values
-    except ValueError:
-        print('error cannot marching cubes')
+    except Exception:                    # the reference's bare `except:` (`mesh_util.py:94-96`): any failure of the
+        print('error cannot marching cubes')     # extraction or the vertex transform reads as "no mesh"
         return -1
 
 
