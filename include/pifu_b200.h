@@ -145,7 +145,9 @@ int pifu_octree_export(pifu_ctx* ctx, double* sdf64, float* sdf32, void* stream)
 
 /* Marching cubes on a device float32 volume [n0][n1][n2] at `level` (strict v > level is
  * inside).  Replaces measure.marching_cubes_lewiner (call site mesh_util.py:84; third-party,
- * see DESIGN.md "parity unpinned").  Two calls because the output size is data dependent:
+ * see DESIGN.md "parity unpinned").  Ambiguous faces are resolved by Lewiner's face test (the asymptotic decider);
+ * interior (tunnel) tests and the centre vertex of Lewiner's 33 cases are not implemented - INTEGRATION.md lists
+ * the deviations.  Two calls because the output size is data dependent:
  * count (synchronises, returns sizes) then emit into caller-allocated device buffers:
  * verts double [nverts][3] in volume-index coordinates (axis order of the volume), faces
  * int32 [nfaces][3], optional normals float [nverts][3] and values float [nverts]. */
@@ -167,6 +169,16 @@ int pifu_mc_emit(pifu_ctx* ctx, double* verts, int* faces, float* normals, float
 int pifu_mc_count_slab(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, double level,
                        int i_global0, int global_n0, int cell_layers, int ghost_layers,
                        long long* nverts, long long* nfaces, long long* ghost_verts, void* stream);
+
+/* One-call, fully asynchronous form of count + emit (single volume: i_global0 = 0, global_n0 = n0, cell_layers = n0 - 1,
+ * ghost_layers = 0; or a slab as above): classify, scan and emission are queued on `stream` without a host
+ * synchronisation in between.  The outputs are caller-allocated with capacities cap_verts / cap_faces (rows);
+ * counts_device (device, 3 x uint64) receives the true numbers of vertices, faces and ghost-layer vertices.  When a
+ * count exceeds its capacity nothing is written to that array: the caller reads the counts (its only synchronisation,
+ * typically together with the transfer of the mesh) and repeats the call with larger buffers. */
+int pifu_mc_extract(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, double level, int i_global0, int global_n0,
+                    int cell_layers, int ghost_layers, double* verts, int* faces, float* normals, float* values,
+                    long long cap_verts, long long cap_faces, unsigned long long* counts_device, void* stream);
 
 /* Host-side OBJ writer (no GPU involved).  Replaces save_obj_mesh_with_color (mesh_util.py:189-198):
  * "v %.4f %.4f %.4f %.4f %.4f %.4f" per vertex (host double verts [nverts][3], colors [nverts][3]) then

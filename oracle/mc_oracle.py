@@ -1,5 +1,6 @@
-"""CPU ORACLE (test infrastructure): ctypes face of oracle/mc_ref.c (sequential marching cubes).
-Built with gcc into oracle/_build/ by ``build()``; see mc_ref.c for what it follows."""
+"""CPU ORACLE (test infrastructure): ctypes face of oracle/mc_ref.c (sequential marching cubes that derives
+every cell's triangles at run time from the rule in rgb-d-pifuhd_b200/tools/gen_mc_tables.py - no lookup table
+shared with the product).  Built with gcc into oracle/_build/ by ``build()``; see mc_ref.c for what it follows."""
 import ctypes
 import os
 import subprocess
@@ -13,8 +14,7 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "mc_ref.c")
-    tab = os.path.join(os.path.dirname(_HERE), "rgb-d-pifuhd_b200", "csrc", "mc_tables.h")
-    if (not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(tab))):
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(src):
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     # -ffp-contract=off: no fused multiply-add, so the float64 arithmetic is the plain IEEE
@@ -33,7 +33,17 @@ def _load():
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _lib.mc_ref_run_slab.restype = ctypes.c_int
         _lib.mc_ref_ghost_verts.restype = ctypes.c_longlong
+        _lib.mc_ref_cell.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+        _lib.mc_ref_cell.restype = ctypes.c_int
     return _lib
+
+
+def cell_triangles(corner_values, level):
+    """The rule applied to ONE cell: eight corner values (corner order of the rule) -> flat list of edge ids."""
+    v = np.ascontiguousarray(corner_values, dtype=np.float64)
+    out = np.zeros(30, dtype=np.int32)
+    n = _load().mc_ref_cell(v.ctypes.data, float(level), out.ctypes.data)
+    return [int(x) for x in out[:3 * n]]
 
 
 def marching_cubes(volume, level):

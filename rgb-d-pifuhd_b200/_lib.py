@@ -49,6 +49,9 @@ SIGNATURES = {
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           c_ll_p, c_ll_p, c_ll_p, VP]),
     "pifu_mc_emit": (ctypes.c_int, [VP, VP, VP, VP, VP, VP]),
+    "pifu_mc_extract": (ctypes.c_int, [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, VP, VP, VP, VP, ctypes.c_longlong,
+                                       ctypes.c_longlong, VP, VP]),
     "pifu_write_obj": (ctypes.c_int, [ctypes.c_char_p, VP, VP, ctypes.c_longlong, VP, ctypes.c_longlong]),
     "pifu_bn_relu_f32": (ctypes.c_int, [VP, VP, VP, VP, VP, ctypes.c_double, ctypes.c_int, VP, ctypes.c_longlong,
                                         ctypes.c_int, ctypes.c_longlong, VP]),

@@ -30,6 +30,10 @@ struct OctreeState {
     int step = 0;
     long long voxels = 0;
     double* sdf = nullptr;           // [R0*R1*R2]
+    float* sdf32 = nullptr;          // the same field rounded to float32 (the cast scikit-image applies on entry), kept
+                                     // in step by every kernel that writes `sdf`: marching cubes reads it directly
+    float* sdf32_own = nullptr;      // library-owned target (stepwise form); the one-call form writes the caller's buffer
+    long long cap_vox32 = 0;
     uint8_t* todo = nullptr;         // `notprocessed`
     uint8_t* skip = nullptr;         // per cell of the current level
     uint32_t* skip_list = nullptr;   // the level's skip cells, compacted (any order)
@@ -49,7 +53,7 @@ struct OctreeState {
 
 void octree_free(OctreeState* s) {
     if (!s) return;
-    cudaFree(s->sdf); cudaFree(s->todo); cudaFree(s->skip); cudaFree(s->mid); cudaFree(s->ids);
+    cudaFree(s->sdf); cudaFree(s->sdf32_own); cudaFree(s->todo); cudaFree(s->skip); cudaFree(s->mid); cudaFree(s->ids);
     cudaFree(s->skip_list); cudaFree(s->skip_count);
     cudaFree(s->block_sums); cudaFree(s->partials); cudaFree(s->total_dev); cudaFree(s->vals);
     delete s;
@@ -86,17 +90,19 @@ __global__ void init_todo_kernel(uint8_t* __restrict__ todo, int R0, int R1, int
 // of the stride).  Every other voxel is evaluated or filled before anything reads it: a level's corners are
 // stride-lattice points, each either processed earlier or in this level's frontier, and the last level
 // evaluates all that is left.
-__global__ void zero_last_planes_kernel(double* __restrict__ sdf, int R0, int R1, int R2) {
+__global__ void zero_last_planes_kernel(double* __restrict__ sdf, float* __restrict__ sdf32, int R0, int R1, int R2) {
     const long long a = static_cast<long long>(R1) * R2, b = static_cast<long long>(R0) * R2, c = static_cast<long long>(R0) * R1;
     const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    long long v = -1;
     if (t < a) {
-        sdf[static_cast<long long>(R0 - 1) * a + t] = 0.0;
+        v = static_cast<long long>(R0 - 1) * a + t;
     } else if (t < a + b) {
         const long long u = t - a;
-        sdf[((u / R2) * R1 + (R1 - 1)) * R2 + u % R2] = 0.0;
+        v = ((u / R2) * R1 + (R1 - 1)) * R2 + u % R2;
     } else if (t < a + b + c) {
-        sdf[(t - a - b) * R2 + (R2 - 1)] = 0.0;
+        v = (t - a - b) * R2 + (R2 - 1);
     }
+    if (v >= 0) { sdf[v] = 0.0; sdf32[v] = 0.f; }
 }
 
 // candidate c of the stride lattice (n0 x n1 x n2 points) -> voxel id
@@ -172,11 +178,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK) frontier_write_kernel(const uint8_
 
 template <typename T>
 __global__ void commit_kernel(const T* __restrict__ vals, const long long* __restrict__ ids, long long n,
-                              double* __restrict__ sdf, uint8_t* __restrict__ todo) {
+                              double* __restrict__ sdf, float* __restrict__ sdf32, uint8_t* __restrict__ todo) {
     const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (p >= n) return;
     const long long v = ids[p];
     sdf[v] = static_cast<double>(vals[p]);       // the callable's values stored into the float64 field (`:148`)
+    sdf32[v] = static_cast<float>(vals[p]);
     todo[v] = 0;
 }
 
@@ -238,7 +245,7 @@ __host__ __device__ constexpr uint32_t nb_later_mask() {           // cells visi
 // cell's midpoint unless a skip cell visited LATER by the reference's loop covers them too (last writer wins).
 // A voxel at offset d of cell c is covered by the cells c + o with o_a = 0, o_a = +1 if d_a == step (high face)
 // or o_a = -1 if d_a == 0 (low face); "later" = lexicographically larger = first nonzero o_a is +1.
-__global__ void __launch_bounds__(256) fill_cells_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo,
+__global__ void __launch_bounds__(256) fill_cells_kernel(double* __restrict__ sdf, float* __restrict__ sdf32, uint8_t* __restrict__ todo,
                                                          const uint8_t* __restrict__ skip, const double* __restrict__ mid,
                                                          const uint32_t* __restrict__ skip_list,
                                                          const unsigned long long* __restrict__ skip_count, int step,
@@ -276,6 +283,7 @@ __global__ void __launch_bounds__(256) fill_cells_kernel(double* __restrict__ sd
             if (later & cover) continue;
             const long long p = (static_cast<long long>(px) * R1 + py) * R2 + pz;
             sdf[p] = m;
+            sdf32[p] = static_cast<float>(m);
             todo[p] = 0;
         }
     }
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(256) fill_cells_kernel(double* __restrict__ sd
 // One thread per 4 consecutive voxels of a lattice row (i, j, 4 qk .. 4 qk + 3), so a warp's stores cover
 // 1 KiB of the float64 field contiguously.  The voxels of one run of `step` share their candidate cells,
 // except that a run's first voxel may also lie on the high face of cell ck - 1.
-__global__ void __launch_bounds__(256) fill_kernel(double* __restrict__ sdf, uint8_t* __restrict__ todo,
+__global__ void __launch_bounds__(256) fill_kernel(double* __restrict__ sdf, float* __restrict__ sdf32, uint8_t* __restrict__ todo,
                                                    const uint8_t* __restrict__ skip, const double* __restrict__ mid, int step,
                                                    int shift, int c0, int c1, int c2, int R0, int R1, int R2, int quads) {
     // grid (quads, rows j, planes i): no index divisions; `shift` >= 0 when step == 1 << shift
@@ -346,18 +354,14 @@ __global__ void __launch_bounds__(256) fill_kernel(double* __restrict__ sdf, uin
     if (hit_mask == 0xFu && (v0 & 3) == 0) {
         *reinterpret_cast<double2*>(sdf + v0) = make_double2(val[0], val[1]);
         *reinterpret_cast<double2*>(sdf + v0 + 2) = make_double2(val[2], val[3]);
+        *reinterpret_cast<float4*>(sdf32 + v0) = make_float4(static_cast<float>(val[0]), static_cast<float>(val[1]),
+                                                             static_cast<float>(val[2]), static_cast<float>(val[3]));
         *reinterpret_cast<uint32_t*>(todo + v0) = 0u;
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (hit_mask & (1u << q)) { sdf[v0 + q] = val[q]; todo[v0 + q] = 0; }
+            if (hit_mask & (1u << q)) { sdf[v0 + q] = val[q]; sdf32[v0 + q] = static_cast<float>(val[q]); todo[v0 + q] = 0; }
     }
-}
-
-__global__ void to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        out[i] = static_cast<float>(in[i]);
 }
 
 template <typename T>
@@ -374,7 +378,7 @@ inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 }  // namespace
 
-int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s) {
+int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s, float* sdf32_target) {
     OctreeState*& st = ctx_octree(c);
     if (!st) st = new OctreeState();
     if (init_res <= 0 || R0 <= 0 || R1 <= 0 || R2 <= 0) { set_error("octree: bad resolution"); return -1; }
@@ -388,15 +392,22 @@ int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double thres
     capv = st->cap_vox;
     if (grow(&st->todo, &capv, st->voxels)) return -1;
     st->cap_vox = capv;
+    if (sdf32_target) {
+        st->sdf32 = sdf32_target;
+    } else {
+        if (grow(&st->sdf32_own, &st->cap_vox32, st->voxels)) return -1;
+        st->sdf32 = st->sdf32_own;
+    }
     if (!st->total_dev) PIFU_CUDA(cudaMalloc(&st->total_dev, 2 * sizeof(unsigned long long)));
     const int quads = ceil_div(R2, 4);
     init_todo_kernel<<<ceil_div(static_cast<long long>(R0) * R1 * quads, 256), 256, 0, s>>>(st->todo, R0, R1, R2, quads);
     if (st->step > 0) {
         const long long planes = static_cast<long long>(R1) * R2 + static_cast<long long>(R0) * R2 + static_cast<long long>(R0) * R1;
-        zero_last_planes_kernel<<<ceil_div(planes, 256), 256, 0, s>>>(st->sdf, R0, R1, R2);
+        zero_last_planes_kernel<<<ceil_div(planes, 256), 256, 0, s>>>(st->sdf, st->sdf32, R0, R1, R2);
     } else {
         // resolution < init_resolution: the reference's loop never runs and the field stays all zero (`:138-140`)
         PIFU_CUDA(cudaMemsetAsync(st->sdf, 0, static_cast<size_t>(st->voxels) * sizeof(double), s));
+        PIFU_CUDA(cudaMemsetAsync(st->sdf32, 0, static_cast<size_t>(st->voxels) * sizeof(float), s));
     }
     PIFU_CUDA(cudaGetLastError());
     ctx_count_launch(c, 2);
@@ -444,9 +455,9 @@ int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStre
     if (st->frontier) {
         if (!vals && !vals64) { set_error("octree: null values for a frontier of %lld points", st->frontier); return -1; }
         if (vals64)
-            commit_kernel<double><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals64, st->ids, st->frontier, st->sdf, st->todo);
+            commit_kernel<double><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals64, st->ids, st->frontier, st->sdf, st->sdf32, st->todo);
         else
-            commit_kernel<float><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals, st->ids, st->frontier, st->sdf, st->todo);
+            commit_kernel<float><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals, st->ids, st->frontier, st->sdf, st->sdf32, st->todo);
         ctx_count_launch(c, 1);
     }
     const int step = st->step;
@@ -475,12 +486,12 @@ int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStre
                 while (tx < quads && tx < 256) tx *= 2;
                 const dim3 blk(tx, 256 / tx, 1);
                 const dim3 grd(ceil_div(quads, tx), ceil_div(st->R[1], blk.y), st->R[0]);
-                fill_kernel<<<grd, blk, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, step, shift, c0, c1, c2,
+                fill_kernel<<<grd, blk, 0, s>>>(st->sdf, st->sdf32, st->todo, st->skip, st->mid, step, shift, c0, c1, c2,
                                                st->R[0], st->R[1], st->R[2], quads);
             } else {
                 // fine levels fill a thin shell: persistent warps over the compacted skip cells; the count stays on
                 // the device (no host sync) (step 4 / 2: 0.12 / 0.25 ms against 0.34 / 0.52 ms voxel by voxel)
-                fill_cells_kernel<<<ctx_num_sms(c) * 8, 256, 0, s>>>(st->sdf, st->todo, st->skip, st->mid, st->skip_list,
+                fill_cells_kernel<<<ctx_num_sms(c) * 8, 256, 0, s>>>(st->sdf, st->sdf32, st->todo, st->skip, st->mid, st->skip_list,
                                                                     st->skip_count, step, c0, c1, c2, st->R[0], st->R[1], st->R[2]);
             }
             ctx_count_launch(c, 2);
@@ -495,11 +506,8 @@ int octree_export(pifu_ctx* c, double* sdf64, float* sdf32, cudaStream_t s) {
     OctreeState* st = ctx_octree(c);
     if (!st || !st->sdf) { set_error("octree: no field"); return -1; }
     if (sdf64) PIFU_CUDA(cudaMemcpyAsync(sdf64, st->sdf, st->voxels * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    if (sdf32) {
-        to_f32_kernel<<<4096, 256, 0, s>>>(st->sdf, sdf32, st->voxels);
-        PIFU_CUDA(cudaGetLastError());
-        ctx_count_launch(c, 1);
-    }
+    if (sdf32 && sdf32 != st->sdf32)      // the one-call form wrote the caller's buffer all along
+        PIFU_CUDA(cudaMemcpyAsync(sdf32, st->sdf32, st->voxels * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 
@@ -518,7 +526,7 @@ extern "C" {
 
 int pifu_octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_resolution, double threshold, void* stream) {
     if (!c) { set_error("null context"); return -1; }
-    return octree_begin(c, R0, R1, R2, init_resolution, threshold, static_cast<cudaStream_t>(stream));
+    return octree_begin(c, R0, R1, R2, init_resolution, threshold, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 int pifu_octree_frontier(pifu_ctx* c, long long* n, const long long** ids, int* step, void* stream) {
@@ -556,7 +564,7 @@ int pifu_eval_grid_octree(pifu_ctx* c, int levels, int R0, int R1, int R2, int i
         return -1;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (octree_begin(c, R0, R1, R2, init_resolution, threshold, s)) return -1;
+    if (octree_begin(c, R0, R1, R2, init_resolution, threshold, s, sdf32)) return -1;
     int lvl = 0;
     for (;;) {
         OctreeState* st = ctx_octree(c);

@@ -50,6 +50,7 @@ class Engine:
         self._normalised = [False, False]
         self._keep = {}
         self._hold = {}
+        self._mc_hint = {}
         self.precision = 0
 
     def __del__(self):
@@ -312,28 +313,47 @@ class Engine:
         return sdf64, sdf32
 
     # ------------------------------------------------------------------ marching cubes
+    def _mc_extract(self, f, level, i_global0, global_n0, cell_layers, ghost, want_normals, key):
+        """count + emit without a host synchronisation in between (`pifu_mc_extract`): the outputs are allocated
+        from the sizes of the previous extraction of the same kind (+ 50 %); the counts come back with one read,
+        and only an overflow repeats the call.  -> (verts, faces, normals, values, ghost_verts), exact-size views."""
+        hint = self._mc_hint.get(key)
+        if hint is None:
+            hint = (64 * f.shape[1] * f.shape[2] // 8 + 4096, 128 * f.shape[1] * f.shape[2] // 8 + 8192)
+        cap_v, cap_f = int(hint[0] * 3 // 2) + 1024, int(hint[1] * 3 // 2) + 2048
+        while True:
+            verts = torch.empty((cap_v, 3), device=self.device, dtype=torch.float64)
+            faces = torch.empty((cap_f, 3), device=self.device, dtype=torch.int32)
+            normals = torch.empty((cap_v, 3), device=self.device, dtype=torch.float32) if want_normals else None
+            values = torch.empty((cap_v,), device=self.device, dtype=torch.float32) if want_normals else None
+            counts = torch.empty(3, device=self.device, dtype=torch.int64)
+            _lib.check(self.lib.pifu_mc_extract(
+                self.h, ctypes.c_void_p(f.data_ptr()), f.shape[0], f.shape[1], f.shape[2], float(level),
+                int(i_global0), int(global_n0), int(cell_layers), 1 if ghost else 0,
+                ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(faces.data_ptr()),
+                ctypes.c_void_p(normals.data_ptr()) if want_normals else None,
+                ctypes.c_void_p(values.data_ptr()) if want_normals else None,
+                cap_v, cap_f, ctypes.c_void_p(counts.data_ptr()), _stream(self.device_index)))
+            nv, nf, ng = (int(x) for x in counts.tolist())
+            self._mc_hint[key] = (nv, nf)
+            if nv <= cap_v and nf <= cap_f:
+                break
+            cap_v, cap_f = max(cap_v, nv), max(cap_f, nf)
+        self._keep["mc_field"] = f
+        return (verts[:nv], faces[:nf], normals[:nv] if want_normals else None,
+                values[:nv] if want_normals else None, ng)
+
     def marching_cubes(self, field, level, want_normals=True):
         """field: device float32 [n0, n1, n2].  -> (verts f64 [V,3], faces i32 [F,3], normals, values)
         on the device.  Raises ValueError like skimage when there is no surface at `level`."""
         f = field.to(self.device, torch.float32).contiguous()
         if f.dim() != 3:
             raise ValueError("Input volume should be a 3D array")
-        nv, nf = ctypes.c_longlong(), ctypes.c_longlong()
-        _lib.check(self.lib.pifu_mc_count(self.h, ctypes.c_void_p(f.data_ptr()), f.shape[0], f.shape[1], f.shape[2],
-                                          float(level), ctypes.byref(nv), ctypes.byref(nf), _stream(self.device_index)))
-        if nv.value == 0:
+        verts, faces, normals, values, _ = self._mc_extract(f, level, 0, f.shape[0], f.shape[0] - 1, False, want_normals,
+                                                            ("whole",) + tuple(f.shape))
+        if verts.shape[0] == 0:
             raise ValueError("No surface found at the given iso value (or level outside the data range)")
-        verts = torch.empty((nv.value, 3), device=self.device, dtype=torch.float64)
-        faces = torch.empty((nf.value, 3), device=self.device, dtype=torch.int32)
-        normals = torch.empty((nv.value, 3), device=self.device, dtype=torch.float32) if want_normals else None
-        values = torch.empty((nv.value,), device=self.device, dtype=torch.float32) if want_normals else None
-        _lib.check(self.lib.pifu_mc_emit(self.h, ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(faces.data_ptr()),
-                                         ctypes.c_void_p(normals.data_ptr()) if want_normals else None,
-                                         ctypes.c_void_p(values.data_ptr()) if want_normals else None,
-                                         _stream(self.device_index)))
-        self._keep["mc_field"] = f
         return verts, faces, normals, values
-
 
     def marching_cubes_slab(self, field, level, i_global0, global_n0, cell_layers, ghost, want_normals=True):
         """Slab form (multi-GPU): `field` = planes [i_global0, i_global0 + n0) of a global_n0-plane
@@ -342,23 +362,8 @@ class Engine:
         ghost_verts vertices and renumbers faces by (first own global vertex number - ghost_verts).
         An empty slab returns zero-length tensors (a neighbour may still hold the surface)."""
         f = field.to(self.device, torch.float32).contiguous()
-        nv, nf, ng = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
-        _lib.check(self.lib.pifu_mc_count_slab(
-            self.h, ctypes.c_void_p(f.data_ptr()), f.shape[0], f.shape[1], f.shape[2], float(level),
-            int(i_global0), int(global_n0), int(cell_layers), 1 if ghost else 0,
-            ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(ng), _stream(self.device_index)))
-        verts = torch.empty((nv.value, 3), device=self.device, dtype=torch.float64)
-        faces = torch.empty((nf.value, 3), device=self.device, dtype=torch.int32)
-        normals = torch.empty((nv.value, 3), device=self.device, dtype=torch.float32) if want_normals else None
-        values = torch.empty((nv.value,), device=self.device, dtype=torch.float32) if want_normals else None
-        if nv.value:
-            _lib.check(self.lib.pifu_mc_emit(self.h, ctypes.c_void_p(verts.data_ptr()),
-                                             ctypes.c_void_p(faces.data_ptr()) if nf.value else None,
-                                             ctypes.c_void_p(normals.data_ptr()) if want_normals else None,
-                                             ctypes.c_void_p(values.data_ptr()) if want_normals else None,
-                                             _stream(self.device_index)))
-        self._keep["mc_field"] = f
-        return verts, faces, normals, values, int(ng.value)
+        return self._mc_extract(f, level, i_global0, global_n0, cell_layers, ghost, want_normals,
+                                ("slab", int(i_global0), int(cell_layers)) + tuple(f.shape))
 
 
 class _DevView:

@@ -69,3 +69,97 @@ def test_first_use_numbering_and_errors():
     flat = np.full((6, 6, 6), 0.25, np.float32)
     with pytest.raises((ValueError, RuntimeError)):
         mc_oracle.marching_cubes(flat, 0.5)
+
+
+# ----------------------------------------------------------------------------- the rule, the tables, the oracle
+def _generator():
+    import importlib.util
+    import os
+    from helpers import ROOT
+    path = os.path.join(ROOT, "rgb-d-pifuhd_b200", "tools", "gen_mc_tables.py")
+    spec = importlib.util.spec_from_file_location("gen_mc_tables", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _header_rows():
+    """(MC_AMB, MC_SUB_BASE, MC_TRIS rows) parsed from the header the CUDA kernels compile."""
+    import os
+    import re
+    from helpers import ROOT
+    text = open(os.path.join(ROOT, "rgb-d-pifuhd_b200", "csrc", "mc_tables.h")).read()
+
+    def flat(name):
+        m = re.search(name + r"\[[^\]]*\](?:\[[^\]]*\])? = \{(.*?)\};", text, re.S)
+        return [int(x) for x in re.findall(r"-?\d+", m.group(1))]
+    nsub = int(re.search(r"#define MC_NSUB (\d+)", text).group(1))
+    max_t = int(re.search(r"#define MC_MAX_TRIS (\d+)", text).group(1))
+    tris = np.array(flat("MC_TRIS")).reshape(nsub, 3 * max_t)
+    return flat("MC_AMB"), flat("MC_SUB_BASE"), [[int(x) for x in r if x >= 0] for r in tris]
+
+
+def test_header_is_the_generators_output():
+    g = _generator()
+    amb, base, rows = g.build()
+    h_amb, h_base, h_rows = _header_rows()
+    assert h_amb == amb and h_base == base
+    assert h_rows == [t for t, _ in rows]
+
+
+def test_oracle_derives_the_table_rows_independently():
+    """oracle/mc_ref.c includes no table: it applies the rule to a cell's eight values at run time.  For random cells
+    (all 254 surface cases, every reachable resolution of their ambiguous faces) its triangles must be the row the
+    CUDA kernels would read - so a wrong table entry, sub-case index or face test cannot hide."""
+    g = _generator()
+    amb, base, rows = _header_rows()
+    rng = np.random.default_rng(0)
+    seen = set()
+    for it in range(60000):
+        case = int(rng.integers(1, 255)) if it >= 254 else it + 1
+        mag = np.exp(rng.uniform(-3, 3, 8))
+        inside = np.array([(case >> c) & 1 for c in range(8)], bool)
+        v = np.where(inside, 0.5 + mag, 0.5 - mag)
+        bits = q = 0
+        for fi, f in enumerate(g.FACES):
+            if (amb[case] >> fi) & 1:
+                i0 = 0 if inside[f[0]] else 1
+                pin = (v[f[i0]] - 0.5) * (v[f[i0 + 2]] - 0.5)
+                pout = (v[f[i0 ^ 1]] - 0.5) * (v[f[(i0 ^ 1) + 2]] - 0.5)
+                bits |= int(pin > pout) << q
+                q += 1
+        sub = base[case] + bits
+        assert mc_oracle.cell_triangles(v, 0.5) == rows[sub], (case, bits)
+        seen.add(sub)
+    assert len(seen) > 600                                  # of 656 rows; the rest need value patterns that cannot occur
+
+
+def test_face_test_is_the_asymptotic_decider():
+    """One ambiguous face, bilinear values: the inside corners are joined across the face exactly when the
+    interpolant's saddle value is inside (Lewiner's test_face / Nielson-Hamann)."""
+    g = _generator()
+    rng = np.random.default_rng(3)
+    case = (1 << 0) | (1 << 2)                              # corners 0 and 2: a diagonal of face 0, also cut on other faces
+    for _ in range(500):
+        a, c = 0.5 + rng.uniform(0.01, 1, 2)
+        b, d = 0.5 - rng.uniform(0.01, 1, 2)
+        v = np.array([a, b, c, d, 0.1, 0.1, 0.1, 0.1])
+        tris = mc_oracle.cell_triangles(v, 0.5)
+        saddle = ((a - 0.5) * (c - 0.5) - (b - 0.5) * (d - 0.5)) / ((a - 0.5) + (c - 0.5) - (b - 0.5) - (d - 0.5))
+        edges_used = set(tris)
+        # separated: two triangles (one per inside corner); joined: the corners share one sheet (4 triangles, 6 vertices)
+        assert (len(tris) // 3 == 4) == (saddle > 0), (v, tris)
+        assert edges_used == {0, 3, 8, 1, 2, 10}
+
+
+def test_torus_euler_characteristic():
+    n = 48
+    gx = np.linspace(-1.3, 1.3, n)
+    x, y, z = np.meshgrid(gx, gx, gx, indexing="ij")
+    vol = (0.25 - np.sqrt((np.sqrt(x ** 2 + y ** 2) - 0.8) ** 2 + z ** 2)).astype(np.float32) + 0.5
+    v, f, _, _, _ = mc_oracle.marching_cubes(vol, 0.5)
+    e = edges_of(f)
+    key = e[:, 0].astype(np.int64) * len(v) + e[:, 1]
+    rkey = e[:, 1].astype(np.int64) * len(v) + e[:, 0]
+    assert np.array_equal(np.sort(key), np.sort(rkey)) and len(np.unique(key)) == len(key)
+    assert len(v) - len(key) // 2 + len(f) == 0              # genus 1
