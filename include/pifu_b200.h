@@ -200,6 +200,26 @@ int pifu_bn_relu_f32(const float* x, const float* running_mean, const float* run
 int pifu_cat3_add_f32(const float* a, const float* b, const float* c, const float* s, float* out, long long N,
                       long long la, long long lb, long long lc, void* stream);
 
+/* Vertex colours from an image (no context; launches on the CURRENT device).  Replaces, for one view,
+ * `xyz = net.projection(verts, calib); color = index(image, xyz[:, :2])` of gen_mesh_imgColor (reconstruction.py:110-116;
+ * BasePIFuNet.py:11-65): points device fp32 [3][n] (row stride pstride) are projected with calib (host, 16 floats) -
+ * orthogonal, or perspective (xy / z) - and the device fp32 image [C][H][W] is sampled bilinearly (align_corners=True,
+ * zeros outside, the arithmetic of the query kernels).  out: device fp32 [C][n]. */
+int pifu_sample_image(const float* image_nchw, int C, int H, int W, const float* points, long long pstride, long long n,
+                      const float* calib, int perspective, float* out, void* stream);
+
+/* Largest connected component of a triangle mesh (no context; CURRENT device; synchronous).  Replaces meshcleaning
+ * (reconstruction.py:325-344: trimesh.load(path).split(), keep the component with the greatest extent along axis 0).
+ * trimesh is third-party and absent here; its behaviour for this call is restated: faces sharing an edge that exactly two
+ * faces use are adjacent; with only_watertight (what split() defaults to) a component counts only if every one of its
+ * edges is used by exactly two faces and it has at least 4 faces; components are ordered by their first face; the first
+ * one of maximal extent wins.  All pointers are device memory: verts double [nverts][3], colors double [nverts][3] or
+ * NULL, faces int32 [nfaces][3]; outputs have the capacity of the inputs and receive the kept vertices (original order)
+ * and the renumbered faces; counts (HOST, 2 entries) receives the kept vertex and face counts.  -1 with an error
+ * message when no component qualifies (trimesh: `cc[0]` raises). */
+int pifu_mesh_clean(const double* verts, const double* colors, const int* faces, long long nverts, long long nfaces,
+                    int only_watertight, double* out_verts, double* out_colors, int* out_faces, long long* counts, void* stream);
+
 /* Number of kernels launched by this context since creation (bench accounting). */
 long long pifu_launch_count(pifu_ctx* ctx);
 

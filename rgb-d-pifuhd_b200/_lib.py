@@ -57,6 +57,9 @@ SIGNATURES = {
                                         ctypes.c_int, ctypes.c_longlong, VP]),
     "pifu_cat3_add_f32": (ctypes.c_int, [VP, VP, VP, VP, VP, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
                                          ctypes.c_longlong, VP]),
+    "pifu_sample_image": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, VP, ctypes.c_longlong, ctypes.c_longlong,
+                                         c_float_p, ctypes.c_int, VP, VP]),
+    "pifu_mesh_clean": (ctypes.c_int, [VP, VP, VP, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, VP, VP, VP, c_ll_p, VP]),
     "pifu_launch_count": (ctypes.c_longlong, [VP]),
     "pifu_profile_enable": (ctypes.c_int, [VP, ctypes.c_int]),
     "pifu_profile_read": (ctypes.c_int, [VP, c_ll_p, c_double_p, c_double_p]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpifu_b200.so")
-SOURCES = ["api.cu", "gather.cu", "gemm_tc.cu", "chain_tc.cu", "runs.cu", "refine.cu", "gemm_simt.cu", "pack.cu", "octree.cu", "mc.cu", "norm.cu", "obj.cu", "encoder_ops.cu"]
+SOURCES = ["api.cu", "gather.cu", "gemm_tc.cu", "chain_tc.cu", "runs.cu", "refine.cu", "meshclean.cu", "gemm_simt.cu", "pack.cu", "octree.cu", "mc.cu", "norm.cu", "obj.cu", "encoder_ops.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"] + [f for f in os.environ.get("PIFU_NVCC_FLAGS", "").split() if f]

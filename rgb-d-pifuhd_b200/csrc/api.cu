@@ -1310,6 +1310,19 @@ int pifu_eval_lattice_ids(pifu_ctx* c, int levels, int R0, int R1, int R2, const
     return pifu::eval_ids(c, levels, R0, R1, R2, ids, n, calib, calib_inv, out, static_cast<cudaStream_t>(stream));
 }
 
+int pifu_sample_image(const float* image_nchw, int C, int H, int W, const float* points, long long pstride, long long n,
+                      const float* calib, int perspective, float* out, void* stream) {
+    if (!image_nchw || !points || !calib || !out || C <= 0 || H <= 0 || W <= 0 || n < 0) { set_error("bad arguments to pifu_sample_image"); return -1; }
+    return launch_sample_image(image_nchw, C, H, W, points, pstride, n, calib, perspective ? 1 : 0, out, static_cast<cudaStream_t>(stream));
+}
+
+int pifu_mesh_clean(const double* verts, const double* colors, const int* faces, long long nverts, long long nfaces,
+                    int only_watertight, double* out_verts, double* out_colors, int* out_faces, long long* counts, void* stream) {
+    if (!verts || !faces || !out_verts || !out_faces || !counts || (colors && !out_colors)) { set_error("bad arguments to pifu_mesh_clean"); return -1; }
+    return mesh_clean(verts, colors, faces, nverts, nfaces, only_watertight ? 1 : 0, 0, out_verts, out_colors, out_faces, counts, 0,
+                      static_cast<cudaStream_t>(stream));
+}
+
 int pifu_debug_gemm(pifu_ctx* c, const float* X, const float* W, const float* b, int M, int K, int N,
                     int leaky, float* Y, void* stream) {
     if (!c) { set_error("null context"); return -1; }

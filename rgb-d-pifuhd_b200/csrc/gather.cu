@@ -196,7 +196,39 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
     }
 }
 
+struct Calib12 { float c[12]; };
+
+// Vertex colours from an image (`reconstruction.py:110-116`: xyz = projection(verts, calib); color = index(image, xy)):
+// one thread per point, the image stays NCHW (3 channels: a tap is 3 strided 4-byte reads).
+__global__ void __launch_bounds__(256) sample_image_kernel(const float* __restrict__ img, int C, int H, int W,
+                                                           const float* __restrict__ pts, long long pstride, long long n,
+                                                           const Calib12 cal, int perspective, float* __restrict__ out) {
+    const long long p = blockIdx.x * 256LL + threadIdx.x;
+    if (p >= n) return;
+    float x, y, z;
+    project(cal.c, perspective, __ldg(pts + p), __ldg(pts + pstride + p), __ldg(pts + 2 * pstride + p), x, y, z);
+    const Taps t = make_taps(x, y, H, W, 1);
+    const long long plane = static_cast<long long>(H) * W;
+    for (int ch = 0; ch < C; ++ch) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (t.off[i] >= 0) acc = fmaf(__ldg(img + ch * plane + t.off[i]), t.w[i], acc);
+        out[ch * n + p] = acc;
+    }
+}
+
 }  // namespace
+
+int launch_sample_image(const float* img, int C, int H, int W, const float* pts, long long pstride, long long n,
+                        const float* calib12, int perspective, float* out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    Calib12 cal;
+    for (int q = 0; q < 12; ++q) cal.c[q] = calib12[q];
+    sample_image_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(img, C, H, W, pts, pstride, n, cal, perspective, out);
+    PIFU_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_gather(const GatherArgs& a, cudaStream_t s) {
     if (a.n <= 0) return 0;

@@ -16,6 +16,14 @@ int launch_nchw_to_nhwc(const float* in, float* out, int C, int HW, cudaStream_t
 int launch_unblock(const uint8_t* buf, const uint8_t* buf_lo, int kb_stride, int kb_off, int C, int n, float* dst, long long ld,
                    cudaStream_t s);
 
+// gather.cu: bilinear samples of an NCHW image at projected points (vertex colours); calib12 = host, rows 0..2 of the 4x4
+int launch_sample_image(const float* img, int C, int H, int W, const float* pts, long long pstride, long long n,
+                        const float* calib12, int perspective, float* out, cudaStream_t s);
+
+// meshclean.cu
+int mesh_clean(const double* verts, const double* colors, const int* faces, long long nv, long long nf, int only_watertight,
+               int axis, double* out_verts, double* out_colors, int* out_faces, long long* counts_host, int num_sms, cudaStream_t s);
+
 // norm.cu: normalised stacks (GroupNorm / batch statistics) and the un-fused last layer
 struct ASeg;
 int launch_group_norm(const float* x, uint8_t* buf, uint8_t* buf_lo, int nkb, int channels, int groups, int m_tiles, int n_valid,

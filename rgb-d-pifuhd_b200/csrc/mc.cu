@@ -14,16 +14,19 @@
 // first-use order (MC_VERTS of its table row).
 //
 // Passes (HBM-bound; the field is read from DRAM once):
-//   classify  one thread per 4 x 8 cells (4 rows, 8 cells along axis 2): 10 field rows x 9 values -> 9-bit inside
-//             masks; ~99 % of the threads see one side of the level only and write nothing.  The others add their
-//             rows' vertex / triangle counts to per-row sums (integer atomics, order-free).
+//   classify  streaming form: a warp owns 8 cell rows x 128 values and walks 16 layers; every field plane of the tile is
+//             read once as 16-byte vectors (9 independent loads per lane, no shared memory, no barrier) and reduced to
+//             inside bits packed into 64-bit words; `any ^ all` of the eight corner words marks the surface cells
+//             among a lane's 32 cells.  ~99 % of the lanes see one side of the level only and do nothing more.
+//             Surface cells add their vertex / triangle counts to per-row sums (integer atomics, order-free).
 //   scan      device-wide exclusive scan of the two per-row arrays; rows with any output are listed.
-//   vertices  persistent blocks over the listed rows: cases and table rows of the row's cells recomputed from the
-//             field (L2), block scan -> first vertex number of every surface cell, written with its table row to
-//             a sparse per-cell record; the row's vertices are then computed one per thread.
-//   faces     same traversal; vertex numbers come from the owning cells' records.
+//   rows      teams of threads over the listed rows: cases and table rows recomputed from the field (L2), team scans
+//             -> every surface cell's record {first vertex number, table row} in a sparse per-cell array, and one job
+//             per vertex / triangle written at its own final index.
+//   vertices, faces   flat passes, one thread per vertex / triangle; face indices come from the owning cells' records.
 // No per-cell array is written for the 99 % of cells the surface does not touch.
 #include <cmath>
+#include <cstdlib>
 
 #include "../../include/pifu_b200.h"
 #include "common.cuh"
@@ -47,6 +50,9 @@ struct McState {
     uint8_t* own = nullptr;            // [256][8] vertices a cell of case cs creates, by border mask
     unsigned long long* totals = nullptr;   // [4] device: vertices, triangles, ghost-layer vertices, listed rows
     uint32_t* active = nullptr;        // rows that create a vertex or a triangle
+    unsigned long long* vjobs = nullptr;   // one job per vertex / triangle, at the vertex's / triangle's own index
+    unsigned long long* tjobs = nullptr;
+    long long cap_vjobs = 0, cap_tjobs = 0;
     long long cap_cells = 0, cap_rows = 0, cap_partials = 0;
     long long nverts = 0, nfaces = 0;
     // slab mode (multi-GPU): the volume is planes [i0, i0 + n[0]) of a g0-plane field;
@@ -57,7 +63,7 @@ struct McState {
 void mc_free(McState* s) {
     if (!s) return;
     cudaFree(s->cellinfo); cudaFree(s->vsums); cudaFree(s->tsums); cudaFree(s->totals);
-    cudaFree(s->partials); cudaFree(s->own); cudaFree(s->active);
+    cudaFree(s->partials); cudaFree(s->own); cudaFree(s->active); cudaFree(s->vjobs); cudaFree(s->tjobs);
     delete s;
 }
 
@@ -65,7 +71,6 @@ namespace {
 
 constexpr int CPT = 8;                 // cells per thread along axis 2
 constexpr int RPT = 4;                 // cell rows per classify thread along axis 1
-constexpr int EMIT_LIST = 6144;        // vertices / triangles of one row chunk redistributed over the block's threads
 
 // n*: planes of the local volume; c*: cell layers processed; nq = threads per cell row, njg = row groups per layer;
 // i0 / g0: global index of local plane 0 and global plane count (slab mode); ghost: leading cell
@@ -190,6 +195,109 @@ __global__ void __launch_bounds__(256) classify_kernel(const float* __restrict__
     }
 }
 
+// Pass 1, streaming form (the default): no shared memory, no barriers.  A WARP owns a tile of WR cell rows x 128 values
+// along axis 2 and walks WL cell layers; per layer every lane issues WR + 1 independent 16-byte loads (its 4 values of
+// each field row of the new plane) and reduces them to 4-bit inside masks, packed 4 bits per row into one 64-bit word
+// per plane (A: values k .. k+3; B: values k+1 .. k+4, the last bit shuffled in from the next lane).  One 64-bit
+// expression - `any ^ all` over the eight corner words of the two planes - then marks the surface cells among the
+// lane's WR x 4 cells; the previous plane's words are kept for the next layer, so every field value is loaded once
+// (+ 1/WR for the shared row, + 1/WL for the shared plane, + 1/128 for the tile's last column).
+constexpr int WR = 8;
+constexpr int WL = 16;
+
+struct PlaneBits { unsigned long long a, b; };
+
+__device__ __forceinline__ PlaneBits warp_plane_bits(const float* __restrict__ f, const Dims& d, int plane, int j0, int frows,
+                                                     int k0, float lf, int vec, int lane) {
+    float4 v[WR + 1];
+    float nx[WR + 1];
+    const float* base = f + (static_cast<long long>(plane) * d.n1 + j0) * d.n2 + k0;
+    const bool tail = lane == 31 && k0 + 4 < d.n2;          // the tile's last column + 1 belongs to the next tile
+#pragma unroll
+    for (int r = 0; r <= WR; ++r) {
+        v[r] = make_float4(lf, lf, lf, lf);
+        nx[r] = lf;
+        if (r < frows) {
+            const float* p = base + static_cast<long long>(r) * d.n2;
+            if (vec && k0 + 4 <= d.n2) {
+                v[r] = __ldg(reinterpret_cast<const float4*>(p));
+            } else {
+                if (k0 < d.n2) v[r].x = __ldg(p);
+                if (k0 + 1 < d.n2) v[r].y = __ldg(p + 1);
+                if (k0 + 2 < d.n2) v[r].z = __ldg(p + 2);
+                if (k0 + 3 < d.n2) v[r].w = __ldg(p + 3);
+            }
+            if (tail) nx[r] = __ldg(p + 4);
+        }
+    }
+    PlaneBits pb = {0ull, 0ull};
+#pragma unroll
+    for (int r = 0; r <= WR; ++r) {
+        const uint32_t nib = (v[r].x > lf ? 1u : 0u) | (v[r].y > lf ? 2u : 0u) | (v[r].z > lf ? 4u : 0u) | (v[r].w > lf ? 8u : 0u);
+        uint32_t next = __shfl_down_sync(0xffffffffu, nib, 1) & 1u;
+        if (lane == 31) next = nx[r] > lf ? 1u : 0u;
+        pb.a |= static_cast<unsigned long long>(nib) << (4 * r);
+        pb.b |= static_cast<unsigned long long>((nib >> 1) | (next << 3)) << (4 * r);
+    }
+    return pb;
+}
+
+__global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
+                                                            int nkt, int nbands, int nchunks, const uint8_t* __restrict__ own,
+                                                            uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums) {
+    const int lane = threadIdx.x & 31;
+    const long long wg = blockIdx.x * 8LL + (threadIdx.x >> 5);
+    const int kt = static_cast<int>(wg % nkt);
+    const long long rest = wg / nkt;
+    const int band = static_cast<int>(rest % nbands), ch = static_cast<int>(rest / nbands);
+    if (ch >= nchunks) return;
+    const int k0 = kt * 128 + 4 * lane, j0 = band * WR;
+    const int crows = d.c1 - j0 < WR ? d.c1 - j0 : WR;            // cell rows of the tile; field rows: crows + 1
+    const int ia = ch * WL, ib = ia + WL < d.c0 ? ia + WL : d.c0;
+    // cells of this lane that exist: 4 bits per row, rows < crows
+    const int nc = d.c2 - k0;
+    const unsigned long long vm = nc >= 4 ? 0xfull : (nc > 0 ? ((1ull << nc) - 1ull) : 0ull);
+    unsigned long long valid = 0ull;
+    for (int r = 0; r < crows; ++r) valid |= vm << (4 * r);
+    PlaneBits lo = warp_plane_bits(f, d, ia, j0, crows + 1, k0, lf, vec, lane);
+    for (int i = ia; i < ib; ++i) {
+        const PlaneBits hi = warp_plane_bits(f, d, i + 1, j0, crows + 1, k0, lf, vec, lane);
+        const unsigned long long any = lo.a | (lo.a >> 4) | lo.b | (lo.b >> 4) | hi.a | (hi.a >> 4) | hi.b | (hi.b >> 4);
+        const unsigned long long all = lo.a & (lo.a >> 4) & lo.b & (lo.b >> 4) & hi.a & (hi.a >> 4) & hi.b & (hi.b >> 4);
+        unsigned long long act = (any ^ all) & valid;
+        if (act != 0ull) {
+            const int zi = (i + d.i0 == 0) ? 1 : 0;
+            int cur = -1;
+            uint32_t nv = 0, nt = 0;
+            while (act) {
+                const int bit = __ffsll(static_cast<long long>(act)) - 1;
+                act &= act - 1ull;
+                const int r = bit >> 2, m = bit & 3;
+                if (r != cur) {                                   // counts are flushed row by row
+                    if (cur >= 0) {
+                        const long long row = static_cast<long long>(i) * d.c1 + j0 + cur;
+                        if (nv) atomicAdd(vsums + row, nv);
+                        if (nt) atomicAdd(tsums + row, nt);
+                    }
+                    cur = r; nv = 0; nt = 0;
+                }
+                const int s0 = bit, s1 = bit + 4;                 // row r / row r + 1 of the packed words
+                const uint32_t cs = static_cast<uint32_t>((lo.a >> s0) & 1ull) | (static_cast<uint32_t>((lo.b >> s0) & 1ull) << 1) |
+                                    (static_cast<uint32_t>((lo.b >> s1) & 1ull) << 2) | (static_cast<uint32_t>((lo.a >> s1) & 1ull) << 3) |
+                                    (static_cast<uint32_t>((hi.a >> s0) & 1ull) << 4) | (static_cast<uint32_t>((hi.b >> s0) & 1ull) << 5) |
+                                    (static_cast<uint32_t>((hi.b >> s1) & 1ull) << 6) | (static_cast<uint32_t>((hi.a >> s1) & 1ull) << 7);
+                const int j = j0 + r, k = k0 + m;
+                nv += __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0)));
+                if (i >= d.ghost) nt += MC_NTRI[cell_sub(f, d, level, i, j, k, cs)];
+            }
+            const long long row = static_cast<long long>(i) * d.c1 + j0 + cur;
+            if (nv) atomicAdd(vsums + row, nv);
+            if (nt) atomicAdd(tsums + row, nt);
+        }
+        lo = hi;
+    }
+}
+
 // weights 1 / (FLT_EPSILON + |v - level|) in float64 (== linear interpolation up to the epsilon)
 __device__ __forceinline__ void edge_vertex(const float* __restrict__ f, const Dims& d, double level, int i, int j,
                                             int k, int e, double* pos, float* nrm, float* val) {
@@ -259,93 +367,145 @@ __device__ __forceinline__ RowMasks load_masks(const float* __restrict__ f, cons
     return r;
 }
 
-// Pass 2: vertices of the listed rows + the records of their surface cells.  The capacity checks make the pass
-// safe to launch before the host knows the counts (pifu_mc_extract): nothing is written past cap_verts.
-__global__ void __launch_bounds__(SCAN_BLOCK) emit_vertices_kernel(const float* __restrict__ f, Dims d, double level, float lf,
-                                                                   int vec, const uint8_t* __restrict__ own,
-                                                                   const uint32_t* __restrict__ voffs,
-                                                                   uint2* __restrict__ cellinfo, double* __restrict__ verts,
-                                                                   float* __restrict__ normals, float* __restrict__ values,
-                                                                   long long cap_verts, const uint32_t* __restrict__ active,
-                                                                   const unsigned long long* __restrict__ n_active) {
-    __shared__ uint32_t todo[EMIT_LIST];
+// The emission passes work row by row.  A cell row of the common volumes needs far fewer than 256 threads (64 for
+// 512 cells), and a row's work is a chain of dependent steps (field loads -> scan -> list -> vertex arithmetic), so a
+// block is cut into TEAMS of T = nq rounded up to a power of two (32 .. 256) threads, one listed row per team and
+// iteration, synchronised by the team's own named barrier: 4 x more rows in flight per block at 512^3.
+struct Team {
+    int T, id, tid, teams;                 // threads per team, team of this thread, thread within the team, teams per block
+    __device__ __forceinline__ void sync() const {
+        if (T == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" :: "r"(id + 1), "r"(T) : "memory");
+    }
+};
+__device__ __forceinline__ Team make_team(int T) {
+    Team t;
+    t.T = T; t.id = threadIdx.x / T; t.tid = threadIdx.x - t.id * T; t.teams = SCAN_BLOCK / T;
+    return t;
+}
+// exclusive scan of one value per thread across a team; *total = the team's sum.  wsum: SCAN_BLOCK / 32 words of smem.
+__device__ __forceinline__ uint32_t team_exclusive_scan(const Team& tm, uint32_t v, uint32_t* total, uint32_t* wsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = warp_inclusive_scan(v, lane);
+    if (tm.T == 32) {
+        *total = __shfl_sync(0xffffffffu, inc, 31);
+        return inc - v;
+    }
+    tm.sync();                              // wsum of the previous call consumed
+    if (lane == 31) wsum[warp] = inc;
+    tm.sync();
+    const int w0 = (tm.id * tm.T) >> 5, wn = tm.T >> 5;
+    uint32_t before = 0, all = 0;
+    for (int w = 0; w < wn; ++w) {
+        const uint32_t x = wsum[w0 + w];
+        all += x;
+        if (w0 + w < warp) before += x;
+    }
+    *total = all;
+    return before + inc - v;
+}
+
+// Pass 2 (rows): per listed row, the cases and table rows of its cells recomputed from the field, team scans of the
+// vertices its cells own and of their triangles -> every surface cell's record {first vertex number, table row}, and
+// one JOB per vertex / triangle written at the vertex's / triangle's own final index:
+//   vertex job   cell id << 4 | edge                 triangle job   cell id << 16 | table row << 4 | triangle
+// The arithmetic then runs in two flat passes, one thread per vertex / per triangle, at full occupancy (the row pass
+// is a short chain: loads -> scan -> stores).  Capacity checks make every pass safe to launch before the host knows
+// the counts (pifu_mc_extract): nothing is written past cap_verts / cap_faces.
+__global__ void __launch_bounds__(SCAN_BLOCK) emit_rows_kernel(const float* __restrict__ f, Dims d, double level, float lf, int vec,
+                                                               int T, const uint8_t* __restrict__ own,
+                                                               const uint32_t* __restrict__ voffs, const uint32_t* __restrict__ toffs,
+                                                               uint2* __restrict__ cellinfo, unsigned long long* __restrict__ vjobs,
+                                                               unsigned long long* __restrict__ tjobs, long long cap_verts,
+                                                               long long cap_faces, const uint32_t* __restrict__ active,
+                                                               const unsigned long long* __restrict__ n_active) {
+    __shared__ uint32_t wsum[2][SCAN_BLOCK / 32];
+    const Team tm = make_team(T);
     const long long na = static_cast<long long>(*n_active);
-    const bool fits = static_cast<long long>(voffs[static_cast<long long>(d.c0) * d.c1]) <= cap_verts;
-    for (long long a = blockIdx.x; a < na; a += gridDim.x) {
+    const long long rows = static_cast<long long>(d.c0) * d.c1;
+    const bool vfits = static_cast<long long>(voffs[rows]) <= cap_verts, tfits = static_cast<long long>(toffs[rows]) <= cap_faces;
+    for (long long a = static_cast<long long>(blockIdx.x) * tm.teams + tm.id; a < na; a += static_cast<long long>(gridDim.x) * tm.teams) {
         const long long row = active[a];
         const int i = static_cast<int>(row / d.c1), j = static_cast<int>(row - static_cast<long long>(i) * d.c1);
-        uint32_t carry = voffs[row];
-        for (int q0 = 0; q0 < d.nq; q0 += SCAN_BLOCK) {
-            const int kq = q0 + threadIdx.x;
+        uint32_t vcarry = voffs[row], tcarry = toffs[row];
+        for (int q0 = 0; q0 < d.nq; q0 += tm.T) {
+            const int kq = q0 + tm.tid;
             const int k0 = kq * CPT;
-            uint32_t cases[CPT], nv = 0, nact = 0;
-            uint8_t cnt[CPT];
+            uint32_t nv = 0, nt = 0, actm = 0;
+            RowMasks r = {0u, 0u, 0u, 0u};
             if (kq < d.nq) {
-                const RowMasks r = load_masks(f, d, i, j, k0, lf, vec);
+                r = load_masks(f, d, i, j, k0, lf, vec);
                 const int zij = zero_mask(i + d.i0, j, 1);
 #pragma unroll
                 for (int m = 0; m < CPT; ++m) {
-                    cases[m] = 0u; cnt[m] = 0;
                     if (k0 + m >= d.c2) continue;
                     const uint32_t cs = case_of(r.m00, r.m01, r.m10, r.m11, m);
-                    cases[m] = cs;
-                    if (cs != 0u && cs != 255u) { cnt[m] = __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0))); nv += cnt[m]; ++nact; }
+                    if (cs != 0u && cs != 255u) { actm |= 1u << m; nv += __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0))); }
                 }
             }
-            uint32_t bt;
-            const uint32_t rel = block_exclusive_scan(nv, &bt);      // rank of this thread's first vertex inside the chunk
-            // The surface crosses a handful of the row's cells, so a few threads own all of its vertices (up to 12
-            // each, ~500 dependent cycles apiece).  They only list them - (thread, cell, edge) at the vertex's rank -
-            // and the whole block then computes one vertex per thread.
-            const bool listed = bt <= EMIT_LIST;
-            if (nact != 0u) {
-                uint32_t base = carry + rel, lr = rel;
+            // table rows of the surface cells (face tests on the ambiguous ones) before the scans: the triangle count needs them
+            uint16_t subs[CPT];
+#pragma unroll
+            for (int m = 0; m < CPT; ++m) {
+                subs[m] = 0xffffu;
+                if (actm & (1u << m)) {
+                    subs[m] = static_cast<uint16_t>(cell_sub(f, d, level, i, j, k0 + m, case_of(r.m00, r.m01, r.m10, r.m11, m)));
+                    if (i >= d.ghost) nt += MC_NTRI[subs[m]];
+                }
+            }
+            uint32_t bv, bt;
+            uint32_t vrel = team_exclusive_scan(tm, nv, &bv, wsum[0]);
+            uint32_t trel = team_exclusive_scan(tm, nt, &bt, wsum[1]);
+            if (actm != 0u) {
+                uint32_t vb = vcarry + vrel, tb = tcarry + trel;
+#pragma unroll
                 for (int m = 0; m < CPT; ++m) {
-                    const uint32_t cs = cases[m];
-                    if (cs == 0u || cs == 255u) continue;
+                    if (!(actm & (1u << m))) continue;
                     const int k = k0 + m;
-                    const uint32_t sub = cell_sub(f, d, level, i, j, k, cs);
-                    cellinfo[row * d.c2 + k] = make_uint2(base, sub);
+                    const uint32_t sub = subs[m];
+                    const unsigned long long cell = static_cast<unsigned long long>(row) * d.c2 + k;
+                    cellinfo[cell] = make_uint2(vb, sub);
                     const int zm = zero_mask(i + d.i0, j, k);
-                    uint32_t r = 0;
                     const int nvc = MC_NVERT[sub];
                     for (int q = 0; q < nvc; ++q) {
                         const int e = MC_VERTS[sub][q];
                         if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
-                        if (listed) {
-                            todo[lr + r] = (threadIdx.x << 8) | (static_cast<uint32_t>(m) << 4) | static_cast<uint32_t>(e);
-                        } else if (fits) {                           // more vertices than the list holds: in place
-                            double pos[3];
-                            float nrm[3], val;
-                            edge_vertex(f, d, level, i, j, k, e, pos, nrm, &val);
-                            const size_t o = static_cast<size_t>(base + r);
-                            verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
-                            if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
-                            if (values) values[o] = val;
-                        }
-                        ++r;
+                        if (vfits) vjobs[vb] = (cell << 4) | static_cast<unsigned long long>(e);
+                        ++vb;
                     }
-                    base += cnt[m];
-                    lr += cnt[m];
+                    if (i >= d.ghost) {
+                        const uint32_t n = MC_NTRI[sub];
+                        for (uint32_t t = 0; t < n; ++t, ++tb)
+                            if (tfits) tjobs[tb] = (cell << 16) | (static_cast<unsigned long long>(sub) << 4) | t;
+                    }
                 }
             }
-            __syncthreads();
-            if (listed && fits) {
-                for (uint32_t v = threadIdx.x; v < bt; v += SCAN_BLOCK) {
-                    const uint32_t t = todo[v];
-                    double pos[3];
-                    float nrm[3], val;
-                    edge_vertex(f, d, level, i, j, (q0 + static_cast<int>(t >> 8)) * CPT + static_cast<int>((t >> 4) & 15u),
-                                static_cast<int>(t & 15u), pos, nrm, &val);
-                    const size_t o = static_cast<size_t>(carry) + v;
-                    verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
-                    if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
-                    if (values) values[o] = val;
-                }
-            }
-            __syncthreads();                                         // todo is reused by the next chunk / row
-            carry += bt;
+            vcarry += bv;
+            tcarry += bt;
         }
+    }
+}
+
+// Pass 3: one thread per vertex.
+__global__ void __launch_bounds__(256) emit_vertices_kernel(const float* __restrict__ f, Dims d, double level,
+                                                            const uint32_t* __restrict__ voffs,
+                                                            const unsigned long long* __restrict__ vjobs, double* __restrict__ verts,
+                                                            float* __restrict__ normals, float* __restrict__ values, long long cap_verts) {
+    const long long nv = voffs[static_cast<long long>(d.c0) * d.c1];
+    if (nv > cap_verts) return;
+    for (long long v = blockIdx.x * 256LL + threadIdx.x; v < nv; v += static_cast<long long>(gridDim.x) * 256) {
+        const unsigned long long job = vjobs[v];
+        const unsigned long long cell = job >> 4;
+        const int k = static_cast<int>(cell % d.c2);
+        const unsigned long long row = cell / d.c2;
+        const int j = static_cast<int>(row % d.c1), i = static_cast<int>(row / d.c1);
+        double pos[3];
+        float nrm[3], val;
+        edge_vertex(f, d, level, i, j, k, static_cast<int>(job & 15u), pos, nrm, &val);
+        const size_t o = static_cast<size_t>(v);
+        verts[3 * o] = pos[0]; verts[3 * o + 1] = pos[1]; verts[3 * o + 2] = pos[2];
+        if (normals) { normals[3 * o] = nrm[0]; normals[3 * o + 1] = nrm[1]; normals[3 * o + 2] = nrm[2]; }
+        if (values) values[o] = val;
     }
 }
 
@@ -367,74 +527,22 @@ __device__ __forceinline__ int vertex_id(const Dims& d, const uint2* __restrict_
     return static_cast<int>(info.x) + r;
 }
 
-// Pass 3: faces, in cell order; vertex numbers come from the owning cells' records.
-__global__ void __launch_bounds__(SCAN_BLOCK) emit_faces_kernel(const float* __restrict__ f, Dims d, float lf, int vec,
-                                                                const uint2* __restrict__ cellinfo,
-                                                                const uint32_t* __restrict__ toffs, int* __restrict__ faces,
-                                                                long long cap_faces, const uint32_t* __restrict__ active,
-                                                                const unsigned long long* __restrict__ n_active) {
-    __shared__ uint32_t todo[EMIT_LIST];
-    const long long na = static_cast<long long>(*n_active);
-    if (static_cast<long long>(toffs[static_cast<long long>(d.c0) * d.c1]) > cap_faces) return;
-    for (long long a = blockIdx.x; a < na; a += gridDim.x) {
-        const long long row = active[a];
-        if (toffs[row + 1] == toffs[row]) continue;
-        const int i = static_cast<int>(row / d.c1), j = static_cast<int>(row - static_cast<long long>(i) * d.c1);
-        uint32_t carry = toffs[row];
-        for (int q0 = 0; q0 < d.nq; q0 += SCAN_BLOCK) {
-            const int kq = q0 + threadIdx.x;
-            const int k0 = kq * CPT;
-            uint32_t nt = 0;
-            uint16_t subs[CPT];
+// Pass 4: one thread per triangle; vertex numbers come from the owning cells' records.
+__global__ void __launch_bounds__(256) emit_faces_kernel(Dims d, const uint2* __restrict__ cellinfo, const uint32_t* __restrict__ toffs,
+                                                         const unsigned long long* __restrict__ tjobs, int* __restrict__ faces,
+                                                         long long cap_faces) {
+    const long long nt = toffs[static_cast<long long>(d.c0) * d.c1];
+    if (nt > cap_faces) return;
+    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < nt; t += static_cast<long long>(gridDim.x) * 256) {
+        const unsigned long long job = tjobs[t];
+        const unsigned long long cell = job >> 16;
+        const uint32_t sub = static_cast<uint32_t>(job >> 4) & 0xfffu, tri = static_cast<uint32_t>(job) & 15u;
+        const int k = static_cast<int>(cell % d.c2);
+        const unsigned long long row = cell / d.c2;
+        const int j = static_cast<int>(row % d.c1), i = static_cast<int>(row / d.c1);
+        const size_t o = static_cast<size_t>(t) * 3;
 #pragma unroll
-            for (int m = 0; m < CPT; ++m) subs[m] = 0xffffu;
-            if (kq < d.nq) {
-                const RowMasks r = load_masks(f, d, i, j, k0, lf, vec);
-#pragma unroll
-                for (int m = 0; m < CPT; ++m) {
-                    if (k0 + m >= d.c2) continue;
-                    const uint32_t cs = case_of(r.m00, r.m01, r.m10, r.m11, m);
-                    if (cs == 0u || cs == 255u) continue;
-                    subs[m] = static_cast<uint16_t>(cellinfo[row * d.c2 + k0 + m].y);
-                    nt += MC_NTRI[subs[m]];
-                }
-            }
-            uint32_t bt;
-            const uint32_t rel = block_exclusive_scan(nt, &bt);
-            // same redistribution as the vertices: list (thread, cell, triangle) at the triangle's rank, then one per thread
-            const bool listed = bt <= EMIT_LIST;
-            if (nt != 0u) {
-                uint32_t lr = rel;
-                for (int m = 0; m < CPT; ++m) {
-                    if (subs[m] == 0xffffu) continue;
-                    const uint32_t n = MC_NTRI[subs[m]];
-                    for (uint32_t t = 0; t < n; ++t) {
-                        if (listed) {
-                            todo[lr + t] = (threadIdx.x << 8) | (static_cast<uint32_t>(m) << 4) | t;
-                        } else {
-                            const size_t o = static_cast<size_t>(carry + lr + t) * 3;
-#pragma unroll
-                            for (int q = 0; q < 3; ++q)
-                                faces[o + q] = vertex_id(d, cellinfo, i, j, k0 + m, MC_TRIS[subs[m]][3 * t + q]);
-                        }
-                    }
-                    lr += n;
-                }
-            }
-            __syncthreads();
-            if (listed) {
-                for (uint32_t v = threadIdx.x; v < bt; v += SCAN_BLOCK) {
-                    const uint32_t e = todo[v];
-                    const int k = (q0 + static_cast<int>(e >> 8)) * CPT + static_cast<int>((e >> 4) & 15u), t = static_cast<int>(e & 15u);
-                    const uint32_t sub = cellinfo[row * d.c2 + k].y;
-                    const size_t o = (static_cast<size_t>(carry) + v) * 3;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cellinfo, i, j, k, MC_TRIS[sub][3 * t + q]);
-                }
-            }
-            __syncthreads();
-            carry += bt;
-        }
+        for (int q = 0; q < 3; ++q) faces[o + q] = vertex_id(d, cellinfo, i, j, k, MC_TRIS[sub][3 * tri + q]);
     }
 }
 
@@ -510,8 +618,17 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     PIFU_CUDA(cudaMemsetAsync(st->vsums, 0, static_cast<size_t>(st->rows + 1) * sizeof(uint32_t), s));
     PIFU_CUDA(cudaMemsetAsync(st->tsums, 0, static_cast<size_t>(st->rows + 1) * sizeof(uint32_t), s));
     PIFU_CUDA(cudaMemsetAsync(st->totals, 0, 4 * sizeof(unsigned long long), s));
-    classify_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(field, d, level_below(level), level,
-                                                                                vec_ok(field, n2), st->own, st->vsums, st->tsums);
+    static const bool per_thread = getenv("PIFU_MC_CLASSIFY") && atoi(getenv("PIFU_MC_CLASSIFY")) == 0;      // A/B measurements
+    const long long nkt = (d.c2 + 127) / 128, nbands = (d.c1 + WR - 1) / WR, nchunks = (d.c0 + WL - 1) / WL;
+    const long long warps = nkt * nbands * nchunks;
+    if (!per_thread && (warps + 7) / 8 <= 0x7fffffffLL) {
+        classify_warp_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(
+            field, d, level_below(level), level, vec_ok(field, n2), static_cast<int>(nkt), static_cast<int>(nbands),
+            static_cast<int>(nchunks), st->own, st->vsums, st->tsums);
+    } else {
+        classify_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(field, d, level_below(level), level,
+                                                                                    vec_ok(field, n2), st->own, st->vsums, st->tsums);
+    }
     device_exclusive_scan(st->vsums, st->tsums, st->rows, st->partials, st->totals, s);
     active_rows_kernel<<<static_cast<unsigned>((st->rows + SCAN_BLOCK - 1) / SCAN_BLOCK), SCAN_BLOCK, 0, s>>>(
         st->vsums, st->tsums, st->rows, st->active, st->totals + 3);
@@ -529,16 +646,25 @@ int mc_emit_async(pifu_ctx* c, double* verts, int* faces, float* normals, float*
                   long long cap_faces, cudaStream_t s) {
     McState* st = ctx_mc(c);
     const Dims d = make_dims(st);
-    const int grid = ctx_num_sms(c) * 4;
     const float lf = level_below(st->level);
     const int vec = vec_ok(st->field, st->n[2]);
-    emit_vertices_kernel<<<grid, SCAN_BLOCK, 0, s>>>(st->field, d, st->level, lf, vec, st->own, st->vsums, st->cellinfo, verts,
-                                                    normals, values, cap_verts, st->active, st->totals + 3);
-    if (faces)
-        emit_faces_kernel<<<grid, SCAN_BLOCK, 0, s>>>(st->field, d, lf, vec, st->cellinfo, st->tsums, faces, cap_faces, st->active,
-                                                     st->totals + 3);
+    if (grow(&st->vjobs, &st->cap_vjobs, cap_verts > 0 ? cap_verts : 1)) return -1;
+    if (grow(&st->tjobs, &st->cap_tjobs, cap_faces > 0 ? cap_faces : 1)) return -1;
+    int T = 32;                                  // team = threads of one cell row, a power of two in [32, 256]
+    while (T < d.nq && T < SCAN_BLOCK) T *= 2;
+    const int sms = ctx_num_sms(c);
+    emit_rows_kernel<<<sms * 6, SCAN_BLOCK, 0, s>>>(st->field, d, st->level, lf, vec, T, st->own, st->vsums, st->tsums, st->cellinfo,
+                                                   st->vjobs, st->tjobs, cap_verts, faces ? cap_faces : 0, st->active, st->totals + 3);
+    long long vb = (cap_verts + 255) / 256, fb = (cap_faces + 255) / 256;
+    if (vb > sms * 32LL) vb = sms * 32LL;
+    if (fb > sms * 32LL) fb = sms * 32LL;
+    if (vb > 0)
+        emit_vertices_kernel<<<static_cast<unsigned>(vb), 256, 0, s>>>(st->field, d, st->level, st->vsums, st->vjobs, verts, normals,
+                                                                      values, cap_verts);
+    if (faces && fb > 0)
+        emit_faces_kernel<<<static_cast<unsigned>(fb), 256, 0, s>>>(d, st->cellinfo, st->tsums, st->tjobs, faces, cap_faces);
     PIFU_CUDA(cudaGetLastError());
-    ctx_count_launch(c, faces ? 2 : 1);
+    ctx_count_launch(c, faces ? 3 : 2);
     return 0;
 }
 

@@ -366,6 +366,41 @@ class Engine:
                                 ("slab", int(i_global0), int(cell_layers)) + tuple(f.shape))
 
 
+    # ------------------------------------------------------------------ colours, cleaning
+    def sample_image(self, image, points, calib, perspective=False):
+        """image [C, H, W] (or [1, C, H, W]), points [3, n], calib [4, 4] -> [C, n] bilinear samples at the projected
+        points (`pifu_sample_image`): projection + `index()` of `reconstruction.py:110-116` in one kernel."""
+        img = image.detach().to(self.device, torch.float32)
+        img = img[0] if img.dim() == 4 else img
+        img = img.contiguous()
+        pts = points.detach().to(self.device, torch.float32)
+        if pts.stride(1) != 1:
+            pts = pts.contiguous()
+        n = pts.shape[1]
+        out = torch.empty((img.shape[0], n), device=self.device, dtype=torch.float32)
+        c16, _ = _calib16(calib)
+        _lib.check(self.lib.pifu_sample_image(ctypes.c_void_p(img.data_ptr()), img.shape[0], img.shape[1], img.shape[2],
+                                              ctypes.c_void_p(pts.data_ptr()), pts.stride(0), n, c16, int(bool(perspective)),
+                                              ctypes.c_void_p(out.data_ptr()), _stream(self.device_index)))
+        return out
+
+    def clean_mesh(self, verts, faces, colors=None, only_watertight=True):
+        """Largest component by extent along axis 0 (`pifu_mesh_clean`; `reconstruction.py:325-344`).
+        -> (verts [V', 3] f64, faces [F', 3] i32, colors [V', 3] f64 | None) on the device."""
+        v = verts.to(self.device, torch.float64).contiguous()
+        f = faces.to(self.device, torch.int32).contiguous()
+        c = colors.to(self.device, torch.float64).contiguous() if colors is not None else None
+        ov, of = torch.empty_like(v), torch.empty_like(f)
+        oc = torch.empty_like(c) if c is not None else None
+        counts = (ctypes.c_longlong * 2)()
+        _lib.check(self.lib.pifu_mesh_clean(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(c.data_ptr()) if c is not None else None,
+                                            ctypes.c_void_p(f.data_ptr()), v.shape[0], f.shape[0], int(bool(only_watertight)),
+                                            ctypes.c_void_p(ov.data_ptr()), ctypes.c_void_p(oc.data_ptr()) if oc is not None else None,
+                                            ctypes.c_void_p(of.data_ptr()), counts, _stream(self.device_index)))
+        nv, nf = int(counts[0]), int(counts[1])
+        return ov[:nv], of[:nf], (oc[:nv] if oc is not None else None)
+
+
 class _DevView:
     """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
 

@@ -238,3 +238,49 @@ def save_obj_mesh_with_color(mesh_path, verts, faces, colors):
     _lib.check(lib.pifu_write_obj(str(mesh_path).encode(), verts.ctypes.data_as(ctypes.c_void_p),
                                   colors.ctypes.data_as(ctypes.c_void_p), len(verts),
                                   faces.ctypes.data_as(ctypes.c_void_p), len(faces)))
+
+
+# ----------------------------------------------------------------------------- SURVEY 8(f) row 4
+def vertex_colors_from_image(net, image, verts, calib_tensor, device=None):
+    """Vertex colours of `gen_mesh_imgColor` (`reconstruction.py:110-116`): project the vertices with the net's
+    projection and the first view's calibration, sample the image bilinearly, map (-1, 1) -> (0, 1).
+    image [B, C, H, W] (first view used, like `image_tensor[:1]`), verts [V, 3] numpy/tensor -> [V, C] float32 numpy."""
+    device = torch.device(device) if device is not None else (image.device if image.is_cuda else torch.device("cuda"))
+    eng = get_engine(device)
+    pts = torch.as_tensor(np.ascontiguousarray(np.asarray(verts).T) if not torch.is_tensor(verts) else verts.T)
+    out = eng.sample_image(image[:1], pts.float(), calib_tensor[0], perspective=net.is_perspective)
+    return (out.T * 0.5 + 0.5).cpu().numpy()
+
+
+def clean_mesh(verts, faces, colors=None, device=None, only_watertight=True):
+    """The component `meshcleaning` keeps (`reconstruction.py:325-344`), on arrays: numpy in / numpy out."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    eng = get_engine(device)
+    v, f, c = eng.clean_mesh(torch.as_tensor(np.asarray(verts, dtype=np.float64)), torch.as_tensor(np.asarray(faces, dtype=np.int32)),
+                             torch.as_tensor(np.asarray(colors, dtype=np.float64)) if colors is not None else None, only_watertight)
+    return v.cpu().numpy(), f.cpu().numpy(), (c.cpu().numpy() if c is not None else None)
+
+
+def load_obj_mesh_with_color(mesh_path):
+    """Inverse of save_obj_mesh_with_color: -> (verts [V, 3], faces [F, 3] int32 0-based in the order they were GIVEN to
+    the writer (it stores f0, f2, f1), colors [V, 3] | None)."""
+    vs, fs = [], []
+    with open(mesh_path) as fh:
+        for line in fh:
+            if line.startswith("v "):
+                vs.append([float(x) for x in line.split()[1:]])
+            elif line.startswith("f "):
+                a, b, c = (int(x.split("/")[0]) - 1 for x in line.split()[1:4])
+                fs.append((a, c, b))
+    v = np.asarray(vs, dtype=np.float64).reshape(-1, 6 if vs and len(vs[0]) >= 6 else 3)
+    return v[:, :3], np.asarray(fs, dtype=np.int32).reshape(-1, 3), (v[:, 3:6] if v.shape[1] >= 6 else None)
+
+
+def meshcleaning(obj_path, device=None):
+    """`reconstruction.py:325-344` (file in, file out): keep the connected component of greatest extent along x.  The
+    component search runs on the device (`pifu_mesh_clean`); the file is rewritten by this package's OBJ writer (the
+    reference exports through trimesh, whose text layout is its own)."""
+    print(f"Processing mesh cleaning: {obj_path}")
+    verts, faces, colors = load_obj_mesh_with_color(obj_path)
+    v, f, c = clean_mesh(verts, faces, colors, device=device)
+    save_obj_mesh_with_color(obj_path, v, f, c if c is not None else np.zeros_like(v))
