@@ -378,7 +378,23 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3, cpu=None):
             tail()                                       # first call: lazy initialisations of the general-points path
             t0, t1, t2, nbytes = tail()
             d["gen_mesh_tail"] = {"vertex_normals_ms": (t1 - t0) * 1e3, "queries": 4 * len(mv), "obj_write_ms": (t2 - t1) * 1e3,
-                                  "obj_bytes": nbytes, "gen_mesh_total_ms": best + (t2 - t0) * 1e3}
+                                  "obj_bytes": nbytes, "gen_mesh_total_ms": best + (t2 - t0) * 1e3,
+                                  "normals_arithmetic": "split precision (finite differences at delta = 0.001)"}
+            # colours sampled from the 1024^2 image (gen_mesh_imgColor, reconstruction.py:110-116) and
+            # meshcleaning (reconstruction.py:325-344), host arrays in / host arrays out
+            img = torch.rand(1, 3, 1024, 1024, device=dev) * 2 - 1
+            for _ in range(2):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                colors = mesh_util.vertex_colors_from_image(netMR, img, mv, cal)
+                t1 = time.perf_counter()
+                try:
+                    cv, cf, _ = mesh_util.clean_mesh(mv, mf, colors, device=dev)
+                    kept = [len(cv), len(cf)]
+                except Exception as e:  # noqa: BLE001
+                    kept = "none (%s)" % (str(e)[:80],)
+                t2 = time.perf_counter()
+            d["postprocess"] = {"vertex_colors_ms": (t1 - t0) * 1e3, "meshcleaning_ms": (t2 - t1) * 1e3, "kept_verts_faces": kept}
         if mode == "octree" and cpu is not None:
             d["vs_cpu"] = field_vs_cpu(field, stats, cpu)
         if mode == "octree":

@@ -143,6 +143,21 @@ int pifu_octree_commit(pifu_ctx* ctx, const float* values_device, void* stream);
 int pifu_octree_commit64(pifu_ctx* ctx, const double* values_device, void* stream);
 int pifu_octree_export(pifu_ctx* ctx, double* sdf64, float* sdf32, void* stream);
 
+/* Slab form of the stepwise octree for a volume sharded along axis 0 (nothing to cite in the
+ * single-device reference beyond mesh_util.py:124-187).  The rank keeps the bookkeeping of planes
+ * [plane_begin, plane_end) of the R0-plane volume - its own planes [own_begin, own_end) plus a margin of twice the
+ * initial stride (R0 // init_resolution) on either side, clipped to the volume; all four are multiples of the initial
+ * stride (or R0).  pifu_octree_frontier then compacts the frontier of the OWN planes only (global lattice ids), and
+ * each level is closed with pifu_octree_commit_pairs: the (lattice id, value) pairs of every rank's frontier (any
+ * order; ids < 0 are padding); pairs outside [plane_begin, plane_end) are ignored.  No boundary plane is exchanged -
+ * what the cells beyond the margin would contribute cannot reach the own planes, nor the two planes either side of
+ * them that slab marching cubes reads (octree.cu).  pifu_octree_field32 gives the float32 field of the local planes
+ * (library-owned device memory, valid until the next begin): *plane_begin = global index of its first plane. */
+int pifu_octree_begin_slab(pifu_ctx* ctx, int R0, int R1, int R2, int init_resolution, double threshold, int plane_begin,
+                           int plane_end, int own_begin, int own_end, void* stream);
+int pifu_octree_commit_pairs(pifu_ctx* ctx, const long long* ids_device, const float* values_device, long long n, void* stream);
+int pifu_octree_field32(pifu_ctx* ctx, const float** field_device, int* plane_begin, int* planes);
+
 /* Marching cubes on a device float32 volume [n0][n1][n2] at `level` (strict v > level is
  * inside).  Replaces measure.marching_cubes_lewiner (call site mesh_util.py:84; third-party,
  * see DESIGN.md "parity unpinned").  Ambiguous faces are resolved by Lewiner's face test (the asymptotic decider);

@@ -51,10 +51,11 @@ bool ctx_normalised(pifu_ctx* c, int levels);      // a normalised MLP: every en
 int ctx_num_sms(pifu_ctx* c);
 void ctx_count_launch(pifu_ctx* c, int n);
 
-int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s, float* sdf32_target);
+int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s, float* sdf32_target,
+                 int lb, int le, int fb, int fe);      // le < 0: the whole volume
 int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s);
 const long long* octree_ids(pifu_ctx* c);
-int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStream_t s);
+int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStream_t s, const long long* pair_ids, long long n_pairs);
 int octree_export(pifu_ctx* c, double* sdf64, float* sdf32, cudaStream_t s);
 int octree_vals(pifu_ctx* c, long long n, float** out);
 

@@ -14,6 +14,14 @@
 //              kernel compacts them): the work follows the cells that fill, not the volume.
 // The field is kept in float64 exactly like the reference's `sdf`, so given identical
 // evaluated values the result is bit-identical to the reference loop.
+//
+// Slab form (multi-GPU): a rank keeps the bookkeeping of planes [lb, le) = its own planes [fb, fe)
+// plus a margin of 2 x the initial stride on either side, compacts the frontier of its OWN planes only, and commits
+// every evaluated (lattice id, value) pair that falls inside [lb, le) - its own and its neighbours', which reach it
+// with the all-gather of the evaluated values anyway.  No boundary plane is exchanged: a voxel's final state depends
+// on evaluated values and skip decisions at most (initial stride - 2) + ... planes away, so whatever the missing cells
+// beyond the margin would have contributed never reaches the own planes (bottom: planes [lb, lb + s0 - 2] end up
+// unreliable, top: [le - 2 s0 + 2, le); marching cubes needs [fb - 1, fe + 2), which stays clear of both).
 #include <vector>
 
 #include "../../include/pifu_b200.h"
@@ -24,7 +32,10 @@
 namespace pifu {
 
 struct OctreeState {
-    int R[3] = {0, 0, 0};
+    int R[3] = {0, 0, 0};              // the volume the bookkeeping runs on (slab form: planes [lb, le) of the global one)
+    int R0g = 0;                       // planes of the global volume
+    int lb = 0;                        // global index of local plane 0
+    int f0 = 0, f1 = 0;                // local planes whose frontier this rank compacts (slab form: its own; else all)
     int init_res = 0;
     double threshold = 0.05;
     int step = 0;
@@ -61,37 +72,16 @@ void octree_free(OctreeState* s) {
 
 namespace {
 
-// `notprocessed` (`mesh_util.py:134-135`): everything but the last plane of each axis.  One thread per 4 voxels
-// of a lattice row.
-__global__ void init_todo_kernel(uint8_t* __restrict__ todo, int R0, int R1, int R2, int quads) {
-    const long long n = static_cast<long long>(R0) * R1 * quads;
-    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (t >= n) return;
-    const int qk = static_cast<int>(t % quads);
-    const long long ij = t / quads;
-    const int j = static_cast<int>(ij % R1);
-    const int i = static_cast<int>(ij / R1);
-    const bool row_ok = i < R0 - 1 && j < R1 - 1;
-    const int k0 = 4 * qk;
-    const long long v0 = ij * R2 + k0;
-    uint32_t w = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (row_ok && k0 + q < R2 - 1) w |= 1u << (8 * q);
-    if ((R2 & 3) == 0) {
-        *reinterpret_cast<uint32_t*>(todo + v0) = w;
-    } else {
-        for (int q = 0; q < 4 && k0 + q < R2; ++q) todo[v0 + q] = (w >> (8 * q)) & 1u;
-    }
-}
-
 // The field only has to start at 0.0 where the octree never writes: the last plane of each axis (`:135`;
 // those planes stay 0.0 in the reference's result and can be read as cell corners when R - 1 is a multiple
 // of the stride).  Every other voxel is evaluated or filled before anything reads it: a level's corners are
 // stride-lattice points, each either processed earlier or in this level's frontier, and the last level
 // evaluates all that is left.
-__global__ void zero_last_planes_kernel(double* __restrict__ sdf, float* __restrict__ sdf32, int R0, int R1, int R2) {
-    const long long a = static_cast<long long>(R1) * R2, b = static_cast<long long>(R0) * R2, c = static_cast<long long>(R0) * R1;
+// The same planes are where `notprocessed` starts False (`:134-135`: everything but the last plane of each axis is True;
+// the rest of `todo` is set by one memset).
+__global__ void zero_last_planes_kernel(double* __restrict__ sdf, float* __restrict__ sdf32, uint8_t* __restrict__ todo, int R0, int R1,
+                                        int R2, int top) {
+    const long long a = top ? static_cast<long long>(R1) * R2 : 0, b = static_cast<long long>(R0) * R2, c = static_cast<long long>(R0) * R1;
     const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     long long v = -1;
     if (t < a) {
@@ -102,7 +92,7 @@ __global__ void zero_last_planes_kernel(double* __restrict__ sdf, float* __restr
     } else if (t < a + b + c) {
         v = (t - a - b) * R2 + (R2 - 1);
     }
-    if (v >= 0) { sdf[v] = 0.0; sdf32[v] = 0.f; }
+    if (v >= 0) { sdf[v] = 0.0; sdf32[v] = 0.f; todo[v] = 0; }
 }
 
 // candidate c of the stride lattice (n0 x n1 x n2 points) -> voxel id
@@ -159,7 +149,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) frontier_count_kernel(const uint8_
 __global__ void __launch_bounds__(SCAN_BLOCK) frontier_write_kernel(const uint8_t* __restrict__ todo, long long nthreads,
                                                                    int tpr, long long ncand, int n1, int n2, int step,
                                                                    int R1, int R2, const uint32_t* __restrict__ block_offs,
-                                                                   long long* __restrict__ ids) {
+                                                                   long long* __restrict__ ids, long long id_off) {
     if (block_offs[blockIdx.x + 1] == block_offs[blockIdx.x]) return;
     const long long t = blockIdx.x * static_cast<long long>(SCAN_BLOCK) + threadIdx.x;
     uint32_t bits = 0;
@@ -173,15 +163,17 @@ __global__ void __launch_bounds__(SCAN_BLOCK) frontier_write_kernel(const uint8_
     long long o = static_cast<long long>(block_offs[blockIdx.x]) + block_exclusive_scan(__popc(bits), &bt);
 #pragma unroll
     for (int m = 0; m < CAND_PT; ++m)
-        if (bits & (1u << m)) ids[o++] = vox0 + static_cast<long long>(m) * step;
+        if (bits & (1u << m)) ids[o++] = vox0 + static_cast<long long>(m) * step + id_off;
 }
 
 template <typename T>
 __global__ void commit_kernel(const T* __restrict__ vals, const long long* __restrict__ ids, long long n,
-                              double* __restrict__ sdf, float* __restrict__ sdf32, uint8_t* __restrict__ todo) {
+                              double* __restrict__ sdf, float* __restrict__ sdf32, uint8_t* __restrict__ todo,
+                              long long id_off, long long voxels) {
     const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (p >= n) return;
-    const long long v = ids[p];
+    const long long v = ids[p] - id_off;           // global lattice id -> voxel of the local volume
+    if (v < 0 || v >= voxels) return;              // slab form: a neighbour's point outside this rank's margin (or padding, id < 0)
     sdf[v] = static_cast<double>(vals[p]);       // the callable's values stored into the float64 field (`:148`)
     sdf32[v] = static_cast<float>(vals[p]);
     todo[v] = 0;
@@ -378,14 +370,27 @@ inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 }  // namespace
 
-int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s, float* sdf32_target) {
+int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double threshold, cudaStream_t s, float* sdf32_target,
+                 int lb, int le, int fb, int fe) {
     OctreeState*& st = ctx_octree(c);
     if (!st) st = new OctreeState();
     if (init_res <= 0 || R0 <= 0 || R1 <= 0 || R2 <= 0) { set_error("octree: bad resolution"); return -1; }
+    const int step0 = R0 / init_res;              // `mesh_util.py:138`: resolution[0] // init_resolution
+    if (le < 0) { lb = 0; le = R0; fb = 0; fe = R0; }            // whole volume
+    if (lb < 0 || le > R0 || lb >= le || fb < lb || fe > le || fb > fe ||
+        (step0 > 0 && (lb % step0 || fb % step0 || (le % step0 && le != R0) || (fe % step0 && fe != R0)))) {
+        set_error("octree: slab planes [%d, %d) / own planes [%d, %d) must nest and start on multiples of the initial stride %d",
+                  lb, le, fb, fe, step0);
+        return -1;
+    }
+    st->R0g = R0;
+    st->lb = lb;
+    st->f0 = fb - lb; st->f1 = fe - lb;
+    R0 = le - lb;                                 // from here on: the local volume
     st->R[0] = R0; st->R[1] = R1; st->R[2] = R2;
     st->init_res = init_res;
     st->threshold = threshold;
-    st->step = R0 / init_res;                     // `mesh_util.py:138`: resolution[0] // init_resolution
+    st->step = step0;
     st->voxels = static_cast<long long>(R0) * R1 * R2;
     long long capv = st->cap_vox;
     if (grow(&st->sdf, &capv, st->voxels)) return -1;
@@ -399,11 +404,10 @@ int octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_res, double thres
         st->sdf32 = st->sdf32_own;
     }
     if (!st->total_dev) PIFU_CUDA(cudaMalloc(&st->total_dev, 2 * sizeof(unsigned long long)));
-    const int quads = ceil_div(R2, 4);
-    init_todo_kernel<<<ceil_div(static_cast<long long>(R0) * R1 * quads, 256), 256, 0, s>>>(st->todo, R0, R1, R2, quads);
+    PIFU_CUDA(cudaMemsetAsync(st->todo, 1, static_cast<size_t>(st->voxels), s));
     if (st->step > 0) {
         const long long planes = static_cast<long long>(R1) * R2 + static_cast<long long>(R0) * R2 + static_cast<long long>(R0) * R1;
-        zero_last_planes_kernel<<<ceil_div(planes, 256), 256, 0, s>>>(st->sdf, st->sdf32, R0, R1, R2);
+        zero_last_planes_kernel<<<ceil_div(planes, 256), 256, 0, s>>>(st->sdf, st->sdf32, st->todo, R0, R1, R2, le == st->R0g ? 1 : 0);
     } else {
         // resolution < init_resolution: the reference's loop never runs and the field stays all zero (`:138-140`)
         PIFU_CUDA(cudaMemsetAsync(st->sdf, 0, static_cast<size_t>(st->voxels) * sizeof(double), s));
@@ -421,14 +425,19 @@ int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s) {
     if (!st || !st->sdf) { set_error("octree: begin was not called"); return -1; }
     if (st->step <= 0) { *n = 0; st->frontier = 0; return 0; }
     const int step = st->step;
-    const int n0 = ceil_div(st->R[0], step), n1 = ceil_div(st->R[1], step), n2 = ceil_div(st->R[2], step);
+    // candidates: the stride lattice of the planes [f0, f1) this rank compacts (all of them unless slab form)
+    const long long plane = static_cast<long long>(st->R[1]) * st->R[2];
+    const uint8_t* todo = st->todo + st->f0 * plane;
+    const long long id_off = (static_cast<long long>(st->lb) + st->f0) * plane;
+    if (st->f1 <= st->f0) { *n = 0; st->frontier = 0; return 0; }
+    const int n0 = ceil_div(st->f1 - st->f0, step), n1 = ceil_div(st->R[1], step), n2 = ceil_div(st->R[2], step);
     const long long ncand = static_cast<long long>(n0) * n1 * n2;
     const int tpr = ceil_div(n2, CAND_PT);                       // threads per lattice row
     const long long nthreads = static_cast<long long>(n0) * n1 * tpr;
     const int blocks = ceil_div(nthreads, SCAN_BLOCK);
     if (grow(&st->block_sums, &st->cap_blocks, blocks + 1)) return -1;
     if (grow(&st->partials, &st->cap_partials, scan_partials_needed(blocks))) return -1;
-    frontier_count_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(st->todo, nthreads, tpr, ncand, n1, n2, step, st->R[1], st->R[2],
+    frontier_count_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(todo, nthreads, tpr, ncand, n1, n2, step, st->R[1], st->R[2],
                                                        st->block_sums);
     device_exclusive_scan(st->block_sums, nullptr, blocks, st->partials, st->total_dev, s);
     PIFU_CUDA(cudaGetLastError());
@@ -437,8 +446,8 @@ int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s) {
     PIFU_CUDA(cudaStreamSynchronize(s));
     if (grow(&st->ids, &st->cap_ids, static_cast<long long>(total))) return -1;
     if (total)
-        frontier_write_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(st->todo, nthreads, tpr, ncand, n1, n2, step, st->R[1], st->R[2],
-                                                           st->block_sums, st->ids);
+        frontier_write_kernel<<<blocks, SCAN_BLOCK, 0, s>>>(todo, nthreads, tpr, ncand, n1, n2, step, st->R[1], st->R[2],
+                                                           st->block_sums, st->ids, id_off);
     PIFU_CUDA(cudaGetLastError());
     ctx_count_launch(c, 5);
     st->frontier = static_cast<long long>(total);
@@ -449,15 +458,20 @@ int octree_frontier(pifu_ctx* c, long long* n, cudaStream_t s) {
 const long long* octree_ids(pifu_ctx* c) { return ctx_octree(c) ? ctx_octree(c)->ids : nullptr; }
 
 // Scatter the frontier's occupancies, then (step > 1) skip test + fill, then halve the stride.
-int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStream_t s) {
+// pair_ids == null: `vals` are the values of this rank's own frontier, in frontier order; else `n_pairs` (lattice id,
+// value) pairs from any ranks (slab form): those inside the local volume are stored, the others ignored
+int octree_commit(pifu_ctx* c, const float* vals, const double* vals64, cudaStream_t s, const long long* pair_ids, long long n_pairs) {
     OctreeState* st = ctx_octree(c);
     if (!st || st->step <= 0) { set_error("octree: nothing to commit"); return -1; }
-    if (st->frontier) {
-        if (!vals && !vals64) { set_error("octree: null values for a frontier of %lld points", st->frontier); return -1; }
+    const long long id_off = static_cast<long long>(st->lb) * st->R[1] * st->R[2];
+    const long long* ids = pair_ids ? pair_ids : st->ids;
+    const long long n = pair_ids ? n_pairs : st->frontier;
+    if (n) {
+        if (!vals && !vals64) { set_error("octree: null values for %lld points", n); return -1; }
         if (vals64)
-            commit_kernel<double><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals64, st->ids, st->frontier, st->sdf, st->sdf32, st->todo);
+            commit_kernel<double><<<ceil_div(n, 256), 256, 0, s>>>(vals64, ids, n, st->sdf, st->sdf32, st->todo, id_off, st->voxels);
         else
-            commit_kernel<float><<<ceil_div(st->frontier, 256), 256, 0, s>>>(vals, st->ids, st->frontier, st->sdf, st->sdf32, st->todo);
+            commit_kernel<float><<<ceil_div(n, 256), 256, 0, s>>>(vals, ids, n, st->sdf, st->sdf32, st->todo, id_off, st->voxels);
         ctx_count_launch(c, 1);
     }
     const int step = st->step;
@@ -526,7 +540,7 @@ extern "C" {
 
 int pifu_octree_begin(pifu_ctx* c, int R0, int R1, int R2, int init_resolution, double threshold, void* stream) {
     if (!c) { set_error("null context"); return -1; }
-    return octree_begin(c, R0, R1, R2, init_resolution, threshold, static_cast<cudaStream_t>(stream), nullptr);
+    return octree_begin(c, R0, R1, R2, init_resolution, threshold, static_cast<cudaStream_t>(stream), nullptr, 0, -1, 0, 0);
 }
 
 int pifu_octree_frontier(pifu_ctx* c, long long* n, const long long** ids, int* step, void* stream) {
@@ -540,12 +554,35 @@ int pifu_octree_frontier(pifu_ctx* c, long long* n, const long long** ids, int* 
 
 int pifu_octree_commit(pifu_ctx* c, const float* vals, void* stream) {
     if (!c) { set_error("null context"); return -1; }
-    return octree_commit(c, vals, nullptr, static_cast<cudaStream_t>(stream));
+    return octree_commit(c, vals, nullptr, static_cast<cudaStream_t>(stream), nullptr, 0);
+}
+
+int pifu_octree_begin_slab(pifu_ctx* c, int R0, int R1, int R2, int init_resolution, double threshold, int plane_begin,
+                           int plane_end, int own_begin, int own_end, void* stream) {
+    if (!c) { set_error("null context"); return -1; }
+    if (plane_end < 0) { set_error("octree: bad slab"); return -1; }
+    return octree_begin(c, R0, R1, R2, init_resolution, threshold, static_cast<cudaStream_t>(stream), nullptr, plane_begin, plane_end,
+                        own_begin, own_end);
+}
+
+int pifu_octree_commit_pairs(pifu_ctx* c, const long long* ids, const float* values, long long n, void* stream) {
+    if (!c || (n > 0 && (!ids || !values)) || n < 0) { set_error("bad arguments to pifu_octree_commit_pairs"); return -1; }
+    static const long long none = -1;
+    return octree_commit(c, values, nullptr, static_cast<cudaStream_t>(stream), n > 0 ? ids : &none, n);
+}
+
+int pifu_octree_field32(pifu_ctx* c, const float** field, int* plane_begin, int* planes) {
+    OctreeState* st = c ? ctx_octree(c) : nullptr;
+    if (!st || !st->sdf32 || !field) { set_error("octree: no field"); return -1; }
+    *field = st->sdf32;
+    if (plane_begin) *plane_begin = st->lb;
+    if (planes) *planes = st->R[0];
+    return 0;
 }
 
 int pifu_octree_commit64(pifu_ctx* c, const double* vals, void* stream) {
     if (!c) { set_error("null context"); return -1; }
-    return octree_commit(c, nullptr, vals, static_cast<cudaStream_t>(stream));
+    return octree_commit(c, nullptr, vals, static_cast<cudaStream_t>(stream), nullptr, 0);
 }
 
 int pifu_octree_export(pifu_ctx* c, double* sdf64, float* sdf32, void* stream) {
@@ -564,7 +601,7 @@ int pifu_eval_grid_octree(pifu_ctx* c, int levels, int R0, int R1, int R2, int i
         return -1;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (octree_begin(c, R0, R1, R2, init_resolution, threshold, s, sdf32)) return -1;
+    if (octree_begin(c, R0, R1, R2, init_resolution, threshold, s, sdf32, 0, -1, 0, 0)) return -1;
     int lvl = 0;
     for (;;) {
         OctreeState* st = ctx_octree(c);
@@ -577,7 +614,7 @@ int pifu_eval_grid_octree(pifu_ctx* c, int levels, int R0, int R1, int R2, int i
             if (octree_vals(c, n, &vals)) return -1;
             if (eval_ids(c, levels, R0, R1, R2, octree_ids(c), n, calib, calib_inv, vals, s)) return -1;
         }
-        if (octree_commit(c, vals, nullptr, s)) return -1;
+        if (octree_commit(c, vals, nullptr, s, nullptr, 0)) return -1;
         ++lvl;
     }
     for (; evaluated_per_level && lvl < max_levels; ++lvl) evaluated_per_level[lvl] = -1;

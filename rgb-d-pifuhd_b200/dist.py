@@ -4,10 +4,13 @@ NCCL is used only to gather occupancy values.
 
 * dense grid: contiguous id ranges = slabs along volume axis 0 (the lattice id is
   (i*R1 + j)*R2 + k), gathered to one rank;
-* octree: every rank runs the (cheap, deterministic) frontier compaction / skip / fill
-  bookkeeping on the full field, the level's frontier is cut into equal shares for the MLP
-  evaluation - better balanced than slabs because the frontier hugs the surface - and the
-  shares are all-gathered so all replicas stay bit-identical.
+* octree, mesh path (`sharded_mesh`): the bookkeeping is sharded by slab too.  A rank keeps its own planes plus a
+  margin of twice the initial stride, compacts the frontier of its own planes, the ranks all-gather the frontier ids,
+  evaluate equal shares of the concatenated list (better balanced than slabs - the frontier hugs the surface),
+  all-gather the values, and every rank commits the pairs that fall inside its planes.  The margin makes any
+  boundary-plane exchange unnecessary (octree.cu) and already holds the two halo planes slab marching cubes reads;
+* octree, field path (`sharded_eval_grid_octree`, when a caller wants the whole field on one rank): every rank runs
+  the bookkeeping on the full field and only the MLP evaluation is split.
 
 The helpers are backend-agnostic (gloo on CPU in the tests, NCCL on the box)."""
 import torch
@@ -163,6 +166,67 @@ def sharded_eval_grid_octree(eng, levels, res, calib, init_resolution=64, thresh
     return sdf32 if (dst is None or r == dst) else None
 
 
+def octree_slab_planes(res, init_resolution, W, r):
+    """(own_begin, own_end, plane_begin, plane_end) of rank r: own planes are whole multiples of the initial stride, the
+    bookkeeping margin is twice that stride on either side (octree.cu)."""
+    s0 = max(res // init_resolution, 1)
+    pb, pe = shard_bounds(res, W, r, align=s0)
+    return pb, pe, max(0, pb - 2 * s0), min(res, pe + 2 * s0)
+
+
+def sharded_octree_slab(eng, levels, res, calib, init_resolution=64, threshold=0.05, group=None, stats=None,
+                        evaluate=None):
+    """Slab-sharded device octree.  Returns (field, plane_begin, own_begin, own_end): the float32 field of this rank's
+    planes [plane_begin, plane_begin + field.shape[0]) - valid on [own_begin - 1, own_end + 2) - or field None for a
+    rank that owns no plane."""
+    W, r = world_size(group), rank(group)
+    if evaluate is None:
+        def evaluate(ids):
+            return eng.eval_lattice_ids(levels, res, ids, calib)
+    pb, pe, lb, le = octree_slab_planes(res, init_resolution, W, r)
+    mine = pe > pb
+    dev = eng.device
+    if mine:
+        eng.octree_begin_slab(res, init_resolution, threshold, lb, le, pb, pe)
+    step = res // init_resolution
+    while step > 0:                                   # every rank walks the same levels, in lock step
+        ids = eng.octree_frontier()[1] if mine else torch.empty(0, device=dev, dtype=torch.int64)
+        n = int(ids.numel())
+        cnt = torch.tensor([n], device=dev, dtype=torch.int64)
+        allc = torch.empty(W, device=dev, dtype=torch.int64)
+        if W > 1:
+            dist.all_gather_into_tensor(allc, cnt, group=group)
+        else:
+            allc = cnt
+        counts = [int(x) for x in allc.tolist()]
+        total = sum(counts)
+        if stats is not None:
+            stats.append(total)
+        if total:
+            per = max(counts)
+            if W > 1:
+                pad = torch.full((per,), -1, device=dev, dtype=torch.int64)
+                pad[:n] = ids
+                buf = torch.empty(W * per, device=dev, dtype=torch.int64)
+                dist.all_gather_into_tensor(buf, pad, group=group)
+                flat = torch.cat([buf[q * per:q * per + counts[q]] for q in range(W)])
+            else:
+                flat = ids
+            b, e = shard_bounds(total, W, r)
+            share = evaluate(flat[b:e]) if e > b else torch.empty(0, device=dev, dtype=torch.float32)
+            vals = gather_concat(share, total, shard_bounds(total, W, 0)[1], group=group, dst=None)
+        else:
+            flat = torch.empty(0, device=dev, dtype=torch.int64)
+            vals = torch.empty(0, device=dev, dtype=torch.float32)
+        if mine:
+            eng.octree_commit_pairs(flat, vals)
+        step //= 2
+    if not mine:
+        return None, lb, pb, pe
+    field, first = eng.octree_field32()
+    return field, first, pb, pe
+
+
 def sharded_mesh(eng, levels, res, calib, use_octree, level=0.5, init_resolution=64, threshold=0.05,
                  group=None, dst=0, stats=None):
     """Field + iso-surface of a res^3 lattice over all ranks (north_star: z-slab sharding, NCCL only
@@ -182,7 +246,16 @@ def sharded_mesh(eng, levels, res, calib, use_octree, level=0.5, init_resolution
             if (eq - bq) // plane < 2:
                 raise ValueError("a %d^3 lattice cut over %d ranks leaves rank %d fewer than the two planes slab marching "
                                  "cubes needs" % (res, W, q))
-    if use_octree:
+    if use_octree and res // init_resolution > 0:
+        field, first, pb, pe = sharded_octree_slab(eng, levels, res, calib, init_resolution, threshold, group=group,
+                                                   stats=stats)
+
+        def planes(lo, hi):
+            if field is None:
+                return torch.empty((0, res, res), device=eng.device, dtype=torch.float32)
+            return field[lo - first:hi - first]
+    elif use_octree:
+        # resolution < init_resolution: the reference's loop never runs, the field is all zero (`mesh_util.py:138`)
         field = sharded_eval_grid_octree(eng, levels, res, calib, init_resolution, threshold, group=group,
                                          dst=None, stats=stats)
 

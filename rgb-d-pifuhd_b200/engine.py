@@ -279,6 +279,30 @@ class Engine:
         _lib.check(self.lib.pifu_octree_begin(self.h, R0, R1, R2, int(init_resolution), float(threshold),
                                               _stream(self.device_index)))
 
+    def octree_begin_slab(self, res, init_resolution, threshold, plane_begin, plane_end, own_begin, own_end):
+        """Slab form (multi-GPU): bookkeeping of planes [plane_begin, plane_end), frontier of [own_begin, own_end)."""
+        R0, R1, R2 = (res, res, res) if np.isscalar(res) else res
+        self._oct_res = (plane_end - plane_begin, R1, R2)
+        _lib.check(self.lib.pifu_octree_begin_slab(self.h, R0, R1, R2, int(init_resolution), float(threshold),
+                                                   int(plane_begin), int(plane_end), int(own_begin), int(own_end),
+                                                   _stream(self.device_index)))
+
+    def octree_commit_pairs(self, ids, vals):
+        """(lattice id, value) pairs of all ranks' frontiers; those outside this rank's planes are ignored."""
+        ids = ids.to(self.device, torch.int64).contiguous()
+        vals = vals.to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.pifu_octree_commit_pairs(self.h, ctypes.c_void_p(ids.data_ptr()) if ids.numel() else None,
+                                                     ctypes.c_void_p(vals.data_ptr()) if vals.numel() else None,
+                                                     ids.numel(), _stream(self.device_index)))
+
+    def octree_field32(self):
+        """-> (float32 [planes, R1, R2] view of the library's field, global index of its first plane)."""
+        ptr, pb, n = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.lib.pifu_octree_field32(self.h, ctypes.byref(ptr), ctypes.byref(pb), ctypes.byref(n)))
+        _, R1, R2 = self._oct_res
+        t = torch.as_tensor(_DevView(ptr.value, n.value * R1 * R2, "<f4"), device=self.device)
+        return t.view(n.value, R1, R2), pb.value
+
     def octree_frontier(self):
         """-> (step, ids) with ids a device int64 view of this level's lattice ids; step 0 = done."""
         n = ctypes.c_longlong()

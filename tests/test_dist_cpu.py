@@ -52,6 +52,9 @@ class FakeEngine:
     def octree_commit(self, vals):
         self.sdf[self.test] = vals.numpy().astype(np.float64)
         self.todo[self.test] = False
+        self._skip_fill()
+
+    def _skip_fill(self):
         s = self.step
         if s > 1:
             v = self.sdf[::s, ::s, ::s]
@@ -124,16 +127,64 @@ def _oracle_slab(field, level, i0, g0, layers, ghost):
 
 
 class FakeMeshEngine(FakeEngine):
+    """+ the slab form of the device octree (octree.cu), restated in numpy on the local planes [lb, le): the global
+    volume's last plane is never processed, the frontier covers the own planes only and carries global lattice ids,
+    and a commit stores whichever (id, value) pairs fall inside the local planes."""
     marching_cubes_slab = staticmethod(_oracle_slab)
 
     def eval_lattice_ids(self, levels, res, ids, calib):
         return self.fn(ids)
 
+    def octree_begin_slab(self, res, init_resolution, threshold, lb, le, pb, pe):
+        from oracle import pifu_oracle
+        self.lb, self.own = lb, (pb - lb, pe - lb)
+        self.sdf = np.zeros((le - lb, res, res))
+        self.todo = np.zeros((le - lb, res, res), bool)
+        self.todo[:, :-1, :-1] = True
+        if le == res:
+            self.todo[-1] = False
+        self.lat = np.zeros((le - lb, res, res), bool)
+        self.step, self.thr, self.mu = res // init_resolution, threshold, pifu_oracle
+        self.slab = True
+
+    def octree_frontier(self):
+        if not getattr(self, "slab", False):
+            return super().octree_frontier()
+        if self.step <= 0:
+            return 0, torch.empty(0, dtype=torch.int64)
+        self.lat[::self.step, ::self.step, ::self.step] = True
+        test = self.lat & self.todo
+        test[:self.own[0]] = False
+        test[self.own[1]:] = False
+        return self.step, torch.from_numpy(np.flatnonzero(test) + self.lb * self.res * self.res)
+
+    def octree_commit_pairs(self, ids, vals):
+        v = ids.numpy() - self.lb * self.res * self.res
+        keep = (v >= 0) & (v < self.sdf.size)
+        self.sdf.reshape(-1)[v[keep]] = vals.numpy()[keep].astype(np.float64)
+        self.todo.reshape(-1)[v[keep]] = False
+        self._skip_fill()
+
+    def octree_field32(self):
+        return torch.from_numpy(self.sdf.astype(np.float32)), self.lb
+
+
+def _ripple(res):
+    """A field whose skip decisions change from cell to cell (thin sheets, saddles): the slab margins are exercised."""
+    def fn(ids):
+        k = ids % res
+        j = (ids // res) % res
+        i = ids // (res * res)
+        x, y, z = (i.double() / res * 2 - 1), (j.double() / res * 2 - 1), (k.double() / res * 2 - 1)
+        v = 0.5 + 0.35 * torch.sin(5.1 * x + 1.3 * y * z) * torch.cos(3.7 * y - 2.2 * z) + 0.2 * (x * y - z * z)
+        return torch.clamp(v, 0, 1).float()
+    return fn
+
 
 def _mesh_worker(rank, world, port, out, res, flat):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    fn = (lambda ids: torch.full((ids.numel(),), 0.25)) if flat else _field(res)
+    fn = (lambda ids: torch.full((ids.numel(),), 0.25)) if flat is True else (_ripple(res) if flat == "ripple" else _field(res))
     eng = FakeMeshEngine(res, fn)
     got = {}
     for mode in ("dense", "octree"):
@@ -149,16 +200,17 @@ def _mesh_worker(rank, world, port, out, res, flat):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,res", [(2, 32), (3, 24)])
-def test_sharded_mesh_equals_whole_volume(tmp_path, world, res):
+@pytest.mark.parametrize("world,res,kind", [(2, 32, False), (3, 24, False), (4, 64, False), (4, 64, "ripple"), (3, 48, "ripple")])
+def test_sharded_mesh_equals_whole_volume(tmp_path, world, res, kind):
     """Slab-by-slab extraction + fragment gather (ghost layer, halo planes, vertex renumbering)
-    gives bit for bit the mesh of a sequential traversal of the whole volume."""
+    gives bit for bit the mesh of a sequential traversal of the whole volume - for the dense field and for the
+    slab-sharded octree (own planes + margin, no boundary exchange: `dist.sharded_octree_slab`)."""
     from oracle import mc_oracle
     from pifu_b200 import mesh_util
     out = str(tmp_path / "mesh.pt")
-    mp.spawn(_mesh_worker, args=(world, 29573 + world, out, res, False), nprocs=world, join=True)
+    mp.spawn(_mesh_worker, args=(world, 29573 + world + (7 if kind else 0), out, res, kind), nprocs=world, join=True)
     got = torch.load(out)
-    fn = _field(res)
+    fn = _ripple(res) if kind == "ripple" else _field(res)
     dense = fn(torch.arange(res ** 3)).view(res, res, res).numpy()
     coords = np.indices((res,) * 3).astype(np.float64)
     octo = orc.eval_grid_octree(
