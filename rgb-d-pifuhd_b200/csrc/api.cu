@@ -253,7 +253,24 @@ int run_layers(pifu_ctx* c, Level& L, bool coarse, int first, int last, int m_ti
         g.explicit_wkb = 1;
         g.nseg = 0;
         g.num_kb = 0;
-        for (int term = 0; term < 3; ++term) {
+        // product path: the residual images ride in the same pipeline stage as their images (4 block loads per 3
+        // products, gemm_tc.cu SPLIT); the K-concatenated form below (6 loads) serves the cross-check kernels
+        static const bool staged_env = !(getenv("PIFU_SPLIT_STAGED") && atoi(getenv("PIFU_SPLIT_STAGED")) == 0);
+        const bool staged = prec != 0 && staged_env && c->gemm_impl == PIFU_GEMM_TCGEN05;
+        if (staged) {
+            int off = 0;
+            for (int k = 0; k < ns; ++k) {
+                g.seg[k] = make_seg(c, l.segs[k], false);
+                g.seg_lo[k] = c->bufs[l.segs[k].buf].ptr_lo;
+                g.seg_wkb[k] = off;
+                off += l.segs[k].nkb;
+            }
+            g.nseg = ns;
+            g.num_kb = l.num_kb;
+            g.split = prec;
+            g.w_lo_off = l.num_kb;
+        }
+        for (int term = 0; term < 3 && !staged; ++term) {
             if ((term == 1 && !xlo) || (term == 2 && !wlo)) continue;
             int off = 0;
             for (int k = 0; k < ns; ++k) {

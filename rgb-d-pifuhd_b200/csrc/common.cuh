@@ -51,6 +51,13 @@ struct GemmArgs {
     int out_kb_stride;      // k-blocks per m-tile in out
     int out_kb_off;
     uint8_t* out_lo;        // split precision: fp16(x - fp16(x)) in the layout of `out` (null = single fp16 image)
+    // split precision, staged form (gemm_tc.cu SPLIT): the segments are listed ONCE; `split` selects the residual
+    // products (bit 0: x_lo W_hi, bit 1: x_hi W_lo), seg_lo[s] is the residual image of segment s and the residual
+    // weights of k-block kb sit at k-block w_lo_off + kb of `w`.  A stage then holds {x_hi, x_lo, W_hi, W_lo} of one
+    // k-block and feeds up to three MMA groups: 4 block loads per 3 products instead of 6.
+    int split;
+    int w_lo_off;
+    const uint8_t* seg_lo[MAX_SEGS];
     int leaky;              // apply leaky_relu(0.01)
     // fused last layer (Conv1d to 1 channel + sigmoid), only when N == BN:
     const float* head_w;    // [N + 64 * sum(head_seg nkb)] fp32; null = no head

@@ -26,11 +26,14 @@ namespace {
 // tcgen05.mma.cta_group::2 with M = 256 (each CTA owns 128 points and their accumulators) and
 // each CTA stages only half of the weight block, so a weight byte fetched from L2 serves 256
 // points instead of 128.
-template <int BN, int CL>
+// SPLIT: a stage holds the fp16 image AND the residual image of the activation block and of the weight block
+// (split precision, common.cuh GemmArgs::split): {x_hi, x_lo, W_hi, W_lo} feed x_hi W_hi + x_lo W_hi + x_hi W_lo.
+template <int BN, int CL, bool SPLIT = false>
 struct Cfg {
     static constexpr int BBLOCK_BYTES = BN * ROW_BYTES;            // whole weight block in HBM
     static constexpr int BLOAD_BYTES = BBLOCK_BYTES / CL;          // rows this CTA stages
-    static constexpr int STAGE_BYTES = ABLOCK_BYTES + BLOAD_BYTES;
+    static constexpr int IMAGES = SPLIT ? 2 : 1;
+    static constexpr int STAGE_BYTES = IMAGES * (ABLOCK_BYTES + BLOAD_BYTES);
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int OUT_BYTES = 2 * ABLOCK_BYTES;     // staging of 128 output columns (2 k-blocks)
@@ -59,14 +62,16 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
-    using C = Cfg<BN, CL>;
+    using C = Cfg<BN, CL, SPLIT>;
     const uint32_t cta_rank = CL == 1 ? 0u : ptx::cluster_ctarank();
     const bool leader = cta_rank == 0;
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzle-128B operands need 1024-byte alignment
+    // SPLIT: the residual images follow the images, stage by stage: sA[stage][hi | lo], sB[stage][hi | lo]
+    constexpr int A_STAGE = C::IMAGES * ABLOCK_BYTES, B_STAGE = C::IMAGES * C::BLOAD_BYTES;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + C::STAGES * ABLOCK_BYTES;
+    uint8_t* sB = smem + C::STAGES * A_STAGE;
     uint8_t* sOut = smem + C::STAGES * C::STAGE_BYTES;
     float* s_bias = reinterpret_cast<float*>(sOut + C::OUT_BYTES);
     float* s_head = s_bias + BN;
@@ -127,16 +132,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const uint8_t* ab = seg.base +
                         (static_cast<size_t>(mt) * seg.kb_stride + seg.kb_off) * ABLOCK_BYTES;
                     if (a.explicit_wkb) kbg = a.seg_wkb[sg];      // split precision: hi and lo images share weight blocks
+                    const uint8_t* ab_lo = nullptr;
+                    if constexpr (SPLIT)
+                        ab_lo = a.seg_lo[sg] + (static_cast<size_t>(mt) * seg.kb_stride + seg.kb_off) * ABLOCK_BYTES;
                     for (int kb = 0; kb < seg.nkb; ++kb, ++kbg) {
                         // leader of a pair: its loads land on pfull, the barrier the peer's forwarder also
                         // arrives on, so the MMA warp waits on ONE barrier per stage
                         uint64_t* fb = (CL == 2 && leader) ? &pfull[stage] : &full[stage];
                         ptx::mbar_wait(&empty[stage], phase ^ 1u);
-                        ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
-                        ptx::bulk_g2s(sA + stage * ABLOCK_BYTES, ab + static_cast<size_t>(kb) * ABLOCK_BYTES,
-                                      ABLOCK_BYTES, fb);
-                        ptx::bulk_g2s(sB + stage * C::BLOAD_BYTES, wt + static_cast<size_t>(kbg) * C::BBLOCK_BYTES,
-                                      C::BLOAD_BYTES, fb);
+                        if constexpr (SPLIT) {
+                            const bool xlo = (a.split & 1) != 0, wlo = (a.split & 2) != 0;
+                            ptx::mbar_arrive_expect_tx(fb, ABLOCK_BYTES + C::BLOAD_BYTES + (xlo ? ABLOCK_BYTES : 0) +
+                                                               (wlo ? C::BLOAD_BYTES : 0));
+                            ptx::bulk_g2s(sA + stage * A_STAGE, ab + static_cast<size_t>(kb) * ABLOCK_BYTES, ABLOCK_BYTES, fb);
+                            if (xlo) ptx::bulk_g2s(sA + stage * A_STAGE + ABLOCK_BYTES, ab_lo + static_cast<size_t>(kb) * ABLOCK_BYTES,
+                                                   ABLOCK_BYTES, fb);
+                            ptx::bulk_g2s(sB + stage * B_STAGE, wt + static_cast<size_t>(kbg) * C::BBLOCK_BYTES, C::BLOAD_BYTES, fb);
+                            if (wlo) ptx::bulk_g2s(sB + stage * B_STAGE + C::BLOAD_BYTES,
+                                                   wt + static_cast<size_t>(a.w_lo_off + kbg) * C::BBLOCK_BYTES, C::BLOAD_BYTES, fb);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+                            ptx::bulk_g2s(sA + stage * ABLOCK_BYTES, ab + static_cast<size_t>(kb) * ABLOCK_BYTES,
+                                          ABLOCK_BYTES, fb);
+                            ptx::bulk_g2s(sB + stage * C::BLOAD_BYTES, wt + static_cast<size_t>(kbg) * C::BBLOCK_BYTES,
+                                          C::BLOAD_BYTES, fb);
+                        }
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -167,12 +187,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 for (int kb = 0; kb < a.num_kb; ++kb) {
                     ptx::mbar_wait(&ready[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t adesc = ptx::make_sw128_desc(u_sA + stage * ABLOCK_BYTES);
-                    const uint64_t bdesc = ptx::make_sw128_desc(u_sB + stage * C::BLOAD_BYTES);
+                    const uint64_t adesc = ptx::make_sw128_desc(u_sA + stage * A_STAGE);
+                    const uint64_t bdesc = ptx::make_sw128_desc(u_sB + stage * B_STAGE);
+                    const uint64_t adesc_lo = ptx::make_sw128_desc(u_sA + stage * A_STAGE + ABLOCK_BYTES);
+                    const uint64_t bdesc_lo = ptx::make_sw128_desc(u_sB + stage * B_STAGE + C::BLOAD_BYTES);
+                    const bool xlo = SPLIT && (a.split & 1) != 0, wlo = SPLIT && (a.split & 2) != 0;
                     if (ptx::elect_one()) {
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k)       // 32 bytes (16 fp16) per MMA along K
                             ptx::umma_f16_ss<CL>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (SPLIT) {
+                            if (xlo) {
+#pragma unroll
+                                for (int k = 0; k < KB / 16; ++k) ptx::umma_f16_ss<CL>(d_tmem, adesc_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                            }
+                            if (wlo) {
+#pragma unroll
+                                for (int k = 0; k < KB / 16; ++k) ptx::umma_f16_ss<CL>(d_tmem, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1u);
+                            }
+                        }
                         ptx::umma_commit_addr<CL>(u_empty + stage * 8);     // frees the smem slot(s) when the MMAs retire
                         if (kb == a.num_kb - 1) ptx::umma_commit_addr<CL>(u_tfull + acc * 8);
                     }
@@ -368,14 +401,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool SPLIT>
 int launch(const GemmArgs& a, int num_sms, cudaStream_t s) {
-    using C = Cfg<BN, CL>;
+    using C = Cfg<BN, CL, SPLIT>;
     static bool configured[32] = {};
     int dev = 0;
     PIFU_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 31]) {
-        PIFU_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PIFU_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
         configured[dev & 31] = true;
     }
@@ -394,7 +427,7 @@ int launch(const GemmArgs& a, int num_sms, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PIFU_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, a));
+    PIFU_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL, SPLIT>, a));
     return 0;
 }
 
@@ -406,10 +439,14 @@ int launch_gemm_tc(const GemmArgs& a, int num_sms, int pair, cudaStream_t s) {
         set_error("gemm: fused last layer needs a 128- or 256-wide hidden layer, got %d", a.N);
         return -1;
     }
+    if (a.split) {                                        // staged split precision: CTA pairs only (the product path)
+        if (a.N % 256 == 0 && (a.head_w == nullptr || a.N == 256)) return launch<256, 2, true>(a, num_sms, s);
+        if (a.N % 128 == 0 && (a.head_w == nullptr || a.N == 128)) return launch<128, 2, true>(a, num_sms, s);
+    }
     if (a.N % 256 == 0 && (a.head_w == nullptr || a.N == 256))
-        return pair ? launch<256, 2>(a, num_sms, s) : launch<256, 1>(a, num_sms, s);
+        return pair ? launch<256, 2, false>(a, num_sms, s) : launch<256, 1, false>(a, num_sms, s);
     if (a.N % 128 == 0 && (a.head_w == nullptr || a.N == 128))
-        return pair ? launch<128, 2>(a, num_sms, s) : launch<128, 1>(a, num_sms, s);
+        return pair ? launch<128, 2, false>(a, num_sms, s) : launch<128, 1, false>(a, num_sms, s);
     set_error("gemm: output width %d is not a multiple of 128", a.N);
     return -1;
 }

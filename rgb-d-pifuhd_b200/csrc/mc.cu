@@ -14,7 +14,7 @@
 // first-use order (MC_VERTS of its table row).
 //
 // Passes (HBM-bound; the field is read from DRAM once):
-//   classify  streaming form: a warp owns 8 cell rows x 128 values and walks 16 layers; every field plane of the tile is
+//   classify  streaming form: a warp owns 8 cell rows x 128 values and walks 8 layers; every field plane of the tile is
 //             read once as 16-byte vectors (9 independent loads per lane, no shared memory, no barrier) and reduced to
 //             inside bits packed into 64-bit words; `any ^ all` of the eight corner words marks the surface cells
 //             among a lane's 32 cells.  ~99 % of the lanes see one side of the level only and do nothing more.
@@ -123,11 +123,20 @@ __device__ __forceinline__ uint32_t case_of(uint32_t m00, uint32_t m01, uint32_t
 // Table row of a surface cell: MC_SUB_BASE[case] + one bit per ambiguous face (ascending face order), set when
 // Lewiner's face test joins the inside corners across the face: (a - L)(c - L) > (b - L)(d - L) for the inside
 // corners a, c and the outside corners b, d, in float64 with separately rounded products (tools/gen_mc_tables.py).
+// (kept out of line: it is the rare path of every pass, and inlining it into their unrolled cell loops made the
+// row pass stall on instruction fetch - ncu: 6.7 warps per issue waiting for instructions)
+__device__ __noinline__ uint32_t cell_sub_ambiguous(const float* __restrict__ f, int n1, int n2, double level, int i, int j, int k,
+                                                    uint32_t cs);
 __device__ __forceinline__ uint32_t cell_sub(const float* __restrict__ f, const Dims& d, double level, int i, int j, int k,
                                              uint32_t cs) {
+    if (MC_AMB[cs] == 0u) return MC_SUB_BASE[cs];
+    return cell_sub_ambiguous(f, d.n1, d.n2, level, i, j, k, cs);
+}
+__device__ __noinline__ uint32_t cell_sub_ambiguous(const float* __restrict__ f, int n1, int n2, double level, int i, int j, int k,
+                                                    uint32_t cs) {
     const uint32_t amb = MC_AMB[cs];
     uint32_t row = MC_SUB_BASE[cs];
-    if (amb == 0u) return row;
+    struct { int n1, n2; } d = {n1, n2};
     double v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c)
@@ -203,8 +212,8 @@ __global__ void __launch_bounds__(256) classify_kernel(const float* __restrict__
 // lane's WR x 4 cells; the previous plane's words are kept for the next layer, so every field value is loaded once
 // (+ 1/WR for the shared row, + 1/WL for the shared plane, + 1/128 for the tile's last column).
 constexpr int WR = 8;
-constexpr int WL = 16;
 
+// inside bits of one plane of the tile, 4 bits per field row (rows 0 .. 8): a = values k .. k+3, b = values k+1 .. k+4
 struct PlaneBits { unsigned long long a, b; };
 
 __device__ __forceinline__ PlaneBits warp_plane_bits(const float* __restrict__ f, const Dims& d, int plane, int j0, int frows,
@@ -242,8 +251,37 @@ __device__ __forceinline__ PlaneBits warp_plane_bits(const float* __restrict__ f
     return pb;
 }
 
+// The same for a full tile (all WR + 1 field rows exist, every lane's 4 values + the next column are inside a 16-byte
+// aligned row): straight-line code, ~200 instructions per plane instead of ~580 (the generic form spends a third of
+// its instructions on 64-bit address arithmetic and a sixth on the per-row branches; ncu showed the pass issue-bound,
+// not memory-bound: 44 % DRAM utilisation at 42 % issue utilisation).  `p` = the lane's first value of field row 0.
+__device__ __forceinline__ PlaneBits warp_plane_bits_full(const float* __restrict__ p, long long n2, float lf, bool tail, int lane) {
+    float4 v[WR + 1];
+    float nx[WR + 1];
+#pragma unroll
+    for (int r = 0; r <= WR; ++r) {
+        v[r] = __ldg(reinterpret_cast<const float4*>(p + r * n2));
+        nx[r] = lf;
+        if (tail) nx[r] = __ldg(p + r * n2 + 4);
+    }
+    uint32_t alo = 0, ahi = 0, tlo = 0, thi = 0;
+#pragma unroll
+    for (int r = 0; r <= WR; ++r) {
+        const uint32_t nib = (v[r].x > lf ? 1u : 0u) | (v[r].y > lf ? 2u : 0u) | (v[r].z > lf ? 4u : 0u) | (v[r].w > lf ? 8u : 0u);
+        const uint32_t t = nx[r] > lf ? 1u : 0u;
+        if (r < WR) { alo |= nib << (4 * r); tlo |= t << (4 * r); } else { ahi = nib; thi = t; }
+    }
+    uint32_t nlo = __shfl_down_sync(0xffffffffu, alo, 1), nhi = __shfl_down_sync(0xffffffffu, ahi, 1);
+    if (lane == 31) { nlo = tlo; nhi = thi; }
+    PlaneBits pb;
+    pb.a = (static_cast<unsigned long long>(ahi) << 32) | alo;
+    pb.b = (static_cast<unsigned long long>(((ahi >> 1) & 0x7u) | ((nhi & 0x1u) << 3)) << 32) |
+           (((alo >> 1) & 0x77777777u) | ((nlo & 0x11111111u) << 3));
+    return pb;
+}
+
 __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
-                                                            int nkt, int nbands, int nchunks, const uint8_t* __restrict__ own,
+                                                            int nkt, int nbands, int nchunks, int WL, const uint8_t* __restrict__ own,
                                                             uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums) {
     const int lane = threadIdx.x & 31;
     const long long wg = blockIdx.x * 8LL + (threadIdx.x >> 5);
@@ -259,9 +297,16 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
     const unsigned long long vm = nc >= 4 ? 0xfull : (nc > 0 ? ((1ull << nc) - 1ull) : 0ull);
     unsigned long long valid = 0ull;
     for (int r = 0; r < crows; ++r) valid |= vm << (4 * r);
-    PlaneBits lo = warp_plane_bits(f, d, ia, j0, crows + 1, k0, lf, vec, lane);
+    // full tile (warp-uniform): every field row exists and every lane's loads are whole, aligned 16-byte vectors
+    const bool full = __all_sync(0xffffffffu, crows == WR && vec && k0 + 4 <= d.n2);
+    const bool tail = lane == 31 && k0 + 4 < d.n2;
+    const long long n2 = d.n2, plane_stride = static_cast<long long>(d.n1) * d.n2;
+    const float* p = f + (static_cast<long long>(ia) * d.n1 + j0) * n2 + k0;
+    PlaneBits lo = full ? warp_plane_bits_full(p, n2, lf, tail, lane) : warp_plane_bits(f, d, ia, j0, crows + 1, k0, lf, vec, lane);
     for (int i = ia; i < ib; ++i) {
-        const PlaneBits hi = warp_plane_bits(f, d, i + 1, j0, crows + 1, k0, lf, vec, lane);
+        p += plane_stride;
+        const PlaneBits hi = full ? warp_plane_bits_full(p, n2, lf, tail, lane)
+                                  : warp_plane_bits(f, d, i + 1, j0, crows + 1, k0, lf, vec, lane);
         const unsigned long long any = lo.a | (lo.a >> 4) | lo.b | (lo.b >> 4) | hi.a | (hi.a >> 4) | hi.b | (hi.b >> 4);
         const unsigned long long all = lo.a & (lo.a >> 4) & lo.b & (lo.b >> 4) & hi.a & (hi.a >> 4) & hi.b & (hi.b >> 4);
         unsigned long long act = (any ^ all) & valid;
@@ -269,6 +314,7 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
             const int zi = (i + d.i0 == 0) ? 1 : 0;
             int cur = -1;
             uint32_t nv = 0, nt = 0;
+#pragma unroll 1
             while (act) {
                 const int bit = __ffsll(static_cast<long long>(act)) - 1;
                 act &= act - 1ull;
@@ -431,53 +477,48 @@ __global__ void __launch_bounds__(SCAN_BLOCK) emit_rows_kernel(const float* __re
         for (int q0 = 0; q0 < d.nq; q0 += tm.T) {
             const int kq = q0 + tm.tid;
             const int k0 = kq * CPT;
+            // surface cells of this lane's 8 cells: `any ^ all` of the eight corner bit-vectors (the rows hold a handful
+            // of them, so everything below walks set bits instead of the 8 cells)
             uint32_t nv = 0, nt = 0, actm = 0;
             RowMasks r = {0u, 0u, 0u, 0u};
             if (kq < d.nq) {
                 r = load_masks(f, d, i, j, k0, lf, vec);
+                const uint32_t any = r.m00 | r.m01 | r.m10 | r.m11 | (r.m00 >> 1) | (r.m01 >> 1) | (r.m10 >> 1) | (r.m11 >> 1);
+                const uint32_t all = r.m00 & r.m01 & r.m10 & r.m11 & (r.m00 >> 1) & (r.m01 >> 1) & (r.m10 >> 1) & (r.m11 >> 1);
+                const int nc = d.c2 - k0 < CPT ? d.c2 - k0 : CPT;
+                actm = (any ^ all) & ((1u << nc) - 1u);
                 const int zij = zero_mask(i + d.i0, j, 1);
-#pragma unroll
-                for (int m = 0; m < CPT; ++m) {
-                    if (k0 + m >= d.c2) continue;
+#pragma unroll 1
+                for (uint32_t todo = actm; todo != 0u; todo &= todo - 1u) {
+                    const int m = __ffs(todo) - 1;
                     const uint32_t cs = case_of(r.m00, r.m01, r.m10, r.m11, m);
-                    if (cs != 0u && cs != 255u) { actm |= 1u << m; nv += __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0))); }
-                }
-            }
-            // table rows of the surface cells (face tests on the ambiguous ones) before the scans: the triangle count needs them
-            uint16_t subs[CPT];
-#pragma unroll
-            for (int m = 0; m < CPT; ++m) {
-                subs[m] = 0xffffu;
-                if (actm & (1u << m)) {
-                    subs[m] = static_cast<uint16_t>(cell_sub(f, d, level, i, j, k0 + m, case_of(r.m00, r.m01, r.m10, r.m11, m)));
-                    if (i >= d.ghost) nt += MC_NTRI[subs[m]];
+                    nv += __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0)));
+                    if (i >= d.ghost) nt += MC_NTRI[cell_sub(f, d, level, i, j, k0 + m, cs)];
                 }
             }
             uint32_t bv, bt;
-            uint32_t vrel = team_exclusive_scan(tm, nv, &bv, wsum[0]);
-            uint32_t trel = team_exclusive_scan(tm, nt, &bt, wsum[1]);
-            if (actm != 0u) {
-                uint32_t vb = vcarry + vrel, tb = tcarry + trel;
-#pragma unroll
-                for (int m = 0; m < CPT; ++m) {
-                    if (!(actm & (1u << m))) continue;
-                    const int k = k0 + m;
-                    const uint32_t sub = subs[m];
-                    const unsigned long long cell = static_cast<unsigned long long>(row) * d.c2 + k;
-                    cellinfo[cell] = make_uint2(vb, sub);
-                    const int zm = zero_mask(i + d.i0, j, k);
-                    const int nvc = MC_NVERT[sub];
-                    for (int q = 0; q < nvc; ++q) {
-                        const int e = MC_VERTS[sub][q];
-                        if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
-                        if (vfits) vjobs[vb] = (cell << 4) | static_cast<unsigned long long>(e);
-                        ++vb;
-                    }
-                    if (i >= d.ghost) {
-                        const uint32_t n = MC_NTRI[sub];
-                        for (uint32_t t = 0; t < n; ++t, ++tb)
-                            if (tfits) tjobs[tb] = (cell << 16) | (static_cast<unsigned long long>(sub) << 4) | t;
-                    }
+            uint32_t vb = vcarry + team_exclusive_scan(tm, nv, &bv, wsum[0]);
+            uint32_t tb = tcarry + team_exclusive_scan(tm, nt, &bt, wsum[1]);
+#pragma unroll 1
+            for (uint32_t todo = actm; todo != 0u; todo &= todo - 1u) {
+                const int m = __ffs(todo) - 1;
+                const int k = k0 + m;
+                const uint32_t cs = case_of(r.m00, r.m01, r.m10, r.m11, m);
+                const uint32_t sub = cell_sub(f, d, level, i, j, k, cs);       // (a table read; face tests only on ambiguous cells)
+                const unsigned long long cell = static_cast<unsigned long long>(row) * d.c2 + k;
+                cellinfo[cell] = make_uint2(vb, sub);
+                const int zm = zero_mask(i + d.i0, j, k);
+                const int nvc = MC_NVERT[sub];
+                for (int q = 0; q < nvc; ++q) {
+                    const int e = MC_VERTS[sub][q];
+                    if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
+                    if (vfits) vjobs[vb] = (cell << 4) | static_cast<unsigned long long>(e);
+                    ++vb;
+                }
+                if (i >= d.ghost) {
+                    const uint32_t n = MC_NTRI[sub];
+                    for (uint32_t t = 0; t < n; ++t, ++tb)
+                        if (tfits) tjobs[tb] = (cell << 16) | (static_cast<unsigned long long>(sub) << 4) | t;
                 }
             }
             vcarry += bv;
@@ -619,12 +660,25 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     PIFU_CUDA(cudaMemsetAsync(st->tsums, 0, static_cast<size_t>(st->rows + 1) * sizeof(uint32_t), s));
     PIFU_CUDA(cudaMemsetAsync(st->totals, 0, 4 * sizeof(unsigned long long), s));
     static const bool per_thread = getenv("PIFU_MC_CLASSIFY") && atoi(getenv("PIFU_MC_CLASSIFY")) == 0;      // A/B measurements
-    const long long nkt = (d.c2 + 127) / 128, nbands = (d.c1 + WR - 1) / WR, nchunks = (d.c0 + WL - 1) / WL;
+    const long long nkt = (d.c2 + 127) / 128, nbands = (d.c1 + WR - 1) / WR;
+    static int resident = 0;                       // blocks of the classify kernel an SM holds
+    if (resident == 0) {
+        PIFU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, classify_warp_kernel, 256, 0));
+        if (resident < 1) resident = 1;
+    }
+    (void)resident;
+    // layers per tile.  Measured at 512^3 (whole extraction): 8 layers 0.369 ms, 12: 0.385, 16: 0.427, 24: 0.468; one wave
+    // of equal 29-layer tiles was twice as slow in the classify pass (the serial chain per warp grows faster than the
+    // tail shrinks).  The pass then reads 3.6 TB/s; torch.max over the same volume reads 4.5 TB/s on this part.
+    static const int wl_env = getenv("PIFU_MC_WL") ? atoi(getenv("PIFU_MC_WL")) : 0;
+    int WL = wl_env > 0 ? wl_env : 8;
+    if (WL > d.c0) WL = d.c0;
+    const long long nchunks = (d.c0 + WL - 1) / WL;
     const long long warps = nkt * nbands * nchunks;
     if (!per_thread && (warps + 7) / 8 <= 0x7fffffffLL) {
         classify_warp_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(
             field, d, level_below(level), level, vec_ok(field, n2), static_cast<int>(nkt), static_cast<int>(nbands),
-            static_cast<int>(nchunks), st->own, st->vsums, st->tsums);
+            static_cast<int>(nchunks), WL, st->own, st->vsums, st->tsums);
     } else {
         classify_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(field, d, level_below(level), level,
                                                                                     vec_ok(field, n2), st->own, st->vsums, st->tsums);
@@ -650,8 +704,11 @@ int mc_emit_async(pifu_ctx* c, double* verts, int* faces, float* normals, float*
     const int vec = vec_ok(st->field, st->n[2]);
     if (grow(&st->vjobs, &st->cap_vjobs, cap_verts > 0 ? cap_verts : 1)) return -1;
     if (grow(&st->tjobs, &st->cap_tjobs, cap_faces > 0 ? cap_faces : 1)) return -1;
-    int T = 32;                                  // team = threads of one cell row, a power of two in [32, 256]
-    while (T < d.nq && T < SCAN_BLOCK) T *= 2;
+    // team = threads that share one cell row: a warp (shuffle scans, no barrier; a 512-cell row takes two chunks of
+    // 32 x 8 cells with a carry) unless the row is long enough to keep a wider team busy
+    int T = 32;
+    while (T * 4 < d.nq && T < SCAN_BLOCK) T *= 2;
+    if (const char* e = getenv("PIFU_MC_TEAM")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) T = v; }
     const int sms = ctx_num_sms(c);
     emit_rows_kernel<<<sms * 6, SCAN_BLOCK, 0, s>>>(st->field, d, st->level, lf, vec, T, st->own, st->vsums, st->tsums, st->cellinfo,
                                                    st->vjobs, st->tjobs, cap_verts, faces ? cap_faces : 0, st->active, st->totals + 3);

@@ -236,3 +236,19 @@ def test_marching_cubes_slabs_assemble_to_whole(vol, splits):
     assert np.array_equal(torch.cat(V).cpu().numpy(), rv)
     assert np.array_equal(torch.cat(VAL).cpu().numpy(), rval)
     assert np.abs(torch.cat(N).cpu().numpy() - rn).max() < 1e-6
+
+
+def test_marching_cubes_extract_overflow_retries():
+    """`pifu_mc_extract` sizes nothing on the host: outputs are allocated from a hint and only the counts come back.
+    A hint that is too small must leave the outputs untouched and the retry must give the same mesh."""
+    from pifu_b200 import get_engine
+    eng = get_engine("cuda")
+    v = _noise((20, 21, 22), 9)
+    rv, rf, _, _, _ = _oracle_mc(v)
+    key = ("whole",) + v.shape
+    eng._mc_hint[key] = (1, 1)                    # capacity ~1 k vertices / ~2 k faces: far too small
+    verts, faces, _, _ = eng.marching_cubes(torch.from_numpy(v).cuda(), 0.5)
+    assert len(rv) > 2048 and np.array_equal(faces.cpu().numpy(), rf) and np.array_equal(verts.cpu().numpy(), rv)
+    assert eng._mc_hint[key] == (len(rv), len(rf))
+    verts2, faces2, _, _ = eng.marching_cubes(torch.from_numpy(v).cuda(), 0.5)      # sized from the hint: one pass
+    assert np.array_equal(faces2.cpu().numpy(), rf) and np.array_equal(verts2.cpu().numpy(), rv)

@@ -60,6 +60,26 @@ def test_split_precision_saturated_field(sat, sat_points):
         eng.set_precision("fast")
 
 
+@pytest.mark.parametrize("impl", ["tc1", "simt"])
+def test_split_precision_k_concatenated_form(sat, sat_points, impl):
+    """The product path stages {x_hi, x_lo, W_hi, W_lo} of a k-block together (gemm_tc.cu SPLIT).  The same three
+    products expressed as extra K segments - [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T - run through the 1-CTA
+    tensor-core kernel and the CUDA-core cross-check: all three must agree with the oracle."""
+    from test_query_gpu import IMPL
+    _, _, _, netMR, eng = sat
+    pts, calib, ref, _, _ = sat_points
+    n = 20000 if impl == "simt" else 100000
+    eng.set_precision("split")
+    eng.set_gemm_impl(IMPL[impl])
+    try:
+        netMR.query(pts[:, :, :n].cuda(), calib.cuda())
+        out = netMR.get_preds().cpu()
+    finally:
+        eng.set_gemm_impl(0)
+        eng.set_precision("fast")
+    assert (out - ref[:, :, :n]).abs().max().item() < 1e-4
+
+
 def test_error_budget_by_rounding_point(sat, sat_points):
     """terms: 0 = fast, 1 = + activation/feature residuals, 2 = + weight residuals, 3 = both.  Each residual
     product removes its rounding point's share; only both together reach the fp32 level."""
