@@ -625,7 +625,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     warmup = max(args.warmup, 3)
     res, what = workload(world)
     if args.res:
@@ -756,7 +756,7 @@ def main():
                    "sample": "%d-point strided sub-lattice of the %d^3 lattice, chunks of 100000, %.1f s" % (npts, res, sec)}
             ids = sample_ids(res, n_s)
             mine = (ids >= id_b) & (ids < id_e)
-            step()
+            # `slab` still holds this rank's field of the last evaluation (no collective here: only rank 0 is in this block)
             got = slab[torch.from_numpy(ids[mine] - id_b).to(dev)].cpu().numpy()
             parity = parity_block(got, ref_vals[mine], "timed step's field (fast arithmetic, gate field sigma 0.75) vs the CPU "
                                   "port on the strided sample%s" % ("" if world == 1 else ", rank 0's slab"))

@@ -156,6 +156,12 @@ int pifu_octree_export(pifu_ctx* ctx, double* sdf64, float* sdf32, void* stream)
 int pifu_octree_begin_slab(pifu_ctx* ctx, int R0, int R1, int R2, int init_resolution, double threshold, int plane_begin,
                            int plane_end, int own_begin, int own_end, void* stream);
 int pifu_octree_commit_pairs(pifu_ctx* ctx, const long long* ids_device, const float* values_device, long long n, void* stream);
+/* Planes (global indices, inside the local planes, starting on the current stride) whose frontier the next
+ * pifu_octree_frontier compacts.  A rank may compact - and evaluate itself - the frontier of ALL its local planes at the
+ * coarse levels, whose frontiers are small: the values are the ones its neighbours compute (a point's value does not
+ * depend on the call it is evaluated in), so those levels need no communication at all; pifu_octree_commit then takes
+ * the values in frontier order as in the single-device form. */
+int pifu_octree_set_frontier_planes(pifu_ctx* ctx, int plane_begin, int plane_end);
 int pifu_octree_field32(pifu_ctx* ctx, const float** field_device, int* plane_begin, int* planes);
 
 /* Marching cubes on a device float32 volume [n0][n1][n2] at `level` (strict v > level is

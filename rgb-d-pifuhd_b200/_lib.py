@@ -46,6 +46,7 @@ SIGNATURES = {
     "pifu_octree_begin_slab": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, VP]),
     "pifu_octree_commit_pairs": (ctypes.c_int, [VP, VP, VP, ctypes.c_longlong, VP]),
+    "pifu_octree_set_frontier_planes": (ctypes.c_int, [VP, ctypes.c_int, ctypes.c_int]),
     "pifu_octree_field32": (ctypes.c_int, [VP, ctypes.POINTER(VP), c_int_p, c_int_p]),
     "pifu_mc_count": (ctypes.c_int, [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                      c_ll_p, c_ll_p, VP]),

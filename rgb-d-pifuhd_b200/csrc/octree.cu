@@ -571,6 +571,20 @@ int pifu_octree_commit_pairs(pifu_ctx* c, const long long* ids, const float* val
     return octree_commit(c, values, nullptr, static_cast<cudaStream_t>(stream), n > 0 ? ids : &none, n);
 }
 
+int pifu_octree_set_frontier_planes(pifu_ctx* c, int plane_begin, int plane_end) {
+    OctreeState* st = c ? ctx_octree(c) : nullptr;
+    if (!st || !st->sdf) { set_error("octree: begin was not called"); return -1; }
+    const int lb = st->lb, le = st->lb + st->R[0];
+    const int s = st->step > 0 ? st->step : 1;
+    if (plane_begin < lb || plane_end > le || plane_begin > plane_end || (plane_begin - lb) % s) {
+        set_error("octree: frontier planes [%d, %d) outside the local planes [%d, %d) or off the stride %d", plane_begin, plane_end, lb, le, s);
+        return -1;
+    }
+    st->f0 = plane_begin - lb;
+    st->f1 = plane_end - lb;
+    return 0;
+}
+
 int pifu_octree_field32(pifu_ctx* c, const float** field, int* plane_begin, int* planes) {
     OctreeState* st = c ? ctx_octree(c) : nullptr;
     if (!st || !st->sdf32 || !field) { set_error("octree: no field"); return -1; }

@@ -89,7 +89,27 @@ def exchange_halo(local, group=None):
     return below, above
 
 
-def sharded_marching_cubes(mc_slab, planes, level, R0, pb, pe, group=None, dst=0):
+def _pack_fragment(v, f, n, val):
+    """One byte buffer per rank: [verts f64 | normals f32 | values f32 | faces i32] (one gather instead of four)."""
+    def raw(t):
+        t = t.contiguous().reshape(-1)
+        return t.view(torch.uint8) if t.numel() else torch.empty(0, dtype=torch.uint8, device=t.device)
+    return torch.cat([raw(v), raw(n), raw(val), raw(f)])
+
+
+def _unpack_fragment(buf, nv, nf):
+    def typed(o, count, dtype, shape):
+        if count == 0:
+            return torch.empty(shape, dtype=dtype, device=buf.device)
+        return buf[o:o + count * dtype.itemsize].view(dtype).view(shape)
+    v = typed(0, nv * 3, torch.float64, (nv, 3))
+    n = typed(nv * 24, nv * 3, torch.float32, (nv, 3))
+    val = typed(nv * 36, nv, torch.float32, (nv,))
+    f = typed(nv * 40, nf * 3, torch.int32, (nf, 3))
+    return v, f, n, val
+
+
+def sharded_marching_cubes(mc_slab, planes, level, R0, pb, pe, group=None, dst=0, mc_async=None, note_counts=None):
     """Marching cubes of a volume sharded along axis 0; every rank extracts the cells of its own
     planes [pb, pe) and the fragments are gathered (vertex numbers offset by the slabs before it)
     into exactly the mesh a traversal of the whole volume produces.
@@ -99,6 +119,46 @@ def sharded_marching_cubes(mc_slab, planes, level, R0, pb, pe, group=None, dst=0
     Returns (verts, faces, normals, values) tensors on `dst`, None elsewhere."""
     W = world_size(group)
     cells_end = min(pe, R0 - 1)
+    if W > 1 and mc_async is not None:
+        # device path: the extraction is queued without a host synchronisation; the counts of all ranks come back with ONE
+        # read (all-gather of three numbers), and the fragments travel in one packed gather
+        dev = planes(pb, pb).device
+        have = cells_end > pb
+        if have:
+            lo, hi = max(pb - 1, 0), min(pe + 2, R0)
+            sub = planes(lo, hi)
+            v, f, n, val, cnt = mc_async(sub, level, lo, R0, cells_end - lo, pb > 0)
+        else:
+            cnt = torch.zeros(3, device=dev, dtype=torch.int64)
+        allc = torch.empty(W * 3, device=dev, dtype=torch.int64)
+        dist.all_gather_into_tensor(allc, cnt, group=group)
+        allc = allc.view(W, 3).tolist()
+        r = rank(group)
+        tv, tf, ng = (int(x) for x in allc[r])
+        if have and (tv > v.shape[0] or tf > f.shape[0]):          # capacity exceeded: nothing was written, extract again
+            v, f, n, val, cnt = mc_async(sub, level, lo, R0, cells_end - lo, pb > 0, cap=(tv, tf))
+        if have and note_counts is not None:
+            note_counts(tv, tf)
+        nvs = [int(c[0] - c[2]) for c in allc]
+        nfs = [int(c[1]) for c in allc]
+        if sum(nvs) == 0:
+            raise ValueError("No surface found at the given iso value (or level outside the data range)")
+        first = sum(nvs[:r])
+        if have:
+            frag = _pack_fragment(v[ng:tv], f[:tf] + (first - ng), n[ng:tv], val[ng:tv])
+        else:
+            frag = torch.empty(0, device=dev, dtype=torch.uint8)
+        sizes = [a * 40 + b * 12 for a, b in zip(nvs, nfs)]
+        per = max(max(sizes), 1)
+        pad = torch.empty(per, device=dev, dtype=torch.uint8)
+        pad[:frag.numel()] = frag
+        if r == dst:
+            parts = [torch.empty_like(pad) for _ in range(W)]
+            dist.gather(pad, parts, dst=dst, group=group)
+            pieces = [_unpack_fragment(p_, a, b) for p_, a, b in zip(parts, nvs, nfs)]
+            return tuple(torch.cat([pc[i] for pc in pieces], 0) for i in range(4))
+        dist.gather(pad, None, dst=dst, group=group)
+        return None
     if cells_end > pb:
         lo, hi = max(pb - 1, 0), min(pe + 2, R0)
         ghost = pb > 0
@@ -174,11 +234,21 @@ def octree_slab_planes(res, init_resolution, W, r):
     return pb, pe, max(0, pb - 2 * s0), min(res, pe + 2 * s0)
 
 
+LOCAL_LEVEL_MIN_STEP = 4      # levels of stride >= this are evaluated by every rank on its own local planes, without communication
+
+
 def sharded_octree_slab(eng, levels, res, calib, init_resolution=64, threshold=0.05, group=None, stats=None,
                         evaluate=None):
     """Slab-sharded device octree.  Returns (field, plane_begin, own_begin, own_end): the float32 field of this rank's
     planes [plane_begin, plane_begin + field.shape[0]) - valid on [own_begin - 1, own_end + 2) - or field None for a
-    rank that owns no plane."""
+    rank that owns no plane.
+
+    Coarse levels (stride >= LOCAL_LEVEL_MIN_STEP: a few hundred thousand points at 512^3) run without any collective:
+    every rank compacts and evaluates the frontier of ALL its local planes, margin included - 1.5 x its fair share of a
+    small level, against three collectives and two host synchronisations saved.  The values are the ones the neighbours
+    compute for the same points (a point's value does not depend on the call it is evaluated in), and inside the region
+    that matters the frontier is the true one because the bookkeeping state is (octree.cu).  The fine levels, which
+    hold 90 % of the points, are balanced: ids all-gathered, equal shares evaluated, values all-gathered."""
     W, r = world_size(group), rank(group)
     if evaluate is None:
         def evaluate(ids):
@@ -189,7 +259,21 @@ def sharded_octree_slab(eng, levels, res, calib, init_resolution=64, threshold=0
     if mine:
         eng.octree_begin_slab(res, init_resolution, threshold, lb, le, pb, pe)
     step = res // init_resolution
+    plane = res * res
     while step > 0:                                   # every rank walks the same levels, in lock step
+        if W > 1 and step >= LOCAL_LEVEL_MIN_STEP:
+            if mine:
+                eng.octree_set_frontier_planes(lb, le)
+                ids = eng.octree_frontier()[1]
+                eng.octree_commit(evaluate(ids) if ids.numel() else torch.empty(0, device=dev, dtype=torch.float32))
+            if stats is not None:                     # points evaluated by their owners = the single-device count
+                own = ((ids >= pb * plane) & (ids < pe * plane)).sum().reshape(1) if mine else torch.zeros(1, device=dev, dtype=torch.int64)
+                dist.all_reduce(own, group=group)
+                stats.append(int(own.item()))
+            step //= 2
+            continue
+        if mine:
+            eng.octree_set_frontier_planes(pb, pe)
         ids = eng.octree_frontier()[1] if mine else torch.empty(0, device=dev, dtype=torch.int64)
         n = int(ids.numel())
         cnt = torch.tensor([n], device=dev, dtype=torch.int64)
@@ -233,7 +317,8 @@ def sharded_mesh(eng, levels, res, calib, use_octree, level=0.5, init_resolution
     for the halo planes / frontier values and the mesh fragments).  Dense: every rank evaluates and
     extracts its own slab, one halo exchange of three planes.  Octree: the replicated bookkeeping
     leaves the whole field on every rank, which then extracts its own slab.  Returns the mesh
-    tensors on `dst` (None elsewhere); raises ValueError on every rank when there is no surface."""
+    tensors on `dst` (None elsewhere); raises ValueError on every rank when there is no surface.
+    (Octree: slab-sharded bookkeeping, `sharded_octree_slab`.)"""
     W, r = world_size(group), rank(group)
     plane = res * res
     b, e = shard_bounds(res * plane, W, r, align=plane)
@@ -274,4 +359,6 @@ def sharded_mesh(eng, levels, res, calib, use_octree, level=0.5, init_resolution
             if hi > pe:
                 parts.append(above[:hi - pe])
             return torch.cat(parts, 0) if len(parts) > 1 else parts[0]
-    return sharded_marching_cubes(eng.marching_cubes_slab, planes, level, res, pb, pe, group=group, dst=dst)
+    return sharded_marching_cubes(eng.marching_cubes_slab, planes, level, res, pb, pe, group=group, dst=dst,
+                                  mc_async=getattr(eng, "marching_cubes_slab_async", None),
+                                  note_counts=getattr(eng, "marching_cubes_note_counts", None))

@@ -287,6 +287,9 @@ class Engine:
                                                    int(plane_begin), int(plane_end), int(own_begin), int(own_end),
                                                    _stream(self.device_index)))
 
+    def octree_set_frontier_planes(self, plane_begin, plane_end):
+        _lib.check(self.lib.pifu_octree_set_frontier_planes(self.h, int(plane_begin), int(plane_end)))
+
     def octree_commit_pairs(self, ids, vals):
         """(lattice id, value) pairs of all ranks' frontiers; those outside this rank's planes are ignored."""
         ids = ids.to(self.device, torch.int64).contiguous()
@@ -366,6 +369,35 @@ class Engine:
         self._keep["mc_field"] = f
         return (verts[:nv], faces[:nf], normals[:nv] if want_normals else None,
                 values[:nv] if want_normals else None, ng)
+
+    def marching_cubes_slab_async(self, field, level, i_global0, global_n0, cell_layers, ghost, cap=None):
+        """Slab extraction without any host synchronisation: -> (verts, faces, normals, values, counts) with the outputs at
+        capacity `cap` = (verts, faces) (default: from the previous extraction of this slab) and counts a device int64 [3]
+        = vertices, faces, ghost vertices.  The caller reads the counts (e.g. together with the other ranks') and calls
+        again with a larger `cap` if one was exceeded."""
+        f = field.to(self.device, torch.float32).contiguous()
+        key = ("slab", int(i_global0), int(cell_layers)) + tuple(f.shape)
+        if cap is None:
+            hint = self._mc_hint.get(key) or (64 * f.shape[1] * f.shape[2] // 8 + 4096, 128 * f.shape[1] * f.shape[2] // 8 + 8192)
+            cap = (int(hint[0] * 3 // 2) + 1024, int(hint[1] * 3 // 2) + 2048)
+        cap_v, cap_f = int(cap[0]), int(cap[1])
+        verts = torch.empty((cap_v, 3), device=self.device, dtype=torch.float64)
+        faces = torch.empty((cap_f, 3), device=self.device, dtype=torch.int32)
+        normals = torch.empty((cap_v, 3), device=self.device, dtype=torch.float32)
+        values = torch.empty((cap_v,), device=self.device, dtype=torch.float32)
+        counts = torch.empty(3, device=self.device, dtype=torch.int64)
+        _lib.check(self.lib.pifu_mc_extract(
+            self.h, ctypes.c_void_p(f.data_ptr()), f.shape[0], f.shape[1], f.shape[2], float(level),
+            int(i_global0), int(global_n0), int(cell_layers), 1 if ghost else 0,
+            ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(faces.data_ptr()), ctypes.c_void_p(normals.data_ptr()),
+            ctypes.c_void_p(values.data_ptr()), cap_v, cap_f, ctypes.c_void_p(counts.data_ptr()), _stream(self.device_index)))
+        self._keep["mc_field"] = f
+        self._mc_last_key = key
+        return verts, faces, normals, values, counts
+
+    def marching_cubes_note_counts(self, nv, nf):
+        """Remember the sizes of the last asynchronous slab extraction (its next capacity)."""
+        self._mc_hint[self._mc_last_key] = (int(nv), int(nf))
 
     def marching_cubes(self, field, level, want_normals=True):
         """field: device float32 [n0, n1, n2].  -> (verts f64 [V,3], faces i32 [F,3], normals, values)

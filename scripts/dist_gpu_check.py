@@ -18,7 +18,8 @@ res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+import datetime
+dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 rank, world = dist.get_rank(), dist.get_world_size()
 netG, netMR, eng, calib = bench.build_mesh_problem(dev)
 cal = calib.to(dev)

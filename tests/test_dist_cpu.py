@@ -132,6 +132,17 @@ class FakeMeshEngine(FakeEngine):
     and a commit stores whichever (id, value) pairs fall inside the local planes."""
     marching_cubes_slab = staticmethod(_oracle_slab)
 
+    def marching_cubes_slab_async(self, field, level, i0, g0, layers, ghost, cap=None):
+        """The device engine's asynchronous form: outputs at a capacity, counts as a tensor; the first call is given a
+        capacity that is too small, so the retry path of `sharded_marching_cubes` runs as well."""
+        v, f, n, val, ng = _oracle_slab(field, level, i0, g0, layers, ghost)
+        counts = torch.tensor([v.shape[0], f.shape[0], ng], dtype=torch.int64)
+        cap = cap if cap is not None else (max(v.shape[0] - 3, 0), f.shape[0] + 5)
+        if v.shape[0] > cap[0] or f.shape[0] > cap[1]:
+            return (torch.zeros((cap[0], 3), dtype=torch.float64), torch.zeros((cap[1], 3), dtype=torch.int32),
+                    torch.zeros((cap[0], 3)), torch.zeros(cap[0]), counts)
+        return v, f, n, val, counts
+
     def eval_lattice_ids(self, levels, res, ids, calib):
         return self.fn(ids)
 
@@ -156,7 +167,16 @@ class FakeMeshEngine(FakeEngine):
         test = self.lat & self.todo
         test[:self.own[0]] = False
         test[self.own[1]:] = False
-        return self.step, torch.from_numpy(np.flatnonzero(test) + self.lb * self.res * self.res)
+        self._last_ids = torch.from_numpy(np.flatnonzero(test) + self.lb * self.res * self.res)
+        return self.step, self._last_ids
+
+    def octree_set_frontier_planes(self, plane_begin, plane_end):
+        self.own = (plane_begin - self.lb, plane_end - self.lb)
+
+    def octree_commit(self, vals):
+        if not getattr(self, "slab", False):
+            return super().octree_commit(vals)
+        self.octree_commit_pairs(self._last_ids, vals)
 
     def octree_commit_pairs(self, ids, vals):
         v = ids.numpy() - self.lb * self.res * self.res
