@@ -186,7 +186,8 @@ int pifu_mc_emit(pifu_ctx* ctx, double* verts, int* faces, float* normals, float
  * (the next layer's triangles refer to them) but emits no faces; *ghost_verts returns how many
  * leading vertices it numbered, so that for a slab whose first own vertex has global number G
  *   global vertex id = local id - *ghost_verts + G
- * and the caller drops the first *ghost_verts vertices.  pifu_mc_emit is unchanged. */
+ * and the caller drops the first *ghost_verts vertices (they are numbered but NOT written: the slab before computes
+ * them, and their normals would need a plane this slab does not hold).  pifu_mc_emit is unchanged. */
 int pifu_mc_count_slab(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, double level,
                        int i_global0, int global_n0, int cell_layers, int ghost_layers,
                        long long* nverts, long long* nfaces, long long* ghost_verts, void* stream);

@@ -238,7 +238,9 @@ static void push_face(int a, int b, int c) {
 static double grad(const float* f, const int* n, const long long* st, const int* p, int a, int off) {
     const long long i = p[0] * st[0] + p[1] * st[1] + p[2] * st[2];
     const int g = p[a] + (a == 0 ? off : 0);
-    const int lo = g > 0 ? -1 : 0, hi = g < n[a] - 1 ? 1 : 0;
+    /* p[a] > 0: the slab's first plane has nothing below it in memory; only vertices of the ghost layer (dropped by the
+     * caller) can ask for it */
+    const int lo = (g > 0 && p[a] > 0) ? -1 : 0, hi = g < n[a] - 1 ? 1 : 0;
     return ((double)f[i + hi * st[a]] - (double)f[i + lo * st[a]]) / (double)(hi - lo);
 }
 

@@ -531,10 +531,14 @@ __global__ void __launch_bounds__(SCAN_BLOCK) emit_rows_kernel(const float* __re
 __global__ void __launch_bounds__(256) emit_vertices_kernel(const float* __restrict__ f, Dims d, double level,
                                                             const uint32_t* __restrict__ voffs,
                                                             const unsigned long long* __restrict__ vjobs, double* __restrict__ verts,
-                                                            float* __restrict__ normals, float* __restrict__ values, long long cap_verts) {
+                                                            float* __restrict__ normals, float* __restrict__ values, long long cap_verts,
+                                                            const unsigned long long* __restrict__ ghost_verts) {
     const long long nv = voffs[static_cast<long long>(d.c0) * d.c1];
     if (nv > cap_verts) return;
-    for (long long v = blockIdx.x * 256LL + threadIdx.x; v < nv; v += static_cast<long long>(gridDim.x) * 256) {
+    // The vertices the ghost layer numbers belong to the slab before (which computes them); the caller drops them, so
+    // they are not computed: their normals would need the plane below the slab's first one, which the slab does not hold.
+    const long long first = d.ghost ? static_cast<long long>(*ghost_verts) : 0;
+    for (long long v = first + blockIdx.x * 256LL + threadIdx.x; v < nv; v += static_cast<long long>(gridDim.x) * 256) {
         const unsigned long long job = vjobs[v];
         const unsigned long long cell = job >> 4;
         const int k = static_cast<int>(cell % d.c2);
@@ -717,7 +721,7 @@ int mc_emit_async(pifu_ctx* c, double* verts, int* faces, float* normals, float*
     if (fb > sms * 32LL) fb = sms * 32LL;
     if (vb > 0)
         emit_vertices_kernel<<<static_cast<unsigned>(vb), 256, 0, s>>>(st->field, d, st->level, st->vsums, st->vjobs, verts, normals,
-                                                                      values, cap_verts);
+                                                                      values, cap_verts, st->totals + 2);
     if (faces && fb > 0)
         emit_faces_kernel<<<static_cast<unsigned>(fb), 256, 0, s>>>(d, st->cellinfo, st->tsums, st->tjobs, faces, cap_faces);
     PIFU_CUDA(cudaGetLastError());
