@@ -247,7 +247,7 @@ def vertex_colors_from_image(net, image, verts, calib_tensor, device=None):
     image [B, C, H, W] (first view used, like `image_tensor[:1]`), verts [V, 3] numpy/tensor -> [V, C] float32 numpy."""
     device = torch.device(device) if device is not None else (image.device if image.is_cuda else torch.device("cuda"))
     eng = get_engine(device)
-    pts = torch.as_tensor(np.ascontiguousarray(np.asarray(verts).T) if not torch.is_tensor(verts) else verts.T)
+    pts = torch.as_tensor(np.ascontiguousarray(np.asarray(verts).T)) if not torch.is_tensor(verts) else verts.T
     out = eng.sample_image(image[:1], pts.float(), calib_tensor[0], perspective=net.is_perspective)
     return (out.T * 0.5 + 0.5).cpu().numpy()
 
@@ -256,8 +256,11 @@ def clean_mesh(verts, faces, colors=None, device=None, only_watertight=True):
     """The component `meshcleaning` keeps (`reconstruction.py:325-344`), on arrays: numpy in / numpy out."""
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     eng = get_engine(device)
-    v, f, c = eng.clean_mesh(torch.as_tensor(np.asarray(verts, dtype=np.float64)), torch.as_tensor(np.asarray(faces, dtype=np.int32)),
-                             torch.as_tensor(np.asarray(colors, dtype=np.float64)) if colors is not None else None, only_watertight)
+    # (ascontiguousarray: `reconstruction()` hands out `faces[:, ::-1]`, a negative-stride view torch cannot wrap)
+    v, f, c = eng.clean_mesh(torch.as_tensor(np.ascontiguousarray(verts, dtype=np.float64)),
+                             torch.as_tensor(np.ascontiguousarray(faces, dtype=np.int32)),
+                             torch.as_tensor(np.ascontiguousarray(colors, dtype=np.float64)) if colors is not None else None,
+                             only_watertight)
     return v.cpu().numpy(), f.cpu().numpy(), (c.cpu().numpy() if c is not None else None)
 
 

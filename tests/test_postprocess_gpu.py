@@ -48,6 +48,9 @@ def test_clean_mesh_vs_oracle(only_watertight):
     colors = np.random.default_rng(0).random(verts.shape)
     rv, rf, rc = mesh_oracle.largest_component(verts, faces, colors, only_watertight)
     gv, gf, gc = mesh_util.clean_mesh(verts, faces, colors, device="cuda", only_watertight=only_watertight)
+    # the flipped, negative-stride face view `reconstruction()` returns (`mesh_util.py:91-92`) must be accepted as well
+    fv, ff, _ = mesh_util.clean_mesh(verts, faces[:, ::-1], None, device="cuda", only_watertight=only_watertight)
+    assert np.array_equal(ff, rf[:, ::-1]) and np.array_equal(fv, rv)
     assert 0 < len(rv) < len(verts)
     assert (rv[:, 0].max() - rv[:, 0].min() > 40) == (not only_watertight)      # the open bar wins only when open components count
     assert np.array_equal(gv, rv) and np.array_equal(gf, rf) and np.array_equal(gc, rc)
