@@ -31,6 +31,15 @@ def perspective(points, calib, transform=None):
     return torch.cat([homo[:, :2, :] / homo[:, 2:3, :], homo[:, 2:3, :]], 1)
 
 
+def check_batch_statistics(mlp, n_items):
+    """A BatchNorm1d MLP left in train mode takes its statistics over ALL items of the call ([B, C, N] -> per channel over
+    B x N, `MLP.py:36-41`); the fused path evaluates the items of a batch one after the other, each with its own
+    statistics - the reference's numbers for a batch of one (what `reconstruction()` passes), not for more.  GroupNorm
+    normalises per item, so it is unaffected."""
+    if n_items > 1 and getattr(mlp, "norm", "none") == "batch" and mlp.training:
+        _not_hot_path("a train-mode BatchNorm1d MLP queried with a batch of %d items (statistics across the batch)" % n_items)
+
+
 class BasePIFuNet(nn.Module):
     def __init__(self, projection_mode="orthogonal", criteria=None):
         super().__init__()

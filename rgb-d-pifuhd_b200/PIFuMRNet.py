@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import encoders
-from .BasePIFuNet import BasePIFuNet, _not_hot_path
+from .BasePIFuNet import BasePIFuNet, _not_hot_path, check_batch_statistics
 from .MLP import MLP
 from .PIFuNetwNML import EncoderHost
 from .engine import get_engine
@@ -114,6 +114,8 @@ class PIFuMRNet(BasePIFuNet, EncoderHost):
             calib_global = calib_local
             calib_local = calib_local[:, None]
         B1, B2 = points.shape[0], points.shape[1]
+        check_batch_statistics(self.mlp, B1 * B2)
+        check_batch_statistics(self.netG.mlp, B1 * B2)
         eng = self._engine_for(points)
         full = self.materialize_intermediates
         cphi = self.netG.mlp.filter_channels[self.netG.mlp.merge_layer + 1]

@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import encoders
-from .BasePIFuNet import BasePIFuNet, _not_hot_path
+from .BasePIFuNet import BasePIFuNet, _not_hot_path, check_batch_statistics
 from .MLP import MLP
 from .engine import get_engine
 
@@ -136,6 +136,7 @@ class PIFuNetwNML(BasePIFuNet, EncoderHost):
             _not_hot_path("training supervision (`labels`)")
         if len(self.im_feat_list) != 1:
             _not_hot_path("train-mode query over %d intermediate feature maps" % len(self.im_feat_list))
+        check_batch_statistics(self.mlp, points.shape[0])
         eng = self._engine_for(points)
         feat = self.im_feat_list[-1]
         cphi = self.mlp.filter_channels[self.mlp.merge_layer + 1]

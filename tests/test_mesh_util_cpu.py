@@ -100,3 +100,38 @@ def test_save_obj_bytes_identical_to_reference_loop(tmp_path):
     assert os.path.getsize(p) == 0
     with pytest.raises(IndexError):
         mesh_util.save_obj_mesh_with_color(p, v[:10], f[:1], c[:5])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours): one JSON line with the contract's keys, the
+    requested steps / warm-up, and the `config` object the GPU arm prints."""
+    import json
+    import subprocess
+    import sys
+    from helpers import ROOT
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    res, what = bench.workload(1)
+    assert d["config"] == bench.config_dict(1, res, what)
+
+
+def test_train_mode_batchnorm_batches_are_refused():
+    import torch
+    from pifu_b200 import BasePIFuNet
+
+    class M(torch.nn.Module):
+        norm = "batch"
+    m = M()
+    BasePIFuNet.check_batch_statistics(m, 1)
+    with pytest.raises(NotImplementedError):
+        BasePIFuNet.check_batch_statistics(m, 2)
+    m.eval()
+    BasePIFuNet.check_batch_statistics(m, 2)

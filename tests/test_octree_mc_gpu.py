@@ -142,11 +142,14 @@ def _noise(shape, seed):
     return rng.uniform(0, 1, shape).astype(np.float32)
 
 
-@pytest.mark.parametrize("vol", ["sphere33", "sphere64", "noise", "noise_ragged", "tiny"])
+@pytest.mark.parametrize("vol", ["sphere33", "sphere64", "noise", "noise_ragged", "tiny", "noise_wide", "noise_aligned"])
 def test_marching_cubes_bit_exact(vol):
     from pifu_b200 import get_engine
+    # noise_wide: rows of 1 099 cells = 138 threads' worth -> the row pass runs teams of 64 threads on named barriers and
+    # the classify pass several 128-value tiles per row; noise_aligned: 16-byte aligned rows (the vector-load paths)
     v = {"sphere33": _sphere(33), "sphere64": _sphere(64), "noise": _noise((24, 24, 24), 1),
-         "noise_ragged": _noise((9, 17, 31), 2), "tiny": _noise((2, 2, 2), 5)}[vol]
+         "noise_ragged": _noise((9, 17, 31), 2), "tiny": _noise((2, 2, 2), 5), "noise_wide": _noise((4, 5, 1100), 7),
+         "noise_aligned": _noise((19, 12, 256), 8)}[vol]
     if vol == "tiny":
         v[0, 0, 0], v[1, 1, 1] = 0.9, 0.1
     rv, rf, rn, rval, _ = _oracle_mc(v)
