@@ -52,6 +52,9 @@ class Engine:
         self._hold = {}
         self._mc_hint = {}
         self.precision = 0
+        import os
+        if os.environ.get("PIFU_PRECISION"):
+            self.set_precision(os.environ["PIFU_PRECISION"])
 
     def __del__(self):
         try:

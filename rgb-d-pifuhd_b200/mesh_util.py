@@ -149,15 +149,26 @@ def eval_field_device(net, cuda, calib_tensor, resolution, use_octree, init_reso
 
 
 def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh=0.5, use_octree=False,
-                   num_samples=10000, transform=None, *, group=None):
+                   num_samples=10000, transform=None, *, group=None, precision=None):
     """`mesh_util.py:40-96`.  Returns (verts float64 [V,3], faces int32 [F,3], normals float32,
     values float32) or -1 when no iso-surface exists.  As in the reference, `b_min`/`b_max`/
     `transform` are accepted and ignored (`:59`), the lattice is [-1, 1)^3 pre-multiplied by
     inv(calib), and faces are flipped when the index->world transform mirrors (`:91-92`).
     `num_samples` chunks host callbacks and, for a normalised MLP (mlp_norm 'group'/'batch'), cuts the
     lattice into the same statistics domains as the reference; with mlp_norm 'none' the fused path is
-    chunk-invariant."""
+    chunk-invariant.  `precision` ('fast' | 'hybrid' | 'split', native nets only) selects the arithmetic of the MLP for
+    this call (`Engine.set_precision`; default: whatever the engine is set to - 'fast' unless the environment variable
+    PIFU_PRECISION names another mode)."""
     device = torch.device(cuda)
+    if precision is not None and _is_native(net):
+        eng = get_engine(device)
+        before = eng.precision
+        eng.set_precision(precision)
+        try:
+            return reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, thresh, use_octree, num_samples,
+                                  transform, group=group)
+        finally:
+            eng.set_precision(before)
     mat = np.eye(4)
     mat[0, 0] = mat[1, 1] = mat[2, 2] = 2.0 / resolution
     mat[0:3, 3] = -1.0

@@ -1,4 +1,5 @@
-"""BASELINE.json's full sizes through size-independent properties (the oracle cannot run 512^3 in a test):
+"""BASELINE.json's full sizes, through size-independent properties where the oracle cannot run 512^3 in a test (the
+per-point MLP: 134 M queries) and directly where it can (marching cubes: a few seconds of C on the GPU's own field):
 
 * dense 512^3 field: a 1/64 sub-lattice re-evaluated as explicit points through the per-layer kernels agrees
   within the occupancy tolerance; the lattice is the reference's [-1, 1 - 2/R] grid (first / last voxel);
@@ -87,6 +88,19 @@ def test_marching_cubes_manifold_dense_and_octree(fields):
     _, eng, _, dense, octree, _ = fields
     _check_mesh(eng, dense.contiguous())
     _check_mesh(eng, octree.contiguous())
+
+
+def test_marching_cubes_512_bit_exact_vs_oracle(fields):
+    """BASELINE configs[2]'s volume: the 512^3 octree field through the CUDA marching cubes and through the sequential
+    C oracle (which shares no table with the kernels): faces, float64 vertices and values bit for bit."""
+    from oracle import mc_oracle
+    _, eng, _, _, octree, _ = fields
+    verts, faces, normals, values = eng.marching_cubes(octree.contiguous(), 0.5)
+    rv, rf, rn, rval, _ = mc_oracle.marching_cubes(octree.cpu().numpy(), 0.5)
+    assert np.array_equal(faces.cpu().numpy(), rf)
+    assert np.array_equal(verts.cpu().numpy(), rv)
+    assert np.array_equal(values.cpu().numpy(), rval)
+    assert np.abs(normals.cpu().numpy() - rn).max() < 1e-6
 
 
 def test_reconstruction_is_the_transformed_mesh(fields):

@@ -232,3 +232,16 @@ def test_hybrid_octree_with_net(sat):
     assert sign_agreement(out, gold) >= 0.9999
     assert (err > OCC_TOL).mean() < 1e-3
     assert err.max() < 0.03
+
+
+def test_reconstruction_precision_keyword(sat):
+    """`reconstruction(..., precision='hybrid')` runs that call in the hybrid arithmetic and leaves the engine as it was."""
+    from pifu_b200 import mesh_util
+    _, _, _, netMR, eng = sat
+    calib = syn.default_calib().cuda()
+    r0 = eng.refined_points()
+    fast = mesh_util.reconstruction(netMR, "cuda", calib, 64, None, None, use_octree=True)
+    assert eng.refined_points() == r0
+    hyb = mesh_util.reconstruction(netMR, "cuda", calib, 64, None, None, use_octree=True, precision="hybrid")
+    assert eng.refined_points() > r0 and eng.precision == 0
+    assert fast != -1 and hyb != -1 and abs(len(hyb[0]) - len(fast[0])) < 0.05 * len(fast[0])
