@@ -18,11 +18,12 @@
 //             read once as 16-byte vectors (9 independent loads per lane, no shared memory, no barrier) and reduced to
 //             inside bits packed into 64-bit words; `any ^ all` of the eight corner words marks the surface cells
 //             among a lane's 32 cells.  ~99 % of the lanes see one side of the level only and do nothing more.
-//             Surface cells add their vertex / triangle counts to per-row sums (integer atomics, order-free).
+//             A surface cell adds its vertex / triangle counts to per-row sums (integer atomics, order-free), sets its
+//             bit in the row's bit words and stores its table row (face tests on ambiguous faces) in its record.
 //   scan      device-wide exclusive scan of the two per-row arrays; rows with any output are listed.
-//   rows      teams of threads over the listed rows: cases and table rows recomputed from the field (L2), team scans
-//             -> every surface cell's record {first vertex number, table row} in a sparse per-cell array, and one job
-//             per vertex / triangle written at its own final index.
+//   rows      one warp per listed row, driven by what classify left behind (the row's surface cells as bit words, their table
+//             rows in the sparse cell records): warp scans -> every surface cell's first vertex number, and one job
+//             per vertex / triangle written at its own final index.  Nothing is recomputed from the field.
 //   vertices, faces   flat passes, one thread per vertex / triangle; face indices come from the owning cells' records.
 // No per-cell array is written for the 99 % of cells the surface does not touch.
 #include <cmath>
@@ -44,6 +45,9 @@ struct McState {
     const float* field = nullptr;
     long long rows = 0;                // cell rows = layers * c1
     uint2* cellinfo = nullptr;         // per cell, written for surface cells only: {first vertex number, table row}
+    uint32_t* rowbits = nullptr;       // per cell row, one bit per cell: surface cells (set by classify, read and cleared by the row pass)
+    long long cap_rowbits = 0;
+    bool rowbits_dirty = true;         // a pass that set bits did not reach the pass that clears them
     uint32_t* vsums = nullptr;         // per row (+1): vertices created -> exclusive offsets, total at [rows]
     uint32_t* tsums = nullptr;         // per row (+1): triangles
     uint32_t* partials = nullptr;      // scan spine
@@ -62,7 +66,7 @@ struct McState {
 
 void mc_free(McState* s) {
     if (!s) return;
-    cudaFree(s->cellinfo); cudaFree(s->vsums); cudaFree(s->tsums); cudaFree(s->totals);
+    cudaFree(s->cellinfo); cudaFree(s->rowbits); cudaFree(s->vsums); cudaFree(s->tsums); cudaFree(s->totals);
     cudaFree(s->partials); cudaFree(s->own); cudaFree(s->active); cudaFree(s->vjobs); cudaFree(s->tjobs);
     delete s;
 }
@@ -157,7 +161,8 @@ __device__ __noinline__ uint32_t cell_sub_ambiguous(const float* __restrict__ f,
 // Pass 1.  Thread g -> layer i, row group jg (RPT rows), cell group kq (CPT cells).
 __global__ void __launch_bounds__(256) classify_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
                                                        const uint8_t* __restrict__ own, uint32_t* __restrict__ vsums,
-                                                       uint32_t* __restrict__ tsums) {
+                                                       uint32_t* __restrict__ tsums, uint2* __restrict__ cellinfo,
+                                                       uint32_t* __restrict__ rowbits, int W) {
     const long long g = blockIdx.x * 256LL + threadIdx.x;
     const long long total = static_cast<long long>(d.c0) * d.njg * d.nq;          // < 2^31 (checked by the host)
     if (g >= total) return;
@@ -191,14 +196,20 @@ __global__ void __launch_bounds__(256) classify_kernel(const float* __restrict__
         const uint32_t m00 = mk[0][r], m01 = mk[0][r + 1], m10 = mk[1][r], m11 = mk[1][r + 1];
         const uint32_t ra = (m00 | m01 | m10 | m11) & span, rl = (m00 & m01 & m10 & m11) & span;
         if (ra == 0u || rl == span) continue;
-        uint32_t nv = 0, nt = 0;
+        uint32_t nv = 0, nt = 0, bits = 0;
+        const long long row = static_cast<long long>(i) * d.c1 + j;
         for (int m = 0; m < nc; ++m) {
             const uint32_t cs = case_of(m00, m01, m10, m11, m);
             if (cs == 0u || cs == 255u) continue;
-            nv += __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k0 + m == 0 ? 4 : 0)));
-            if (i >= d.ghost) nt += MC_NTRI[cell_sub(f, d, level, i, j, k0 + m, cs)];
+            const uint32_t o = __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k0 + m == 0 ? 4 : 0)));
+            nv += o;
+            if (o == 0u && i < d.ghost) continue;       // a ghost-layer cell that numbers nothing: no output, no record, no bit
+            const uint32_t sub = cell_sub(f, d, level, i, j, k0 + m, cs);
+            if (i >= d.ghost) nt += MC_NTRI[sub];
+            cellinfo[row * d.c2 + k0 + m].y = sub;
+            bits |= 1u << ((k0 + m) & 31);
         }
-        const long long row = static_cast<long long>(i) * d.c1 + j;
+        if (bits) atomicOr(rowbits + row * W + (k0 >> 5), bits);
         if (nv) atomicAdd(vsums + row, nv);
         if (nt) atomicAdd(tsums + row, nt);
     }
@@ -282,7 +293,8 @@ __device__ __forceinline__ PlaneBits warp_plane_bits_full(const float* __restric
 
 __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
                                                             int nkt, int nbands, int nchunks, int WL, const uint8_t* __restrict__ own,
-                                                            uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums) {
+                                                            uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums,
+                                                            uint2* __restrict__ cellinfo, uint32_t* __restrict__ rowbits, int W) {
     const int lane = threadIdx.x & 31;
     const long long wg = blockIdx.x * 8LL + (threadIdx.x >> 5);
     const int kt = static_cast<int>(wg % nkt);
@@ -312,8 +324,10 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
         unsigned long long act = (any ^ all) & valid;
         if (act != 0ull) {
             const int zi = (i + d.i0 == 0) ? 1 : 0;
+            // a surface cell leaves: its table row in its (sparse) record, its bit in the row's bit words, its counts in
+            // the row's sums - what the row pass needs, so that pass never looks at the field again
             int cur = -1;
-            uint32_t nv = 0, nt = 0;
+            uint32_t nv = 0, nt = 0, bits = 0;
 #pragma unroll 1
             while (act) {
                 const int bit = __ffsll(static_cast<long long>(act)) - 1;
@@ -322,10 +336,11 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
                 if (r != cur) {                                   // counts are flushed row by row
                     if (cur >= 0) {
                         const long long row = static_cast<long long>(i) * d.c1 + j0 + cur;
+                        if (bits) atomicOr(rowbits + row * W + (k0 >> 5), bits);
                         if (nv) atomicAdd(vsums + row, nv);
                         if (nt) atomicAdd(tsums + row, nt);
                     }
-                    cur = r; nv = 0; nt = 0;
+                    cur = r; nv = 0; nt = 0; bits = 0;
                 }
                 const int s0 = bit, s1 = bit + 4;                 // row r / row r + 1 of the packed words
                 const uint32_t cs = static_cast<uint32_t>((lo.a >> s0) & 1ull) | (static_cast<uint32_t>((lo.b >> s0) & 1ull) << 1) |
@@ -333,10 +348,18 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
                                     (static_cast<uint32_t>((hi.a >> s0) & 1ull) << 4) | (static_cast<uint32_t>((hi.b >> s0) & 1ull) << 5) |
                                     (static_cast<uint32_t>((hi.b >> s1) & 1ull) << 6) | (static_cast<uint32_t>((hi.a >> s1) & 1ull) << 7);
                 const int j = j0 + r, k = k0 + m;
-                nv += __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0)));
-                if (i >= d.ghost) nt += MC_NTRI[cell_sub(f, d, level, i, j, k, cs)];
+                const uint32_t o = __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0)));
+                nv += o;
+                // (a ghost-layer cell that numbers nothing leaves no record and no bit: every bit set belongs to a row with
+                // output, i.e. to a row the row pass visits and clears)
+                if (o == 0u && i < d.ghost) continue;
+                const uint32_t sub = cell_sub(f, d, level, i, j, k, cs);
+                if (i >= d.ghost) nt += MC_NTRI[sub];
+                cellinfo[(static_cast<long long>(i) * d.c1 + j) * d.c2 + k].y = sub;
+                bits |= 1u << (k & 31);
             }
             const long long row = static_cast<long long>(i) * d.c1 + j0 + cur;
+            if (bits) atomicOr(rowbits + row * W + (k0 >> 5), bits);
             if (nv) atomicAdd(vsums + row, nv);
             if (nt) atomicAdd(tsums + row, nt);
         }
@@ -401,113 +424,55 @@ __global__ void __launch_bounds__(SCAN_BLOCK) active_rows_kernel(const uint32_t*
     if (on) active[base + r] = static_cast<uint32_t>(b);
 }
 
-// inside masks of the four field rows around cell row (i, j), cells k0 .. k0 + CPT - 1
-struct RowMasks { uint32_t m00, m01, m10, m11; };
-__device__ __forceinline__ RowMasks load_masks(const float* __restrict__ f, const Dims& d, int i, int j, int k0, float lf, int vec) {
-    RowMasks r;
-    const float* p = f + (static_cast<long long>(i) * d.n1 + j) * d.n2 + k0;
-    r.m00 = row_mask(p, k0, d.n2, lf, vec);
-    r.m01 = row_mask(p + d.n2, k0, d.n2, lf, vec);
-    r.m10 = row_mask(p + static_cast<long long>(d.n1) * d.n2, k0, d.n2, lf, vec);
-    r.m11 = row_mask(p + static_cast<long long>(d.n1) * d.n2 + d.n2, k0, d.n2, lf, vec);
-    return r;
-}
-
-// The emission passes work row by row.  A cell row of the common volumes needs far fewer than 256 threads (64 for
-// 512 cells), and a row's work is a chain of dependent steps (field loads -> scan -> list -> vertex arithmetic), so a
-// block is cut into TEAMS of T = nq rounded up to a power of two (32 .. 256) threads, one listed row per team and
-// iteration, synchronised by the team's own named barrier: 4 x more rows in flight per block at 512^3.
-struct Team {
-    int T, id, tid, teams;                 // threads per team, team of this thread, thread within the team, teams per block
-    __device__ __forceinline__ void sync() const {
-        if (T == 32) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" :: "r"(id + 1), "r"(T) : "memory");
-    }
-};
-__device__ __forceinline__ Team make_team(int T) {
-    Team t;
-    t.T = T; t.id = threadIdx.x / T; t.tid = threadIdx.x - t.id * T; t.teams = SCAN_BLOCK / T;
-    return t;
-}
-// exclusive scan of one value per thread across a team; *total = the team's sum.  wsum: SCAN_BLOCK / 32 words of smem.
-__device__ __forceinline__ uint32_t team_exclusive_scan(const Team& tm, uint32_t v, uint32_t* total, uint32_t* wsum) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t inc = warp_inclusive_scan(v, lane);
-    if (tm.T == 32) {
-        *total = __shfl_sync(0xffffffffu, inc, 31);
-        return inc - v;
-    }
-    tm.sync();                              // wsum of the previous call consumed
-    if (lane == 31) wsum[warp] = inc;
-    tm.sync();
-    const int w0 = (tm.id * tm.T) >> 5, wn = tm.T >> 5;
-    uint32_t before = 0, all = 0;
-    for (int w = 0; w < wn; ++w) {
-        const uint32_t x = wsum[w0 + w];
-        all += x;
-        if (w0 + w < warp) before += x;
-    }
-    *total = all;
-    return before + inc - v;
-}
-
-// Pass 2 (rows): per listed row, the cases and table rows of its cells recomputed from the field, team scans of the
-// vertices its cells own and of their triangles -> every surface cell's record {first vertex number, table row}, and
-// one JOB per vertex / triangle written at the vertex's / triangle's own final index:
+// Pass 2 (rows): one WARP per listed row.  The classify pass left the row's surface cells as bits (one 32-bit word per lane
+// and step) and their table rows in the cell records, so nothing is recomputed from the field: a lane sums the vertices its
+// word's cells own and their triangles, a warp scan turns the sums into the first vertex / triangle number of every cell,
+// and each surface cell gets its record {first vertex number, table row} plus one JOB per vertex / triangle written at the
+// vertex's / triangle's own final index:
 //   vertex job   cell id << 4 | edge                 triangle job   cell id << 16 | table row << 4 | triangle
-// The arithmetic then runs in two flat passes, one thread per vertex / per triangle, at full occupancy (the row pass
-// is a short chain: loads -> scan -> stores).  Capacity checks make every pass safe to launch before the host knows
-// the counts (pifu_mc_extract): nothing is written past cap_verts / cap_faces.
-__global__ void __launch_bounds__(SCAN_BLOCK) emit_rows_kernel(const float* __restrict__ f, Dims d, double level, float lf, int vec,
-                                                               int T, const uint8_t* __restrict__ own,
-                                                               const uint32_t* __restrict__ voffs, const uint32_t* __restrict__ toffs,
-                                                               uint2* __restrict__ cellinfo, unsigned long long* __restrict__ vjobs,
-                                                               unsigned long long* __restrict__ tjobs, long long cap_verts,
-                                                               long long cap_faces, const uint32_t* __restrict__ active,
-                                                               const unsigned long long* __restrict__ n_active) {
-    __shared__ uint32_t wsum[2][SCAN_BLOCK / 32];
-    const Team tm = make_team(T);
+// The arithmetic then runs in two flat passes, one thread per vertex / per triangle.  The pass clears the bit words it
+// reads (the next extraction starts from zeros without a memset).  Capacity checks make every pass safe to launch before
+// the host knows the counts (pifu_mc_extract): nothing is written past cap_verts / cap_faces.
+__global__ void __launch_bounds__(256) emit_rows_kernel(Dims d, int W, const uint8_t* __restrict__ own,
+                                                        const uint32_t* __restrict__ voffs, const uint32_t* __restrict__ toffs,
+                                                        uint2* __restrict__ cellinfo, uint32_t* __restrict__ rowbits,
+                                                        unsigned long long* __restrict__ vjobs, unsigned long long* __restrict__ tjobs,
+                                                        long long cap_verts, long long cap_faces, const uint32_t* __restrict__ active,
+                                                        const unsigned long long* __restrict__ n_active) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = static_cast<long long>(gridDim.x) * 8;
     const long long na = static_cast<long long>(*n_active);
     const long long rows = static_cast<long long>(d.c0) * d.c1;
     const bool vfits = static_cast<long long>(voffs[rows]) <= cap_verts, tfits = static_cast<long long>(toffs[rows]) <= cap_faces;
-    for (long long a = static_cast<long long>(blockIdx.x) * tm.teams + tm.id; a < na; a += static_cast<long long>(gridDim.x) * tm.teams) {
+    for (long long a = blockIdx.x * 8LL + (threadIdx.x >> 5); a < na; a += warps) {
         const long long row = active[a];
         const int i = static_cast<int>(row / d.c1), j = static_cast<int>(row - static_cast<long long>(i) * d.c1);
+        const int zij = zero_mask(i + d.i0, j, 1);
         uint32_t vcarry = voffs[row], tcarry = toffs[row];
-        for (int q0 = 0; q0 < d.nq; q0 += tm.T) {
-            const int kq = q0 + tm.tid;
-            const int k0 = kq * CPT;
-            // surface cells of this lane's 8 cells: `any ^ all` of the eight corner bit-vectors (the rows hold a handful
-            // of them, so everything below walks set bits instead of the 8 cells)
-            uint32_t nv = 0, nt = 0, actm = 0;
-            RowMasks r = {0u, 0u, 0u, 0u};
-            if (kq < d.nq) {
-                r = load_masks(f, d, i, j, k0, lf, vec);
-                const uint32_t any = r.m00 | r.m01 | r.m10 | r.m11 | (r.m00 >> 1) | (r.m01 >> 1) | (r.m10 >> 1) | (r.m11 >> 1);
-                const uint32_t all = r.m00 & r.m01 & r.m10 & r.m11 & (r.m00 >> 1) & (r.m01 >> 1) & (r.m10 >> 1) & (r.m11 >> 1);
-                const int nc = d.c2 - k0 < CPT ? d.c2 - k0 : CPT;
-                actm = (any ^ all) & ((1u << nc) - 1u);
-                const int zij = zero_mask(i + d.i0, j, 1);
-#pragma unroll 1
-                for (uint32_t todo = actm; todo != 0u; todo &= todo - 1u) {
-                    const int m = __ffs(todo) - 1;
-                    const uint32_t cs = case_of(r.m00, r.m01, r.m10, r.m11, m);
-                    nv += __ldg(own + cs * 8 + (zij | (k0 + m == 0 ? 4 : 0)));
-                    if (i >= d.ghost) nt += MC_NTRI[cell_sub(f, d, level, i, j, k0 + m, cs)];
-                }
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t bits = 0;
+            if (w < W) {
+                bits = rowbits[row * W + w];
+                if (bits) rowbits[row * W + w] = 0u;
             }
-            uint32_t bv, bt;
-            uint32_t vb = vcarry + team_exclusive_scan(tm, nv, &bv, wsum[0]);
-            uint32_t tb = tcarry + team_exclusive_scan(tm, nt, &bt, wsum[1]);
+            uint32_t nv = 0, nt = 0;
 #pragma unroll 1
-            for (uint32_t todo = actm; todo != 0u; todo &= todo - 1u) {
-                const int m = __ffs(todo) - 1;
-                const int k = k0 + m;
-                const uint32_t cs = case_of(r.m00, r.m01, r.m10, r.m11, m);
-                const uint32_t sub = cell_sub(f, d, level, i, j, k, cs);       // (a table read; face tests only on ambiguous cells)
+            for (uint32_t todo = bits; todo != 0u; todo &= todo - 1u) {
+                const int k = 32 * w + __ffs(todo) - 1;
+                const uint32_t sub = cellinfo[row * d.c2 + k].y;
+                nv += __ldg(own + MC_SUB_CASE[sub] * 8 + (zij | (k == 0 ? 4 : 0)));
+                if (i >= d.ghost) nt += MC_NTRI[sub];
+            }
+            const uint32_t vinc = warp_inclusive_scan(nv, lane), tinc = warp_inclusive_scan(nt, lane);
+            uint32_t vb = vcarry + vinc - nv, tb = tcarry + tinc - nt;
+#pragma unroll 1
+            for (uint32_t todo = bits; todo != 0u; todo &= todo - 1u) {
+                const int k = 32 * w + __ffs(todo) - 1;
                 const unsigned long long cell = static_cast<unsigned long long>(row) * d.c2 + k;
-                cellinfo[cell] = make_uint2(vb, sub);
-                const int zm = zero_mask(i + d.i0, j, k);
+                const uint32_t sub = cellinfo[cell].y;
+                cellinfo[cell].x = vb;
+                const int zm = zij | (k == 0 ? 4 : 0);
                 const int nvc = MC_NVERT[sub];
                 for (int q = 0; q < nvc; ++q) {
                     const int e = MC_VERTS[sub][q];
@@ -521,8 +486,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) emit_rows_kernel(const float* __re
                         if (tfits) tjobs[tb] = (cell << 16) | (static_cast<unsigned long long>(sub) << 4) | t;
                 }
             }
-            vcarry += bv;
-            tcarry += bt;
+            vcarry += __shfl_sync(0xffffffffu, vinc, 31);
+            tcarry += __shfl_sync(0xffffffffu, tinc, 31);
         }
     }
 }
@@ -651,6 +616,16 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     const long long threads = static_cast<long long>(d.c0) * d.njg * d.nq;
     if (threads > 0x7fffffffLL || st->rows > 0xfffffff0LL) { set_error("marching cubes: volume too large for one launch"); return -1; }
     if (grow(&st->cellinfo, &st->cap_cells, cells)) return -1;
+    const int W = (d.c2 + 31) / 32;                              // bit words per cell row
+    {
+        const long long before = st->cap_rowbits;
+        if (grow(&st->rowbits, &st->cap_rowbits, st->rows * W)) return -1;
+        // the row pass clears what the classify pass sets; a fresh allocation, or an extraction that never reached its row
+        // pass, starts from a memset instead
+        if (st->cap_rowbits != before || st->rowbits_dirty)
+            PIFU_CUDA(cudaMemsetAsync(st->rowbits, 0, static_cast<size_t>(st->cap_rowbits) * sizeof(uint32_t), s));
+        st->rowbits_dirty = true;
+    }
     long long cap = st->cap_rows;
     if (grow(&st->vsums, &cap, st->rows + 1)) return -1;
     cap = st->cap_rows;
@@ -682,10 +657,11 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     if (!per_thread && (warps + 7) / 8 <= 0x7fffffffLL) {
         classify_warp_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(
             field, d, level_below(level), level, vec_ok(field, n2), static_cast<int>(nkt), static_cast<int>(nbands),
-            static_cast<int>(nchunks), WL, st->own, st->vsums, st->tsums);
+            static_cast<int>(nchunks), WL, st->own, st->vsums, st->tsums, st->cellinfo, st->rowbits, W);
     } else {
         classify_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(field, d, level_below(level), level,
-                                                                                    vec_ok(field, n2), st->own, st->vsums, st->tsums);
+                                                                                    vec_ok(field, n2), st->own, st->vsums, st->tsums,
+                                                                                    st->cellinfo, st->rowbits, W);
     }
     device_exclusive_scan(st->vsums, st->tsums, st->rows, st->partials, st->totals, s);
     active_rows_kernel<<<static_cast<unsigned>((st->rows + SCAN_BLOCK - 1) / SCAN_BLOCK), SCAN_BLOCK, 0, s>>>(
@@ -704,18 +680,14 @@ int mc_emit_async(pifu_ctx* c, double* verts, int* faces, float* normals, float*
                   long long cap_faces, cudaStream_t s) {
     McState* st = ctx_mc(c);
     const Dims d = make_dims(st);
-    const float lf = level_below(st->level);
-    const int vec = vec_ok(st->field, st->n[2]);
     if (grow(&st->vjobs, &st->cap_vjobs, cap_verts > 0 ? cap_verts : 1)) return -1;
     if (grow(&st->tjobs, &st->cap_tjobs, cap_faces > 0 ? cap_faces : 1)) return -1;
     // team = threads that share one cell row: a warp (shuffle scans, no barrier; a 512-cell row takes two chunks of
     // 32 x 8 cells with a carry) unless the row is long enough to keep a wider team busy
-    int T = 32;
-    while (T * 4 < d.nq && T < SCAN_BLOCK) T *= 2;
-    if (const char* e = getenv("PIFU_MC_TEAM")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) T = v; }
     const int sms = ctx_num_sms(c);
-    emit_rows_kernel<<<sms * 6, SCAN_BLOCK, 0, s>>>(st->field, d, st->level, lf, vec, T, st->own, st->vsums, st->tsums, st->cellinfo,
-                                                   st->vjobs, st->tjobs, cap_verts, faces ? cap_faces : 0, st->active, st->totals + 3);
+    emit_rows_kernel<<<sms * 8, 256, 0, s>>>(d, (d.c2 + 31) / 32, st->own, st->vsums, st->tsums, st->cellinfo, st->rowbits, st->vjobs,
+                                            st->tjobs, cap_verts, faces ? cap_faces : 0, st->active, st->totals + 3);
+    st->rowbits_dirty = false;                   // every word a surface cell set has been cleared by the pass just queued
     long long vb = (cap_verts + 255) / 256, fb = (cap_faces + 255) / 256;
     if (vb > sms * 32LL) vb = sms * 32LL;
     if (fb > sms * 32LL) fb = sms * 32LL;

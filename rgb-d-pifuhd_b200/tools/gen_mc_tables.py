@@ -249,6 +249,11 @@ def main():
     L.append("MC_TABLE_QUALIFIER unsigned short MC_SUB_BASE[256] = {%s};" % ",".join(str(b) for b in base))
     L.append("MC_TABLE_QUALIFIER unsigned char MC_FACE_CORNERS[6][4] = {%s};" %
              ",".join("{%d,%d,%d,%d}" % f for f in FACES))
+    case_of_row = []
+    for case in range(256):
+        case_of_row += [case] * ((base[case + 1] if case < 255 else nsub) - base[case])
+    L.append("// the case a table row belongs to")
+    L.append("MC_TABLE_QUALIFIER unsigned char MC_SUB_CASE[MC_NSUB] = {%s};" % ",".join(str(c) for c in case_of_row))
     L.append("MC_TABLE_QUALIFIER unsigned char MC_NTRI[MC_NSUB] = {%s};" % ",".join(str(len(t) // 3) for t, _ in rows))
     L.append("MC_TABLE_QUALIFIER unsigned char MC_NVERT[MC_NSUB] = {%s};" % ",".join(str(len(v)) for _, v in rows))
     body = ["{%s}" % ",".join(str(x) for x in t + [-1] * (3 * max_t - len(t))) for t, _ in rows]

@@ -1,7 +1,9 @@
 #!/bin/bash
-python -m pytest tests/test_octree_mc_gpu.py -m gpu -x -q 2>&1 | tail -3
-for wl in 12 8; do echo "WL=$wl"; PIFU_MC_WL=$wl python scripts/profile_mc.py 512 5; done
-PIFU_MC_TEAM=64 python scripts/profile_mc.py 512 5
+python -m pytest tests/test_octree_mc_gpu.py tests/test_fullsize_gpu.py tests/test_postprocess_gpu.py -m gpu -x -q 2>&1 | tail -3
+PIFU_MC_CLASSIFY=0 python -m pytest tests/test_octree_mc_gpu.py -m gpu -x -q -k "marching" 2>&1 | tail -2
+python scripts/profile_mc.py 512 5
+PIFU_MC_CLASSIFY=0 python scripts/profile_mc.py 512 3
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-    --log-file gpurun_out/r02_mc_v8_launches.csv python scripts/profile_mc.py 512 1 > /dev/null 2>&1
-python scripts/launch_summary.py gpurun_out/r02_mc_v8_launches.csv 40 | grep -E "total|classify|emit|scan|active"
+    --log-file gpurun_out/r02_mc_v9_launches.csv python scripts/profile_mc.py 512 1 > /dev/null 2>&1
+python scripts/launch_summary.py gpurun_out/r02_mc_v9_launches.csv 40 | grep -E "total|classify|emit|scan|active|Memset|memset"
+timeout 600 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_octree_mc_gpu.py -m gpu -x -q -k "marching" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Invalid" | head -5
