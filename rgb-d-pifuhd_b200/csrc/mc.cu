@@ -45,13 +45,15 @@ struct McState {
     const float* field = nullptr;
     long long rows = 0;                // cell rows = layers * c1
     uint2* cellinfo = nullptr;         // per cell, written for surface cells only: {first vertex number, table row}
-    uint32_t* rowbits = nullptr;       // per cell row, one bit per cell: surface cells (set by classify, read and cleared by the row pass)
+    unsigned long long* rowbits = nullptr;   // per cell row and 32 cells, one 64-bit word: bits 0-31 = the surface cells, bits 32-47 /
+                                       // 48-63 = the vertices they own / their triangles (added by classify - the contributors'
+                                       // bits are disjoint, so one atomicAdd carries all three - read and cleared by the row pass)
     long long cap_rowbits = 0;
     bool rowbits_dirty = true;         // a pass that set bits did not reach the pass that clears them
     uint32_t* vsums = nullptr;         // per row (+1): vertices created -> exclusive offsets, total at [rows]
     uint32_t* tsums = nullptr;         // per row (+1): triangles
     uint32_t* partials = nullptr;      // scan spine
-    uint8_t* own = nullptr;            // [256][8] vertices a cell of case cs creates, by border mask
+    uint32_t* own = nullptr;           // [256][8] what classify needs of a case in one load (own_table_kernel)
     unsigned long long* totals = nullptr;   // [4] device: vertices, triangles, ghost-layer vertices, listed rows
     uint32_t* active = nullptr;        // rows that create a vertex or a triangle
     unsigned long long* vjobs = nullptr;   // one job per vertex / triangle, at the vertex's / triangle's own index
@@ -85,19 +87,36 @@ __device__ __forceinline__ int zero_mask(int i, int j, int k) {
     return (i == 0 ? 1 : 0) | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0);
 }
 
-// own[cs * 8 + zmask]: number of lattice edges first used by a cell of case cs whose low faces
-// on the axes in zmask lie on the volume border (no earlier cell shares them).  The set of cut edges depends on the
-// case only, not on how the ambiguous faces resolve.
-__global__ void own_table_kernel(uint8_t* __restrict__ own) {
+// What the passes need of a table row / of a case, packed so that one load replaces a chain of dependent ones.
+//   CELL WORD (cellinfo[cell].y, written by classify, read by the row pass and by the faces pass):
+//     bits 0-9 table row | 10-13 triangles | 14-17 vertices the cell owns | 18-29 their edges, 4 bits each, in the
+//     row's vertex order - the edge field only for a cell none of whose low faces lies on the volume border (it owns at
+//     most edges 5, 6, 10 then); border cells go through the tables.
+//   own[cs * 8 + zmask]: the cell word of case cs when it has no ambiguous face, with bit 30 set when it has (the table
+//     row then comes from the face tests and the word from sub_word()).  zmask = low faces on the border (no earlier
+//     cell shares their edges); the NUMBER of owned edges depends on the case only, their order on the table row.
+constexpr uint32_t OWN_AMBIGUOUS = 1u << 30;
+__device__ __forceinline__ uint32_t sub_word(uint32_t row, int zm) {
+    uint32_t n = 0, edges = 0;
+    const int nv = MC_NVERT[row];
+    for (int q = 0; q < nv; ++q) {
+        const int e = MC_VERTS[row][q];
+        if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
+        if (n < 3) edges |= static_cast<uint32_t>(e) << (4 * n);
+        ++n;
+    }
+    return row | (static_cast<uint32_t>(MC_NTRI[row]) << 10) | (n << 14) | (edges << 18);
+}
+__global__ void own_table_kernel(uint32_t* __restrict__ own) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 256 * 8) return;
     const int cs = t >> 3, zm = t & 7;
-    const int row = MC_SUB_BASE[cs];
-    int n = 0;
-    const int nv = MC_NVERT[row];
-    for (int q = 0; q < nv; ++q) n += ((MC_EDGE_LOWMASK[MC_VERTS[row][q]] & ~zm) == 0) ? 1 : 0;
-    own[t] = static_cast<uint8_t>(n);
+    own[t] = sub_word(MC_SUB_BASE[cs], zm) | (MC_AMB[cs] ? OWN_AMBIGUOUS : 0u);
 }
+__device__ __forceinline__ uint32_t word_row(uint32_t w) { return w & 1023u; }
+__device__ __forceinline__ uint32_t word_tris(uint32_t w) { return (w >> 10) & 15u; }
+__device__ __forceinline__ uint32_t word_owned(uint32_t w) { return (w >> 14) & 15u; }
+__device__ __forceinline__ uint32_t word_edge(uint32_t w, int q) { return (w >> (18 + 4 * q)) & 15u; }
 
 // bit m set: value k0 + m of the field row at p is inside (v > lf; lf = the largest float <= level, so
 // (double)v > level  <=>  v > lf exactly); values past the end of the row read as outside
@@ -131,11 +150,6 @@ __device__ __forceinline__ uint32_t case_of(uint32_t m00, uint32_t m01, uint32_t
 // row pass stall on instruction fetch - ncu: 6.7 warps per issue waiting for instructions)
 __device__ __noinline__ uint32_t cell_sub_ambiguous(const float* __restrict__ f, int n1, int n2, double level, int i, int j, int k,
                                                     uint32_t cs);
-__device__ __forceinline__ uint32_t cell_sub(const float* __restrict__ f, const Dims& d, double level, int i, int j, int k,
-                                             uint32_t cs) {
-    if (MC_AMB[cs] == 0u) return MC_SUB_BASE[cs];
-    return cell_sub_ambiguous(f, d.n1, d.n2, level, i, j, k, cs);
-}
 __device__ __noinline__ uint32_t cell_sub_ambiguous(const float* __restrict__ f, int n1, int n2, double level, int i, int j, int k,
                                                     uint32_t cs) {
     const uint32_t amb = MC_AMB[cs];
@@ -158,11 +172,16 @@ __device__ __noinline__ uint32_t cell_sub_ambiguous(const float* __restrict__ f,
     return row;
 }
 
+// what a lane adds to the 64-bit word of 32 cells its surface cells fall into
+__device__ __forceinline__ unsigned long long word_record(uint32_t bits, uint32_t nv, uint32_t nt) {
+    return static_cast<unsigned long long>(bits) | (static_cast<unsigned long long>(nv) << 32) | (static_cast<unsigned long long>(nt) << 48);
+}
+
 // Pass 1.  Thread g -> layer i, row group jg (RPT rows), cell group kq (CPT cells).
 __global__ void __launch_bounds__(256) classify_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
-                                                       const uint8_t* __restrict__ own, uint32_t* __restrict__ vsums,
+                                                       const uint32_t* __restrict__ own, uint32_t* __restrict__ vsums,
                                                        uint32_t* __restrict__ tsums, uint2* __restrict__ cellinfo,
-                                                       uint32_t* __restrict__ rowbits, int W) {
+                                                       unsigned long long* __restrict__ rowbits, int W) {
     const long long g = blockIdx.x * 256LL + threadIdx.x;
     const long long total = static_cast<long long>(d.c0) * d.njg * d.nq;          // < 2^31 (checked by the host)
     if (g >= total) return;
@@ -201,15 +220,17 @@ __global__ void __launch_bounds__(256) classify_kernel(const float* __restrict__
         for (int m = 0; m < nc; ++m) {
             const uint32_t cs = case_of(m00, m01, m10, m11, m);
             if (cs == 0u || cs == 255u) continue;
-            const uint32_t o = __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k0 + m == 0 ? 4 : 0)));
+            const int zm = zi | (j == 0 ? 2 : 0) | (k0 + m == 0 ? 4 : 0);
+            uint32_t word = __ldg(own + cs * 8 + zm);
+            const uint32_t o = word_owned(word);
             nv += o;
             if (o == 0u && i < d.ghost) continue;       // a ghost-layer cell that numbers nothing: no output, no record, no bit
-            const uint32_t sub = cell_sub(f, d, level, i, j, k0 + m, cs);
-            if (i >= d.ghost) nt += MC_NTRI[sub];
-            cellinfo[row * d.c2 + k0 + m].y = sub;
+            if (word & OWN_AMBIGUOUS) word = sub_word(cell_sub_ambiguous(f, d.n1, d.n2, level, i, j, k0 + m, cs), zm);
+            if (i >= d.ghost) nt += word_tris(word);
+            cellinfo[row * d.c2 + k0 + m].y = word;
             bits |= 1u << ((k0 + m) & 31);
         }
-        if (bits) atomicOr(rowbits + row * W + (k0 >> 5), bits);
+        if (bits) atomicAdd(rowbits + row * W + (k0 >> 5), word_record(bits, nv, nt));
         if (nv) atomicAdd(vsums + row, nv);
         if (nt) atomicAdd(tsums + row, nt);
     }
@@ -292,9 +313,9 @@ __device__ __forceinline__ PlaneBits warp_plane_bits_full(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
-                                                            int nkt, int nbands, int nchunks, int WL, const uint8_t* __restrict__ own,
+                                                            int nkt, int nbands, int nchunks, int WL, const uint32_t* __restrict__ own,
                                                             uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums,
-                                                            uint2* __restrict__ cellinfo, uint32_t* __restrict__ rowbits, int W) {
+                                                            uint2* __restrict__ cellinfo, unsigned long long* __restrict__ rowbits, int W) {
     const int lane = threadIdx.x & 31;
     const long long wg = blockIdx.x * 8LL + (threadIdx.x >> 5);
     const int kt = static_cast<int>(wg % nkt);
@@ -336,7 +357,7 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
                 if (r != cur) {                                   // counts are flushed row by row
                     if (cur >= 0) {
                         const long long row = static_cast<long long>(i) * d.c1 + j0 + cur;
-                        if (bits) atomicOr(rowbits + row * W + (k0 >> 5), bits);
+                        if (bits) atomicAdd(rowbits + row * W + (k0 >> 5), word_record(bits, nv, nt));
                         if (nv) atomicAdd(vsums + row, nv);
                         if (nt) atomicAdd(tsums + row, nt);
                     }
@@ -348,18 +369,20 @@ __global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restr
                                     (static_cast<uint32_t>((hi.a >> s0) & 1ull) << 4) | (static_cast<uint32_t>((hi.b >> s0) & 1ull) << 5) |
                                     (static_cast<uint32_t>((hi.b >> s1) & 1ull) << 6) | (static_cast<uint32_t>((hi.a >> s1) & 1ull) << 7);
                 const int j = j0 + r, k = k0 + m;
-                const uint32_t o = __ldg(own + cs * 8 + (zi | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0)));
+                const int zm = zi | (j == 0 ? 2 : 0) | (k == 0 ? 4 : 0);
+                uint32_t word = __ldg(own + cs * 8 + zm);
+                const uint32_t o = word_owned(word);
                 nv += o;
                 // (a ghost-layer cell that numbers nothing leaves no record and no bit: every bit set belongs to a row with
                 // output, i.e. to a row the row pass visits and clears)
                 if (o == 0u && i < d.ghost) continue;
-                const uint32_t sub = cell_sub(f, d, level, i, j, k, cs);
-                if (i >= d.ghost) nt += MC_NTRI[sub];
-                cellinfo[(static_cast<long long>(i) * d.c1 + j) * d.c2 + k].y = sub;
+                if (word & OWN_AMBIGUOUS) word = sub_word(cell_sub_ambiguous(f, d.n1, d.n2, level, i, j, k, cs), zm);
+                if (i >= d.ghost) nt += word_tris(word);
+                cellinfo[(static_cast<long long>(i) * d.c1 + j) * d.c2 + k].y = word;
                 bits |= 1u << (k & 31);
             }
             const long long row = static_cast<long long>(i) * d.c1 + j0 + cur;
-            if (bits) atomicOr(rowbits + row * W + (k0 >> 5), bits);
+            if (bits) atomicAdd(rowbits + row * W + (k0 >> 5), word_record(bits, nv, nt));
             if (nv) atomicAdd(vsums + row, nv);
             if (nt) atomicAdd(tsums + row, nt);
         }
@@ -424,18 +447,35 @@ __global__ void __launch_bounds__(SCAN_BLOCK) active_rows_kernel(const uint32_t*
     if (on) active[base + r] = static_cast<uint32_t>(b);
 }
 
-// Pass 2 (rows): one WARP per listed row.  The classify pass left the row's surface cells as bits (one 32-bit word per lane
-// and step) and their table rows in the cell records, so nothing is recomputed from the field: a lane sums the vertices its
-// word's cells own and their triangles, a warp scan turns the sums into the first vertex / triangle number of every cell,
-// and each surface cell gets its record {first vertex number, table row} plus one JOB per vertex / triangle written at the
-// vertex's / triangle's own final index:
+// Pass 2 (rows): one WARP per listed row.  The classify pass left, per 32 cells of the row, one 64-bit word (the surface
+// cells as bits, the vertices they own, their triangles) and the cells' words in their records, so nothing is
+// recomputed from the field and no table is read for an interior cell.  First a lane takes one 64-bit word and a warp
+// scan turns the sums into the first vertex / triangle number of every 32 cells; then the warp walks the words that hold
+// surface cells, ONE LANE PER CELL: the 32 cell words arrive in one coalesced load (four such loads are in flight), a
+// second scan places the cells, and each surface cell gets its record {first vertex number, cell word} plus one JOB per
+// vertex / triangle written at the vertex's / triangle's own final index (neighbouring lanes write neighbouring jobs):
 //   vertex job   cell id << 4 | edge                 triangle job   cell id << 16 | table row << 4 | triangle
-// The arithmetic then runs in two flat passes, one thread per vertex / per triangle.  The pass clears the bit words it
-// reads (the next extraction starts from zeros without a memset).  Capacity checks make every pass safe to launch before
-// the host knows the counts (pifu_mc_extract): nothing is written past cap_verts / cap_faces.
-__global__ void __launch_bounds__(256) emit_rows_kernel(Dims d, int W, const uint8_t* __restrict__ own,
-                                                        const uint32_t* __restrict__ voffs, const uint32_t* __restrict__ toffs,
-                                                        uint2* __restrict__ cellinfo, uint32_t* __restrict__ rowbits,
+// (A lane per 32 cells walking its own cells was 2x slower on the bench's field, whose surface runs along axis 2 for
+// whole rows: up to 32 dependent loads in a row per lane - 84 -> 169 us when the tables left the loop and nothing hid
+// the loads any more.)  The arithmetic then runs in two flat passes, one thread per vertex / per triangle.  The pass
+// clears the bit words it reads (the next extraction starts from zeros without a memset).  Capacity checks make every
+// pass safe to launch before the host knows the counts (pifu_mc_extract): nothing is written past cap_verts / cap_faces.
+// vertex jobs of a cell with a low face on the volume border (it owns the border's edges too): through the tables
+__device__ __noinline__ void border_cell_vertices(unsigned long long cell, uint32_t sub, int zm, uint32_t vb,
+                                                  unsigned long long* __restrict__ vjobs) {
+    const int nvc = MC_NVERT[sub];
+    for (int q = 0; q < nvc; ++q) {
+        const int e = MC_VERTS[sub][q];
+        if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
+        vjobs[vb++] = (cell << 4) | static_cast<unsigned long long>(e);
+    }
+}
+
+constexpr int ROW_WORDS_IN_FLIGHT = 4;
+
+__global__ void __launch_bounds__(256) emit_rows_kernel(Dims d, int W, const uint32_t* __restrict__ voffs,
+                                                        const uint32_t* __restrict__ toffs, uint2* __restrict__ cellinfo,
+                                                        unsigned long long* __restrict__ rowbits,
                                                         unsigned long long* __restrict__ vjobs, unsigned long long* __restrict__ tjobs,
                                                         long long cap_verts, long long cap_faces, const uint32_t* __restrict__ active,
                                                         const unsigned long long* __restrict__ n_active) {
@@ -448,42 +488,64 @@ __global__ void __launch_bounds__(256) emit_rows_kernel(Dims d, int W, const uin
         const long long row = active[a];
         const int i = static_cast<int>(row / d.c1), j = static_cast<int>(row - static_cast<long long>(i) * d.c1);
         const int zij = zero_mask(i + d.i0, j, 1);
+        const bool faces = i >= d.ghost;
         uint32_t vcarry = voffs[row], tcarry = toffs[row];
         for (int w0 = 0; w0 < W; w0 += 32) {
             const int w = w0 + lane;
-            uint32_t bits = 0;
+            uint32_t bits = 0, nv = 0, nt = 0;
             if (w < W) {
-                bits = rowbits[row * W + w];
-                if (bits) rowbits[row * W + w] = 0u;
-            }
-            uint32_t nv = 0, nt = 0;
-#pragma unroll 1
-            for (uint32_t todo = bits; todo != 0u; todo &= todo - 1u) {
-                const int k = 32 * w + __ffs(todo) - 1;
-                const uint32_t sub = cellinfo[row * d.c2 + k].y;
-                nv += __ldg(own + MC_SUB_CASE[sub] * 8 + (zij | (k == 0 ? 4 : 0)));
-                if (i >= d.ghost) nt += MC_NTRI[sub];
+                const unsigned long long rec = rowbits[row * W + w];
+                if (rec) rowbits[row * W + w] = 0ull;
+                bits = static_cast<uint32_t>(rec);
+                nv = static_cast<uint32_t>(rec >> 32) & 0xffffu;
+                nt = static_cast<uint32_t>(rec >> 48);
             }
             const uint32_t vinc = warp_inclusive_scan(nv, lane), tinc = warp_inclusive_scan(nt, lane);
-            uint32_t vb = vcarry + vinc - nv, tb = tcarry + tinc - nt;
+            const uint32_t vb = vcarry + vinc - nv, tb = tcarry + tinc - nt;
+            uint32_t mask = __ballot_sync(0xffffffffu, bits != 0u);          // the words that hold surface cells
 #pragma unroll 1
-            for (uint32_t todo = bits; todo != 0u; todo &= todo - 1u) {
-                const int k = 32 * w + __ffs(todo) - 1;
-                const unsigned long long cell = static_cast<unsigned long long>(row) * d.c2 + k;
-                const uint32_t sub = cellinfo[cell].y;
-                cellinfo[cell].x = vb;
-                const int zm = zij | (k == 0 ? 4 : 0);
-                const int nvc = MC_NVERT[sub];
-                for (int q = 0; q < nvc; ++q) {
-                    const int e = MC_VERTS[sub][q];
-                    if ((MC_EDGE_LOWMASK[e] & ~zm) != 0) continue;
-                    if (vfits) vjobs[vb] = (cell << 4) | static_cast<unsigned long long>(e);
-                    ++vb;
+            while (mask != 0u) {
+                int src[ROW_WORDS_IN_FLIGHT];
+                uint32_t word[ROW_WORDS_IN_FLIGHT];
+                unsigned long long cell[ROW_WORDS_IN_FLIGHT];
+#pragma unroll
+                for (int u = 0; u < ROW_WORDS_IN_FLIGHT; ++u) {
+                    src[u] = -1;
+                    if (mask != 0u) { src[u] = __ffs(mask) - 1; mask &= mask - 1u; }
+                    const uint32_t b = __shfl_sync(0xffffffffu, bits, src[u] < 0 ? 0 : src[u]);
+                    cell[u] = static_cast<unsigned long long>(row) * d.c2 + 32 * (w0 + (src[u] < 0 ? 0 : src[u])) + lane;
+                    word[u] = 0u;
+                    if (src[u] >= 0 && ((b >> lane) & 1u)) word[u] = cellinfo[cell[u]].y;       // (a cell word is never 0)
                 }
-                if (i >= d.ghost) {
-                    const uint32_t n = MC_NTRI[sub];
-                    for (uint32_t t = 0; t < n; ++t, ++tb)
-                        if (tfits) tjobs[tb] = (cell << 16) | (static_cast<unsigned long long>(sub) << 4) | t;
+#pragma unroll
+                for (int u = 0; u < ROW_WORDS_IN_FLIGHT; ++u) {
+                    if (src[u] < 0) break;                                    // warp-uniform
+                    const uint32_t wv = __shfl_sync(0xffffffffu, vb, src[u]), wt = __shfl_sync(0xffffffffu, tb, src[u]);
+                    const uint32_t n = word_owned(word[u]), t = faces ? word_tris(word[u]) : 0u;
+                    const uint32_t both = n | (t << 16);                      // a word's sums stay below 2^16 (32 x 12, 32 x 10)
+                    const uint32_t exc = warp_inclusive_scan(both, lane) - both;
+                    if (word[u] != 0u) {
+                        const uint32_t vpos = wv + (exc & 0xffffu), tpos = wt + (exc >> 16);
+                        const uint32_t sub = word_row(word[u]);
+                        cellinfo[cell[u]].x = vpos;
+                        const int k = 32 * (w0 + src[u]) + lane;
+                        const int zm = zij | (k == 0 ? 4 : 0);
+                        if (vfits) {
+                            if (zm == 0) {                            // interior cell: its (at most 3) owned edges are in the word
+#pragma unroll
+                                for (uint32_t q = 0; q < 3; ++q)
+                                    if (q < n) vjobs[vpos + q] = (cell[u] << 4) | word_edge(word[u], q);
+                            } else {
+                                border_cell_vertices(cell[u], sub, zm, vpos, vjobs);
+                            }
+                        }
+                        if (tfits) {
+                            const unsigned long long base = (cell[u] << 16) | (static_cast<unsigned long long>(sub) << 4);
+#pragma unroll
+                            for (uint32_t q = 0; q < MC_MAX_TRIS; ++q)
+                                if (q < t) tjobs[tpos + q] = base | q;
+                        }
+                    }
                 }
             }
             vcarry += __shfl_sync(0xffffffffu, vinc, 31);
@@ -528,11 +590,16 @@ __device__ __forceinline__ int vertex_id(const Dims& d, const uint2* __restrict_
     const uint2 info = cellinfo[(static_cast<long long>(oi) * d.c1 + oj) * d.c2 + ok];
     const int zm = zero_mask(oi + d.i0, oj, ok);
     int r = 0;
-    const int nvc = MC_NVERT[info.y];
-    for (int q = 0; q < nvc; ++q) {
-        const int e2 = MC_VERTS[info.y][q];
-        if (e2 == oe) break;
-        r += ((MC_EDGE_LOWMASK[e2] & ~zm) == 0) ? 1 : 0;
+    if (zm == 0) {                                                // interior owner: rank of the edge inside its word
+        r = word_edge(info.y, 0) == static_cast<uint32_t>(oe) ? 0 : word_edge(info.y, 1) == static_cast<uint32_t>(oe) ? 1 : 2;
+    } else {
+        const uint32_t sub = word_row(info.y);
+        const int nvc = MC_NVERT[sub];
+        for (int q = 0; q < nvc; ++q) {
+            const int e2 = MC_VERTS[sub][q];
+            if (e2 == oe) break;
+            r += ((MC_EDGE_LOWMASK[e2] & ~zm) == 0) ? 1 : 0;
+        }
     }
     return static_cast<int>(info.x) + r;
 }
@@ -601,7 +668,7 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     int launches = 0;
     if (!st) st = new McState();
     if (!st->own) {
-        PIFU_CUDA(cudaMalloc(&st->own, 256 * 8));
+        PIFU_CUDA(cudaMalloc(&st->own, 256 * 8 * sizeof(uint32_t)));
         own_table_kernel<<<8, 256, 0, s>>>(st->own);
         ++launches;
     }
@@ -623,7 +690,7 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
         // the row pass clears what the classify pass sets; a fresh allocation, or an extraction that never reached its row
         // pass, starts from a memset instead
         if (st->cap_rowbits != before || st->rowbits_dirty)
-            PIFU_CUDA(cudaMemsetAsync(st->rowbits, 0, static_cast<size_t>(st->cap_rowbits) * sizeof(uint32_t), s));
+            PIFU_CUDA(cudaMemsetAsync(st->rowbits, 0, static_cast<size_t>(st->cap_rowbits) * sizeof(unsigned long long), s));
         st->rowbits_dirty = true;
     }
     long long cap = st->cap_rows;
@@ -685,7 +752,7 @@ int mc_emit_async(pifu_ctx* c, double* verts, int* faces, float* normals, float*
     // team = threads that share one cell row: a warp (shuffle scans, no barrier; a 512-cell row takes two chunks of
     // 32 x 8 cells with a carry) unless the row is long enough to keep a wider team busy
     const int sms = ctx_num_sms(c);
-    emit_rows_kernel<<<sms * 8, 256, 0, s>>>(d, (d.c2 + 31) / 32, st->own, st->vsums, st->tsums, st->cellinfo, st->rowbits, st->vjobs,
+    emit_rows_kernel<<<sms * 8, 256, 0, s>>>(d, (d.c2 + 31) / 32, st->vsums, st->tsums, st->cellinfo, st->rowbits, st->vjobs,
                                             st->tjobs, cap_verts, faces ? cap_faces : 0, st->active, st->totals + 3);
     st->rowbits_dirty = false;                   // every word a surface cell set has been cleared by the pass just queued
     long long vb = (cap_verts + 255) / 256, fb = (cap_faces + 255) / 256;
