@@ -312,12 +312,13 @@ __device__ __forceinline__ PlaneBits warp_plane_bits_full(const float* __restric
     return pb;
 }
 
-__global__ void __launch_bounds__(256) classify_warp_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
+template <int WPB>                     // warps per block
+__global__ void __launch_bounds__(32 * WPB) classify_warp_kernel(const float* __restrict__ f, Dims d, float lf, double level, int vec,
                                                             int nkt, int nbands, int nchunks, int WL, const uint32_t* __restrict__ own,
                                                             uint32_t* __restrict__ vsums, uint32_t* __restrict__ tsums,
                                                             uint2* __restrict__ cellinfo, unsigned long long* __restrict__ rowbits, int W) {
     const int lane = threadIdx.x & 31;
-    const long long wg = blockIdx.x * 8LL + (threadIdx.x >> 5);
+    const long long wg = blockIdx.x * static_cast<long long>(WPB) + (threadIdx.x >> 5);
     const int kt = static_cast<int>(wg % nkt);
     const long long rest = wg / nkt;
     const int band = static_cast<int>(rest % nbands), ch = static_cast<int>(rest / nbands);
@@ -707,12 +708,6 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     PIFU_CUDA(cudaMemsetAsync(st->totals, 0, 4 * sizeof(unsigned long long), s));
     static const bool per_thread = getenv("PIFU_MC_CLASSIFY") && atoi(getenv("PIFU_MC_CLASSIFY")) == 0;      // A/B measurements
     const long long nkt = (d.c2 + 127) / 128, nbands = (d.c1 + WR - 1) / WR;
-    static int resident = 0;                       // blocks of the classify kernel an SM holds
-    if (resident == 0) {
-        PIFU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, classify_warp_kernel, 256, 0));
-        if (resident < 1) resident = 1;
-    }
-    (void)resident;
     // layers per tile.  Measured at 512^3 (whole extraction): 8 layers 0.369 ms, 12: 0.385, 16: 0.427, 24: 0.468; one wave
     // of equal 29-layer tiles was twice as slow in the classify pass (the serial chain per warp grows faster than the
     // tail shrinks).  The pass then reads 3.6 TB/s; torch.max over the same volume reads 4.5 TB/s on this part.
@@ -721,10 +716,14 @@ int mc_count_async(pifu_ctx* c, const float* field, int n0, int n1, int n2, doub
     if (WL > d.c0) WL = d.c0;
     const long long nchunks = (d.c0 + WL - 1) / WL;
     const long long warps = nkt * nbands * nchunks;
-    if (!per_thread && (warps + 7) / 8 <= 0x7fffffffLL) {
-        classify_warp_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(
-            field, d, level_below(level), level, vec_ok(field, n2), static_cast<int>(nkt), static_cast<int>(nbands),
-            static_cast<int>(nchunks), WL, st->own, st->vsums, st->tsums, st->cellinfo, st->rowbits, W);
+    static const int wpb = getenv("PIFU_MC_WPB") ? atoi(getenv("PIFU_MC_WPB")) : 2;            // A/B: 8 -> 0.340 / 0.353 ms, 4 -> 0.337 / 0.332, 2 -> 0.333 / 0.333 (bench field)
+    if (!per_thread && (warps + 1) / 2 <= 0x7fffffffLL) {
+#define PIFU_CLASSIFY(WPB)                                                                                              \
+        classify_warp_kernel<WPB><<<static_cast<unsigned>((warps + WPB - 1) / WPB), 32 * WPB, 0, s>>>(                   \
+            field, d, level_below(level), level, vec_ok(field, n2), static_cast<int>(nkt), static_cast<int>(nbands),  \
+            static_cast<int>(nchunks), WL, st->own, st->vsums, st->tsums, st->cellinfo, st->rowbits, W)
+        if (wpb == 2) PIFU_CLASSIFY(2); else if (wpb == 4) PIFU_CLASSIFY(4); else PIFU_CLASSIFY(8);
+#undef PIFU_CLASSIFY
     } else {
         classify_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(field, d, level_below(level), level,
                                                                                     vec_ok(field, n2), st->own, st->vsums, st->tsums,

@@ -21,3 +21,15 @@ print("narrow", m["octree_hybrid_narrow_band"]["latency_ms"], m["octree_hybrid_n
 print("tail", m["octree"]["gen_mesh_tail"], m["octree"]["postprocess"])
 print("cpu", m["cpu_baseline_ms"], "enc", d["encoders"]["frames_256_octree"]["frames_per_s"])
 PY
+# marching cubes, dominant kernel: DRAM traffic and issue utilisation of one launch on the bench's octree field
+ncu --set full --clock-control none -k regex:classify_warp_kernel -c 1 -o gpurun_out/r02_mc_classify -f python scripts/profile_mesh.py 512 octree > /dev/null 2>&1
+ncu -i gpurun_out/r02_mc_classify.ncu-rep --page raw --csv 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin))
+h,u,v=rows[0],rows[1],rows[2]
+want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','dram__throughput.avg.pct_of_peak_sustained_elapsed','sm__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','l1tex__t_sector_hit_rate.pct','lts__t_sector_hit_rate.pct']
+for w in want:
+    for i,n in enumerate(h):
+        if n==w: print(w, v[i], u[i])
+" | tee gpurun_out/r02_mc_classify_ncu.txt
+rm -f gpurun_out/r02_mc_classify.ncu-rep
