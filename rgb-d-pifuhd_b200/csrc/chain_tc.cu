@@ -77,8 +77,7 @@ constexpr bool SCOUT = CHAIN_SCOUT != 0;
 
 constexpr int NUM_THREADS = 384;
 constexpr int ALU_WARP0 = 4;
-constexpr int ALU_THREADS = 256;
-constexpr int ALU_WARPS = 8;
+constexpr int ALU_WARPS = 8;           // 256 threads: the count in alu_bar()
 
 __device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }
 __device__ __forceinline__ void alu_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }

@@ -7,7 +7,6 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pifu_b200 import synthetic as syn   # noqa: E402
 import bench                              # noqa: E402
 
 torch.set_grad_enabled(False)

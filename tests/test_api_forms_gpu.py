@@ -1,7 +1,6 @@
 """GPU: the call forms and state the reference API exposes beyond the single-view query
 (`PIFuMRNet.py:119-186` multi-crop form, batches, `calc_normal` of both nets, perspective),
 checked per item against the CPU oracle and for the reference's tensor shapes / stacking order."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,5 @@
 """CPU, gloo, world_size 2: the host-side sharding logic of the N>1 path."""
 import os
-import sys
 
 import numpy as np
 import pytest
@@ -8,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helpers import ROOT, orc
+from helpers import orc
 
 from pifu_b200 import dist as pdist
 
@@ -98,7 +97,6 @@ def _worker(rank, world, port, out):
 
 
 def test_two_rank_sharding_matches_single(tmp_path):
-    from pifu_b200 import mesh_util
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(2, 29571, out), nprocs=2, join=True)
     got = torch.load(out)
@@ -226,7 +224,6 @@ def test_sharded_mesh_equals_whole_volume(tmp_path, world, res, kind):
     gives bit for bit the mesh of a sequential traversal of the whole volume - for the dense field and for the
     slab-sharded octree (own planes + margin, no boundary exchange: `dist.sharded_octree_slab`)."""
     from oracle import mc_oracle
-    from pifu_b200 import mesh_util
     out = str(tmp_path / "mesh.pt")
     mp.spawn(_mesh_worker, args=(world, 29573 + world + (7 if kind else 0), out, res, kind), nprocs=world, join=True)
     got = torch.load(out)

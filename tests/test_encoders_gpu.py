@@ -3,7 +3,6 @@ replay must reproduce the plain eager fp32 forward of the same module (the refer
 float32 round-off; TF32 / bf16 are opt-in and only checked for sanity.  Full-size encoders of the reference
 configuration (`options.py` defaults via `train.py:102-120`): coarse 4-stack hourglass on 512^2, fine 1-stack
 'no_down' on 1024^2."""
-import numpy as np
 import pytest
 import torch
 

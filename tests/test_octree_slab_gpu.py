@@ -3,7 +3,6 @@ same device - walk the levels in lock step exactly as `dist.sharded_octree_slab`
 local planes without exchange, fine levels through the concatenated frontier), with an analytic field as eval_func.
 Every rank's planes [own - 1, own + 2) must equal the single-volume device octree bit for bit, and the slab meshes
 must assemble into the whole-volume mesh."""
-import numpy as np
 import pytest
 import torch
 
