@@ -134,6 +134,47 @@ def test_oracle_derives_the_table_rows_independently():
     assert len(seen) > 600                                  # of 656 rows; the rest need value patterns that cannot occur
 
 
+def test_table_properties_the_kernels_pack_on():
+    """csrc/mc.cu packs a surface cell into one 32-bit word (table row 10 bits, triangles 4, owned vertices 4, up to three
+    owned edges 4 bits each) and the row pass writes an interior cell's vertex jobs from that word alone.  That is sound
+    only if, for every table row: the row index fits 10 bits, the triangle and vertex counts fit 4, and a cell none of
+    whose low faces lies on the volume border is the first user of at most the three edges at its high corner (5, 6, 10:
+    the edges whose LOWMASK is 0), which all appear in the row's vertex list when the case cuts them."""
+    import os
+    import re
+    from helpers import ROOT
+    text = open(os.path.join(ROOT, "rgb-d-pifuhd_b200", "csrc", "mc_tables.h")).read()
+
+    def flat(name):
+        m = re.search(name + r"\[[^\]]*\](?:\[[^\]]*\])? = \{(.*?)\};", text, re.S)
+        return [int(x) for x in re.findall(r"-?\d+", m.group(1))]
+    nsub = int(re.search(r"#define MC_NSUB (\d+)", text).group(1))
+    max_t = int(re.search(r"#define MC_MAX_TRIS (\d+)", text).group(1))
+    assert nsub <= 1024 and max_t <= 15
+    ntri, nvert, low = flat("MC_NTRI"), flat("MC_NVERT"), flat("MC_EDGE_LOWMASK")
+    verts = np.array(flat("MC_VERTS")).reshape(nsub, -1)
+    sub_case = flat("MC_SUB_CASE")
+    assert len(ntri) == nsub and len(nvert) == nsub and len(low) == 12 and len(sub_case) == nsub
+    assert [e for e in range(12) if low[e] == 0] == [5, 6, 10]
+    g = _generator()
+    for r in range(nsub):
+        if sub_case[r] in (0, 255):                             # no surface: never packed
+            assert ntri[r] == 0 and nvert[r] == 0
+            continue
+        assert 1 <= ntri[r] <= max_t and 3 <= nvert[r] <= 12    # (a surface cell's word is never 0: the row pass relies on it)
+        vs = [int(e) for e in verts[r][:nvert[r]]]
+        assert len(set(vs)) == len(vs) and all(0 <= e < 12 for e in vs)
+        # the row's vertices are exactly the edges its case cuts (so the owned COUNT depends on the case only)
+        case = sub_case[r]
+        cut = sorted(e for e in range(12) if ((case >> g.EDGES[e][0]) & 1) != ((case >> g.EDGES[e][1]) & 1))
+        assert sorted(vs) == cut, (r, case)
+        for zm in range(8):
+            owned = [e for e in vs if (low[e] & ~zm) == 0]
+            assert len(owned) <= 12
+            if zm == 0:
+                assert len(owned) <= 3 and set(owned) <= {5, 6, 10}
+
+
 def test_face_test_is_the_asymptotic_decider():
     """One ambiguous face, bilinear values: the inside corners are joined across the face exactly when the
     interpolant's saddle value is inside (Lewiner's test_face / Nielson-Hamann)."""
