@@ -1,4 +1,6 @@
 """Build libpifu_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import contextlib
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -41,12 +43,29 @@ def up_to_date():
         return False
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """One builder at a time: the ranks of a torchrun launch may all find the library missing at once."""
+    fd = os.open(LIB + ".lock", os.O_CREAT | os.O_RDWR, 0o644)
+    try:
+        fcntl.flock(fd, fcntl.LOCK_EX)
+        yield
+    finally:
+        fcntl.flock(fd, fcntl.LOCK_UN)
+        os.close(fd)
+
+
 def build(force=False, verbose=False):
     """Compile every .cu into objects (parallel) and link the shared library."""
+    with _build_lock():
+        return _build_locked(force, verbose)
+
+
+def _build_locked(force, verbose):
     stamp = LIB + ".stamp"
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
+        return LIB                                  # (also: another process built it while this one waited for the lock)
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
@@ -65,10 +84,12 @@ def build(force=False, verbose=False):
         if verbose and out.strip():
             print(out)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout.decode())
+    os.replace(tmp, LIB)                            # atomic: a process that mapped the old file keeps it
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB
