@@ -204,3 +204,18 @@ def test_torus_euler_characteristic():
     rkey = e[:, 1].astype(np.int64) * len(v) + e[:, 0]
     assert np.array_equal(np.sort(key), np.sort(rkey)) and len(np.unique(key)) == len(key)
     assert len(v) - len(key) // 2 + len(f) == 0              # genus 1
+
+
+@pytest.mark.parametrize("name", ["random14", "blob24", "ragged_9_12_17"])
+def test_oracle_reproduces_committed_fixture(name):
+    """tests/golden/mc_rule.npz (oracle/make_golden_mc.py) pins the rule: the oracle built here must give the committed
+    meshes bit for bit (float64 positions included: -ffp-contract=off).  The GPU suite compares the kernels with the same
+    file.  (Not a scikit-image fixture - that package is absent; see the header of the generating script.)"""
+    import hashlib
+    from helpers import golden
+    g = golden("mc_rule.npz")
+    v, f, n, val = mc_oracle.marching_cubes(g[name + "_volume"], float(g[name + "_level"]))[:4]
+    assert np.array_equal(f, g[name + "_faces"])
+    assert np.array_equal(v, g[name + "_verts"])
+    assert hashlib.sha256(np.ascontiguousarray(n).tobytes()).hexdigest() == str(g[name + "_normals_sha256"])
+    assert hashlib.sha256(np.ascontiguousarray(val).tobytes()).hexdigest() == str(g[name + "_values_sha256"])

@@ -162,6 +162,19 @@ def test_marching_cubes_bit_exact(vol):
     assert np.abs(normals.cpu().numpy() - rn).max() < 1e-6
 
 
+@pytest.mark.parametrize("name", ["random14", "blob24", "ragged_9_12_17"])
+def test_marching_cubes_committed_fixture(name):
+    """The kernels against the COMMITTED meshes of tests/golden/mc_rule.npz (oracle/make_golden_mc.py; pinned on CPU by
+    tests/test_mc_oracle.py::test_oracle_reproduces_committed_fixture) - no oracle code runs here."""
+    from pifu_b200 import get_engine
+    g = golden("mc_rule.npz")
+    vol, level = g[name + "_volume"], float(g[name + "_level"])
+    verts, faces, normals, values = get_engine("cuda").marching_cubes(torch.from_numpy(vol).cuda(), level)
+    assert np.array_equal(faces.cpu().numpy(), g[name + "_faces"])
+    assert np.array_equal(verts.cpu().numpy(), g[name + "_verts"])
+    assert hashlib.sha256(values.cpu().numpy().tobytes()).hexdigest() == str(g[name + "_values_sha256"])
+
+
 def test_marching_cubes_no_surface():
     from pifu_b200 import get_engine
     eng = get_engine("cuda")
