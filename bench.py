@@ -697,8 +697,7 @@ def main():
         netMR.im_feat_list = [feat_f_host.to(dev, non_blocking=True)]
         eng.sync_features(0, netG.im_feat_list[-1])
         eng.sync_features(1, netMR.im_feat_list[-1])
-        eng.eval_grid(2, res, calib[0], id_begin=id_b, id_end=id_e, out=slab)
-        field_host.copy_(slab, non_blocking=True)
+        eng.eval_grid_host(2, res, calib[0], field_host, id_begin=id_b, id_end=id_e)
 
     e2e_step()
     barrier()

@@ -51,6 +51,7 @@ class Engine:
         self._keep = {}
         self._hold = {}
         self._mc_hint = {}
+        self._copy_stream = None
         self.precision = 0
         import os
         if os.environ.get("PIFU_PRECISION"):
@@ -238,6 +239,35 @@ class Engine:
         _lib.check(self.lib.pifu_eval_grid(self.h, levels, R0, R1, R2, id_begin, id_end, c16, inv16,
                                            ctypes.c_void_p(out.data_ptr()), _stream(self.device_index)))
         return out
+
+    def eval_grid_host(self, levels, res, calib, out_host, id_begin=0, id_end=None, launches_per_piece=4):
+        """eval_grid with the field delivered to HOST memory (`out_host`: pinned float32 tensor of id_end - id_begin
+        entries; what `mesh_util.py:74` does per chunk with `.cpu()`).  The id range is evaluated in pieces of whole kernel
+        launches (the lattice form cuts a call into launches of 32 x SM-count columns, api.cu) and a piece travels on a
+        copy stream while the next one is computed, so only the last piece's transfer is exposed.  The calling stream
+        waits for the copies: work queued after this call sees `out_host` complete (a host read still needs a sync)."""
+        R0, R1, R2 = (res, res, res) if np.isscalar(res) else res
+        id_end = R0 * R1 * R2 if id_end is None else id_end
+        n = id_end - id_begin
+        if out_host.numel() != n or out_host.dtype != torch.float32 or out_host.device.type != "cpu":
+            raise ValueError("out_host must be a float32 host tensor of %d entries" % n)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        piece = 32 * sms * R2 * max(1, int(launches_per_piece))
+        dev = torch.empty(n, device=self.device, dtype=torch.float32)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs, main = self._copy_stream, torch.cuda.current_stream(self.device)
+        flat = out_host.view(-1)
+        for a in range(0, n, piece):
+            b = min(a + piece, n)
+            self.eval_grid(levels, res, calib, id_begin + a, id_begin + b, out=dev[a:b])
+            done = torch.cuda.Event()
+            done.record(main)
+            cs.wait_event(done)
+            with torch.cuda.stream(cs):
+                flat[a:b].copy_(dev[a:b], non_blocking=True)
+        main.wait_stream(cs)
+        return out_host
 
     def eval_lattice_ids(self, levels, res, ids, calib):
         R0, R1, R2 = (res, res, res) if np.isscalar(res) else res

@@ -73,6 +73,24 @@ def test_chain_vs_oracle(setup, R, rng, calib_name):
     assert np.abs(out - layer).max() < OCC_TOL
 
 
+def test_eval_grid_host_delivery(setup):
+    """Engine.eval_grid_host (field to pinned host memory, copies of finished pieces overlapping the next piece's
+    kernels) returns exactly what eval_grid + .cpu() returns - whole volume, a ragged sub-range, and a range shorter
+    than one piece."""
+    _, _, _, eng = setup
+    calib = syn.default_calib()
+    R = (80, 64, 256)                                   # 5 120 columns: more than one launch (4 736 columns on 148 SMs)
+    total = R[0] * R[1] * R[2]
+    for a, b, lpp in ((0, total, 1), (256 * 13, total - 256 * 7, 1), (0, 256 * 40, 4)):
+        want = eng.eval_grid(2, R, calib[0], id_begin=a, id_end=b).cpu()
+        host = torch.full((b - a,), -1.0).pin_memory()
+        got = eng.eval_grid_host(2, R, calib[0], host, id_begin=a, id_end=b, launches_per_piece=lpp)
+        torch.cuda.synchronize()
+        assert got is host and torch.equal(host, want)
+    with pytest.raises(ValueError):
+        eng.eval_grid_host(2, R, calib[0], torch.empty(5), id_begin=0, id_end=256)
+
+
 def test_chain_not_taken_when_z_mixes_into_xy(setup):
     """A calibration that rotates z into x makes the samples vary along the column: the dense
     path must fall back to the per-layer kernels and still match the oracle."""
