@@ -19,7 +19,7 @@ class PIFuMRNet(BasePIFuNet, EncoderHost):
     explicitly, `reconstruction.py:285-286`), plus ``image_filter`` for the fine encoder ('auto': the
     'no_down' hourglass of `PIFuMRNet.py:38-39`; a module; or None, see PIFuNetwNML)."""
 
-    def __init__(self, opt, netG, projection_mode="otthogonal", criteria=None, image_filter="auto"):
+    def __init__(self, opt, netG, projection_mode="otthogonal", criteria={"occ": nn.MSELoss()}, image_filter="auto"):  # noqa: B006 (the reference's defaults, typo included: `PIFuMRNet.py:19-24`)
         super().__init__(projection_mode=projection_mode, criteria=criteria)
         self.name = "hg_pifu"
         self.opt = opt

@@ -69,7 +69,7 @@ class PIFuNetwNML(BasePIFuNet, EncoderHost):
     module returning ``(feature_list, normx)`` - e.g. the reference's own `Filter` - is used as given;
     None leaves the net without encoder (feature maps are then assigned to `im_feat_list` directly)."""
 
-    def __init__(self, opt, projection_mode="orthogonal", criteria=None, image_filter="auto"):
+    def __init__(self, opt, projection_mode="orthogonal", criteria={"occ": nn.MSELoss()}, image_filter="auto"):  # noqa: B006 (the reference's default, `PIFuNetwNML.py:19-23`)
         super().__init__(projection_mode=projection_mode, criteria=criteria)
         self.name = "hg_pifu"
         self.opt = opt
