@@ -51,3 +51,30 @@ def test_signature_matches_reference(name):
     for p in ours[len(ref):]:                                            # additions must not change how old calls bind
         assert p.default is not inspect.Parameter.empty or p.kind in (p.VAR_KEYWORD, p.VAR_POSITIONAL), \
             "%s: added parameter %r has no default" % (name, p.name)
+
+
+def test_attributes_the_callers_read():
+    """What `reconstruction.py` reads off the nets (`:37-40` netF / netB / nmlF / nmlB, `:69` nmls, `:113,165,182`
+    projection, `:285-292` nn.Module life cycle) exists on the mirror with the reference's meaning."""
+    import torch
+    from torch import nn
+    from pifu_b200 import config
+    from pifu_b200.BasePIFuNet import orthogonal, perspective
+    from pifu_b200.PIFuMRNet import PIFuMRNet
+    from pifu_b200.PIFuNetwNML import PIFuNetwNML
+    netG = PIFuNetwNML(config.coarse_opt(), "orthogonal", image_filter=None)
+    netMR = PIFuMRNet(config.fine_opt(), netG, "orthogonal", image_filter=None)
+    assert isinstance(netG, nn.Module) and isinstance(netMR, nn.Module) and netMR.netG is netG
+    for a in ("netF", "netB", "nmlF", "nmlB", "phi", "im_feat_list", "opt", "projection", "preds", "mlp", "training"):
+        assert hasattr(netG, a), a
+    for a in ("nmls", "im_feat_list", "opt", "projection", "preds", "preds_interm", "preds_low", "mlp", "training"):
+        assert hasattr(netMR, a), a
+    assert netMR.projection is orthogonal and netG.projection is orthogonal
+    assert PIFuMRNet(config.fine_opt(), netG, image_filter=None).projection is perspective   # the reference's default typo (`PIFuMRNet.py:22`)
+    assert list(netG.criteria) == ["occ"]
+    netMR.eval()
+    assert not netMR.training and not netG.training
+    sd = netMR.state_dict()                                              # load_state_dict round trip (`reconstruction.py:290-292`)
+    netMR.load_state_dict(sd)
+    assert any(k.startswith("netG.mlp.filters.") for k in sd) and any(k.startswith("mlp.filters.") for k in sd)
+    assert torch.is_tensor(sd["mlp.filters.0.weight"])
