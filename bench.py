@@ -51,6 +51,17 @@ def ncu_traffic(kernel):
         return None
 
 
+def ncu_mc_traffic():
+    """DRAM bytes of the marching-cubes launches of one 512^3 extraction on the bench's octree field (committed ncu launch
+    list, profiles/ncu_traffic.json); None when there is none."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("marching_cubes")
+        return None if not d else {"bytes_per_extraction": d["dram_bytes_per_extraction"], "verts": d["verts"],
+                                   "faces": d["faces"], "source": d["source"]}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def build_problem():
     """Seeded random-init two-level net + band-limited feature maps (pifu_b200.synthetic)."""
     from pifu_b200 import synthetic as syn
@@ -350,6 +361,8 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3, cpu=None):
              "mc_roofline": {"bound": "hbm", "achieved": mc_bytes / (mc_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
                              "unit": "GB/s", "frac": mc_bytes / (mc_ms * 1e-3) / 1e9 / peaks["hbm"],
                              "algorithmic_bytes": mc_bytes,
+                             "traffic": (ncu_mc_traffic() or {}).get("bytes_per_extraction") if (mode == "octree" and res == 512) else None,
+                             "traffic_detail": ncu_mc_traffic() if (mode == "octree" and res == 512) else None,
                              "note": "4 B/voxel field + 40 B/vertex (f64 position, f32 normal, value) + 12 B/face; "
                                      "count + emit, includes the host sync that sizes the output"}}
         if mode == "octree" and mesh != -1:
