@@ -86,6 +86,8 @@ def test_save_obj_bytes_identical_to_reference_loop(tmp_path):
     c[:len(sp), 1] = np.abs(sp) % 1.0
     f = rng.integers(0, n, (3 * n, 3)).astype(np.int32)
     f[0] = [2 ** 31 - 2, 0, 5]
+    edges = [10 ** k + d for k in range(1, 10) for d in (-2, -1, 0)]   # every digit count of the 1-based index, both sides
+    f[1:1 + len(edges) // 3] = np.array(edges, dtype=np.int64).reshape(-1, 3).astype(np.int32)
     p = str(tmp_path / "native.obj")
     mesh_util.save_obj_mesh_with_color(p, v, f, c)
     ref = io.StringIO()
