@@ -137,3 +137,23 @@ def test_train_mode_batchnorm_batches_are_refused():
         BasePIFuNet.check_batch_statistics(m, 2)
     m.eval()
     BasePIFuNet.check_batch_statistics(m, 2)
+
+
+def test_save_obj_fixed4_property(tmp_path):
+    """Any double - subnormals, huge magnitudes, both zeros, values a few ulps around every kind of decimal tie - prints as
+    printf('%.4f') does (hypothesis draws the values; the library formats them as vertex coordinates)."""
+    from hypothesis import given, settings, strategies as st
+    path = str(tmp_path / "h.obj")
+    anyf = st.floats(allow_nan=False, allow_infinity=False, width=64)
+    near_tie = st.builds(lambda k, u, s: float(np.nextafter((2 * k + 1) / 20000.0 * s, np.inf if u > 0 else -np.inf)) if u else (2 * k + 1) / 20000.0 * s,
+                         st.integers(0, 10 ** 9), st.integers(-1, 1), st.sampled_from([1.0, -1.0, 1e-3, 16.0, 4096.0]))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.one_of(anyf, near_tie), min_size=6, max_size=600))
+    def run(vals):
+        n = len(vals) // 6
+        a = np.array(vals[:6 * n], dtype=np.float64).reshape(n, 6)
+        mesh_util.save_obj_mesh_with_color(path, a[:, :3].copy(), np.zeros((0, 3), np.int32), a[:, 3:].copy())
+        want = "".join('v %.4f %.4f %.4f %.4f %.4f %.4f\n' % tuple(r) for r in a)
+        assert open(path).read() == want
+    run()
