@@ -410,6 +410,23 @@ def mesh_latency(netMR, eng, calib, dev, res=512, reps=3, cpu=None):
                     kept = "none (%s)" % (str(e)[:80],)
                 t2 = time.perf_counter()
             d["postprocess"] = {"vertex_colors_ms": (t1 - t0) * 1e3, "meshcleaning_ms": (t2 - t1) * 1e3, "kept_verts_faces": kept}
+            # the reference's own form: meshcleaning(obj_path), OBJ file in, OBJ file out (`reconstruction.py:325-344`)
+            try:
+                import contextlib
+                import io
+                with tempfile.TemporaryDirectory() as tmp:
+                    path = os.path.join(tmp, "mesh.obj")
+                    mesh_util.save_obj_mesh_with_color(path, mv, mf, colors)
+                    t0 = time.perf_counter()
+                    lv, lf, lc = mesh_util.load_obj_mesh_with_color(path)
+                    t1 = time.perf_counter()
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        mesh_util.meshcleaning(path, device=dev)
+                    t2 = time.perf_counter()
+                d["postprocess"]["obj_read_ms"] = (t1 - t0) * 1e3
+                d["postprocess"]["meshcleaning_file_ms"] = (t2 - t1) * 1e3
+            except Exception as e:  # noqa: BLE001
+                d["postprocess"]["meshcleaning_file_ms"] = "failed (%s)" % (str(e)[:80],)
         if mode == "octree" and cpu is not None:
             d["vs_cpu"] = field_vs_cpu(field, stats, cpu)
         if mode == "octree":

@@ -209,6 +209,15 @@ int pifu_mc_extract(pifu_ctx* ctx, const float* field, int n0, int n1, int n2, d
 int pifu_write_obj(const char* path, const double* verts, const double* colors, long long nverts,
                    const int* faces, long long nfaces);
 
+/* Host-side OBJ reader, the inverse of pifu_write_obj: what meshcleaning (reconstruction.py:325-344, `trimesh.load`) needs
+ * of the file the pipeline wrote.  pifu_obj_counts: counts (HOST, 3 entries) = "v " lines, "f " lines, values on the first
+ * vertex line (3, or 6 with colours).  pifu_read_obj: verts [nverts][3], colors [nverts][3] or NULL, faces [nfaces][3]
+ * 0-based in the order they were GIVEN to the writer (the file stores f0, f2, f1); "a/b/c" references keep the vertex
+ * index; every other line is skipped.  -1 when the counts differ from the file's, a line is malformed, or colours are
+ * asked of a file without them. */
+int pifu_obj_counts(const char* path, long long* counts);
+int pifu_read_obj(const char* path, double* verts, double* colors, int* faces, long long nverts, long long nfaces);
+
 /* Element-wise helper of the PyTorch image encoders (no context): y = relu?((x - mean) / sqrt(var + eps) * weight
  * + bias) per channel, the eval-mode BatchNorm2d + ReLU pairs of Filter.py:23-69 in one pass.  x, y: device fp32
  * [N][C][HW] contiguous (y may alias x); statistics / affine parameters: device fp32 [C] (weight / bias may be null).

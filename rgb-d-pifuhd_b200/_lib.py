@@ -58,6 +58,8 @@ SIGNATURES = {
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, VP, VP, VP, VP, ctypes.c_longlong,
                                        ctypes.c_longlong, VP, VP]),
     "pifu_write_obj": (ctypes.c_int, [ctypes.c_char_p, VP, VP, ctypes.c_longlong, VP, ctypes.c_longlong]),
+    "pifu_obj_counts": (ctypes.c_int, [ctypes.c_char_p, VP]),
+    "pifu_read_obj": (ctypes.c_int, [ctypes.c_char_p, VP, VP, VP, ctypes.c_longlong, ctypes.c_longlong]),
     "pifu_bn_relu_f32": (ctypes.c_int, [VP, VP, VP, VP, VP, ctypes.c_double, ctypes.c_int, VP, ctypes.c_longlong,
                                         ctypes.c_int, ctypes.c_longlong, VP]),
     "pifu_cat3_add_f32": (ctypes.c_int, [VP, VP, VP, VP, VP, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
@@ -76,7 +78,7 @@ SIGNATURES = {
 }
 
 
-ABI_VERSION = 2          # pifu_abi_version() of the library these signatures describe
+ABI_VERSION = 3          # pifu_abi_version() of the library these signatures describe
 
 
 class PifuError(RuntimeError):

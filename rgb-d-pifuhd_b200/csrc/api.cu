@@ -932,7 +932,7 @@ McState*& ctx_mc(pifu_ctx* c) { return c->mc; }
 extern "C" {
 
 const char* pifu_last_error(void) { return g_error.c_str(); }
-int pifu_abi_version(void) { return 2; }
+int pifu_abi_version(void) { return 3; }
 
 int pifu_create(int device, pifu_ctx** out) {
     if (!out) { set_error("null out pointer"); return -1; }

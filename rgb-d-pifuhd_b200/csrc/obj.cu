@@ -17,6 +17,8 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "../../include/pifu_b200.h"
@@ -208,4 +210,219 @@ extern "C" int pifu_write_obj(const char* path, const double* verts, const doubl
         return -1;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// OBJ reader: the inverse of the writer, for `meshcleaning(obj_path)` (`reconstruction.py:325-344` loads the file the
+// pipeline wrote a moment ago; a per-line Python loop needs 2.5 s for the 1 M lines of a 512^3 mesh).  The file is
+// mapped, cut into per-thread segments at line starts, counted, then parsed in place:
+//   "v x y z [r g b]"  -> doubles (decimal fast path: up to 15 significant digits and 10^k <= 10^22 is one correctly
+//                         rounded division of two exact doubles; anything else goes through strtod)
+//   "f a[/..] b[/..] c[/..]" -> 0-based int32 (a, c, b): the order the faces had when they were GIVEN to the writer
+// Every other line is skipped, like the Python loop this replaces (`line.startswith("v ")` / `"f "`).
+namespace {
+
+struct Mapped {
+    const char* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    ~Mapped() {
+        if (p && n) munmap(const_cast<char*>(p), n);
+        if (fd >= 0) close(fd);
+    }
+    bool open_file(const char* path) {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return false;
+        n = static_cast<size_t>(st.st_size);
+        if (n == 0) return true;
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { n = 0; return false; }
+        p = static_cast<const char*>(m);
+        return true;
+    }
+};
+
+inline const char* line_end(const char* q, const char* e) {
+    const void* nl = memchr(q, '\n', static_cast<size_t>(e - q));
+    return nl ? static_cast<const char*>(nl) : e;
+}
+inline bool blank(char ch) { return ch == ' ' || ch == '\t' || ch == '\r'; }
+
+// one number of a vertex line starting at q (< le); advances q past it.  false: no number there
+inline bool parse_double(const char*& q, const char* le, double* out) {
+    static const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                   1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* s = q;
+    bool neg = false;
+    if (s < le && (*s == '-' || *s == '+')) { neg = *s == '-'; ++s; }
+    unsigned long long m = 0;
+    int digits = 0, frac = 0;
+    const char* d0 = s;
+    while (s < le && *s >= '0' && *s <= '9') { m = m * 10 + static_cast<unsigned>(*s - '0'); ++digits; ++s; }
+    if (s < le && *s == '.') {
+        ++s;
+        while (s < le && *s >= '0' && *s <= '9') { m = m * 10 + static_cast<unsigned>(*s - '0'); ++digits; ++frac; ++s; }
+    }
+    const bool plain = s > d0 && digits > 0 && (s == le || blank(*s));
+    if (plain && digits <= 15 && frac <= 22) {                   // (leading zeros only make `digits` pessimistic)
+        const double v = static_cast<double>(m) / P10[frac];
+        *out = neg ? -v : v;
+        q = s;
+        return true;
+    }
+    // exponents, inf / nan, long mantissas: libc, on a terminated copy of the token
+    const char* t = q;
+    while (t < le && !blank(*t)) ++t;
+    const size_t len = static_cast<size_t>(t - q);
+    if (len == 0 || len > 400) return false;
+    char buf[408];
+    memcpy(buf, q, len);
+    buf[len] = 0;
+    char* endp = nullptr;
+    const double v = strtod(buf, &endp);
+    if (endp != buf + len) return false;
+    *out = v;
+    q = t;
+    return true;
+}
+
+struct ObjCounts { long long nv = 0, nf = 0; int cols = 0; bool bad = false; };
+
+// phase 1 (count) or phase 2 (parse into the buffers); [b, e) starts at a line start
+void scan_segment(const char* b, const char* e, ObjCounts& cnt, bool parse, double* verts, double* colors, int* faces,
+                  long long v0, long long f0) {
+    long long iv = v0, jf = f0;
+    for (const char* q = b; q < e;) {
+        const char* le = line_end(q, e);
+        if (le - q >= 2 && q[0] == 'v' && q[1] == ' ') {
+            if (!parse) {
+                if (cnt.cols == 0) {                               // values on the first vertex line of the segment
+                    int k = 0;
+                    const char* s = q + 2;
+                    double tmp;
+                    for (;;) {
+                        while (s < le && blank(*s)) ++s;
+                        if (s >= le || !parse_double(s, le, &tmp)) break;
+                        ++k;
+                    }
+                    cnt.cols = k;
+                }
+                ++cnt.nv;
+            } else {
+                const char* s = q + 2;
+                double val[6] = {0, 0, 0, 0, 0, 0};
+                int k = 0;
+                for (; k < 6; ++k) {
+                    while (s < le && blank(*s)) ++s;
+                    if (s >= le || !parse_double(s, le, &val[k])) break;
+                }
+                if (k < 3 || (colors != nullptr && k < 6)) cnt.bad = true;
+                verts[3 * iv] = val[0]; verts[3 * iv + 1] = val[1]; verts[3 * iv + 2] = val[2];
+                if (colors) { colors[3 * iv] = val[3]; colors[3 * iv + 1] = val[4]; colors[3 * iv + 2] = val[5]; }
+                ++iv;
+            }
+        } else if (le - q >= 2 && q[0] == 'f' && q[1] == ' ') {
+            if (!parse) {
+                ++cnt.nf;
+            } else {
+                const char* s = q + 2;
+                long long idx[3] = {0, 0, 0};
+                int k = 0;
+                for (; k < 3; ++k) {
+                    while (s < le && blank(*s)) ++s;
+                    if (s >= le) break;
+                    bool neg = false;
+                    if (*s == '-') { neg = true; ++s; }
+                    const char* d0 = s;
+                    long long a = 0;
+                    while (s < le && *s >= '0' && *s <= '9') { a = a * 10 + (*s - '0'); ++s; }
+                    if (s == d0) break;
+                    idx[k] = neg ? -a : a;
+                    while (s < le && !blank(*s)) ++s;              // "/vt/vn" of the reference: ignored
+                }
+                if (k < 3) cnt.bad = true;
+                faces[3 * jf] = static_cast<int>(idx[0] - 1);
+                faces[3 * jf + 1] = static_cast<int>(idx[2] - 1);
+                faces[3 * jf + 2] = static_cast<int>(idx[1] - 1);
+                ++jf;
+            }
+        }
+        q = le < e ? le + 1 : e;
+    }
+}
+
+// segment s of T: starts at the first line start at or after s * n / T
+std::vector<const char*> segment_starts(const Mapped& m, int T) {
+    std::vector<const char*> st(static_cast<size_t>(T) + 1, m.p + m.n);
+    st[0] = m.p;
+    for (int s = 1; s < T; ++s) {
+        const char* q = m.p + m.n / static_cast<size_t>(T) * static_cast<size_t>(s);
+        if (q > m.p && q[-1] != '\n') { const char* le = line_end(q, m.p + m.n); q = le < m.p + m.n ? le + 1 : m.p + m.n; }
+        st[static_cast<size_t>(s)] = q;
+    }
+    for (int s = 1; s <= T; ++s)
+        if (st[static_cast<size_t>(s)] < st[static_cast<size_t>(s) - 1]) st[static_cast<size_t>(s)] = st[static_cast<size_t>(s) - 1];
+    return st;
+}
+
+int obj_threads(size_t bytes) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = static_cast<int>(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+    if (const char* env = getenv("PIFU_OBJ_THREADS")) { const int k = atoi(env); if (k >= 1 && k <= 64) n = k; }
+    const size_t by_size = bytes / (256 * 1024) + 1;               // small files: not worth the threads
+    return static_cast<int>(by_size < static_cast<size_t>(n) ? by_size : static_cast<size_t>(n));
+}
+
+template <typename F>
+void run_segments(int T, F&& body) {
+    std::vector<std::thread> pool;
+    for (int s = 1; s < T; ++s) pool.emplace_back([&, s]() { body(s); });
+    body(0);
+    for (auto& th : pool) th.join();
+}
+
+int obj_scan(const char* path, long long* counts, bool parse, double* verts, double* colors, int* faces, long long nverts,
+             long long nfaces) {
+    Mapped m;
+    if (!path || !m.open_file(path)) { pifu::set_error("cannot read %s", path ? path : "(null)"); return -1; }
+    const int T = obj_threads(m.n);
+    const std::vector<const char*> st = segment_starts(m, T);
+    std::vector<ObjCounts> cnt(static_cast<size_t>(T));
+    run_segments(T, [&](int s) { scan_segment(st[static_cast<size_t>(s)], st[static_cast<size_t>(s) + 1], cnt[static_cast<size_t>(s)], false, nullptr, nullptr, nullptr, 0, 0); });
+    long long nv = 0, nf = 0;
+    int cols = 0;
+    std::vector<long long> v0(static_cast<size_t>(T)), f0(static_cast<size_t>(T));
+    for (int s = 0; s < T; ++s) {
+        v0[static_cast<size_t>(s)] = nv; f0[static_cast<size_t>(s)] = nf;
+        nv += cnt[static_cast<size_t>(s)].nv; nf += cnt[static_cast<size_t>(s)].nf;
+        if (cols == 0) cols = cnt[static_cast<size_t>(s)].cols;
+    }
+    if (counts) { counts[0] = nv; counts[1] = nf; counts[2] = cols; }
+    if (!parse) return 0;
+    if (nv != nverts || nf != nfaces || (nv > 0 && !verts) || (nf > 0 && !faces)) {
+        pifu::set_error("%s holds %lld vertices and %lld faces, the buffers %lld and %lld", path, nv, nf, nverts, nfaces);
+        return -1;
+    }
+    if (colors && cols < 6) { pifu::set_error("%s has no vertex colours (%d values per vertex line)", path, cols); return -1; }
+    run_segments(T, [&](int s) {
+        scan_segment(st[static_cast<size_t>(s)], st[static_cast<size_t>(s) + 1], cnt[static_cast<size_t>(s)], true, verts, colors, faces,
+                     v0[static_cast<size_t>(s)], f0[static_cast<size_t>(s)]);
+    });
+    for (int s = 0; s < T; ++s)
+        if (cnt[static_cast<size_t>(s)].bad) { pifu::set_error("%s: malformed vertex or face line", path); return -1; }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pifu_obj_counts(const char* path, long long* counts) {
+    if (!counts) { pifu::set_error("bad arguments to pifu_obj_counts"); return -1; }
+    return obj_scan(path, counts, false, nullptr, nullptr, nullptr, 0, 0);
+}
+
+extern "C" int pifu_read_obj(const char* path, double* verts, double* colors, int* faces, long long nverts, long long nfaces) {
+    if (nverts < 0 || nfaces < 0) { pifu::set_error("bad arguments to pifu_read_obj"); return -1; }
+    return obj_scan(path, nullptr, true, verts, colors, faces, nverts, nfaces);
 }

@@ -157,3 +157,66 @@ def test_save_obj_fixed4_property(tmp_path):
         want = "".join('v %.4f %.4f %.4f %.4f %.4f %.4f\n' % tuple(r) for r in a)
         assert open(path).read() == want
     run()
+
+
+def _python_obj_loop(path):
+    """The per-line loop the native reader replaced (the checker here): 'v ' lines -> floats, 'f ' lines -> 0-based
+    (a, c, b) of the first three references."""
+    vs, fs = [], []
+    with open(path, newline="") as fh:
+        for line in fh:
+            if line.startswith("v "):
+                vs.append([float(x) for x in line.split()[1:]])
+            elif line.startswith("f "):
+                a, b, c = (int(x.split("/")[0]) - 1 for x in line.split()[1:4])
+                fs.append((a, c, b))
+    return vs, fs
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_load_obj_native_reader_matches_line_loop(tmp_path, monkeypatch, threads):
+    """pifu_obj_counts + pifu_read_obj against the Python loop, bit for bit: a written mesh (several segments per thread
+    count), then a hand-made file with comments, vn / vt lines, a/b/c references, CRLF, exponents, signed zeros, long
+    mantissas, no trailing newline."""
+    monkeypatch.setenv("PIFU_OBJ_THREADS", threads)
+    rng = np.random.default_rng(11)
+    n = 30000
+    v = rng.uniform(-300, 300, (n, 3)) * rng.choice([1.0, 1e-3, 1e3], (n, 1))
+    c = rng.uniform(0, 1, (n, 3))
+    f = rng.integers(0, n, (2 * n + 7, 3)).astype(np.int32)
+    p = str(tmp_path / "w.obj")
+    mesh_util.save_obj_mesh_with_color(p, v, f, c)
+    V, F, C = mesh_util.load_obj_mesh_with_color(p)
+    vs, fs = _python_obj_loop(p)
+    assert np.array_equal(np.hstack([V, C]), np.array(vs)) and np.array_equal(F, np.array(fs, dtype=np.int32))
+    assert np.array_equal(F, f)                                          # the order the writer was given
+    q = str(tmp_path / "hand.obj")
+    text = ("# a comment\r\nmtllib x.mtl\nv 1 2 3\nvn 0 0 1\nvt 0.5 0.5\n"
+            "v -0.0 1e-3 2.5E+2\r\nv 0.1234567890123456789 -123456789012345678901234.5 .5\n"
+            "v 7. +8 -9.000\nv inf -inf 1e400\n"
+            "f 1/1/1 2/2/2 3/3/3\nf 4//1 5//2 1//3\r\nf 1 2 3 4\ng grp\nf 5 4 3")          # no trailing newline
+    open(q, "w", newline="").write(text)
+    V, F, C = mesh_util.load_obj_mesh_with_color(q)
+    vs, fs = _python_obj_loop(q)
+    assert C is None and V.shape == (5, 3) and F.shape == (4, 3)
+    ref = np.array(vs)
+    assert np.array_equal(V, ref) and np.array_equal(np.signbit(V), np.signbit(ref))
+    assert np.array_equal(F, np.array(fs, dtype=np.int32))
+
+
+def test_load_obj_native_reader_edges(tmp_path):
+    from pifu_b200._lib import PifuError
+    e = str(tmp_path / "empty.obj")
+    open(e, "w").close()
+    V, F, C = mesh_util.load_obj_mesh_with_color(e)
+    assert V.shape == (0, 3) and F.shape == (0, 3) and C is None
+    with pytest.raises(PifuError):
+        mesh_util.load_obj_mesh_with_color(str(tmp_path / "missing.obj"))
+    b = str(tmp_path / "bad.obj")
+    open(b, "w").write("v 1 2 3\nv 1 x 3\nf 1 2 2\n")
+    with pytest.raises(PifuError):
+        mesh_util.load_obj_mesh_with_color(b)
+    b2 = str(tmp_path / "bad2.obj")
+    open(b2, "w").write("v 1 2 3 0 0 0\nv 1 2 3\nf 1 2\n")
+    with pytest.raises(PifuError):
+        mesh_util.load_obj_mesh_with_color(b2)
